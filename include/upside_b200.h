@@ -1,0 +1,79 @@
+/* Batched C ABI of the B200 engine (plain pointers and sizes, no C++/torch types).
+ *
+ * The reference runs one DerivEngine per OpenMP thread (src/main.cpp:618-667).  Here one engine holds a BATCH of
+ * n_replica copies of one configuration on one GPU and advances all of them per kernel launch.  These entry points
+ * are what a reference-side driver binds instead of looping over `System`s; each cites the reference code it
+ * replaces.  All functions return 0 on success, 1 on failure (message retrievable with ub_last_error, also printed to
+ * stderr), like the reference's engine_c_library.  Buffers are caller-owned, C-contiguous.
+ */
+#ifndef UPSIDE_B200_H
+#define UPSIDE_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct UbEngine UbEngine;
+
+const char* ub_last_error(void);
+int ub_device_count(void);
+
+/* initialize_engine_from_hdf5 for n_replica copies (src/deriv_engine.cpp:195-270, src/main.cpp:486-502).
+ * config_path: .up file; the potential is read from /input/potential, n_atom from /input/pos.  NULL on failure. */
+UbEngine* ub_engine_create(const char* config_path, int n_replica, int device);
+void ub_engine_destroy(UbEngine* e);
+int ub_n_atom(const UbEngine* e);
+int ub_n_replica(const UbEngine* e);
+
+/* /input/pos of the configuration, (n_atom,3) */
+int ub_initial_pos(UbEngine* e, float* pos);
+
+/* positions / momenta of all replicas, (n_replica,n_atom,3) */
+int ub_set_pos(UbEngine* e, const float* pos);
+int ub_get_pos(UbEngine* e, float* pos);
+int ub_set_mom(UbEngine* e, const float* mom);
+int ub_get_mom(UbEngine* e, float* mom);
+
+/* DerivEngine::compute(PotentialAndDerivMode) for every replica (src/deriv_engine.cpp:124-169):
+ * energy (n_replica) and/or deriv (n_replica,n_atom,3) may be NULL */
+int ub_evaluate(UbEngine* e, float* energy, float* deriv);
+
+/* per-node access for one replica (src/engine_c_library.cpp:112-194) */
+int ub_n_nodes(UbEngine* e);
+int ub_node_name(UbEngine* e, int index, char* buf, int buf_len, int* is_potential);
+int ub_get_output_dims(UbEngine* e, const char* node, int* n_elem, int* elem_width);
+int ub_get_output(UbEngine* e, const char* node, int replica, int n, float* out);
+int ub_get_sens(UbEngine* e, const char* node, int replica, int n, float* out);
+int ub_get_node_potential(UbEngine* e, const char* node, float* out /* n_replica */);
+int ub_get_value_by_name(UbEngine* e, const char* node, const char* log_name, int replica, int n, float* out, int* n_written);
+int ub_get_param(UbEngine* e, const char* node, int n, float* out, int* n_param);
+int ub_set_param(UbEngine* e, const char* node, int n, const float* param);
+
+/* pair list a node built in the last evaluation, in the reference's emission order
+ * (PairlistComputation::find_edges, src/interaction_graph.h:201-257); *n_edge receives the full count */
+int ub_get_pairlist(UbEngine* e, const char* node, int replica, int max_edge, int* i1, int* i2, int* n_edge);
+
+/* MD: System setup of src/main.cpp:515-523 (seed_r = base_seed + r, OU thermostat, initial thermalisation),
+ * then n_round x { thermostat every `thermostat_interval` rounds ; integration_cycle } (src/main.cpp:657-663,
+ * src/deriv_engine.cpp:172-192, src/thermostat.cpp:9-18).  temperature: (n_replica). */
+int ub_md_init(UbEngine* e, uint32_t base_seed, const float* temperature, float dt, float thermostat_timescale,
+               int thermostat_interval);
+int ub_md_set_temperature(UbEngine* e, const float* temperature);
+int ub_md_run(UbEngine* e, long n_round);      /* asynchronous; ub_sync waits and reports device-side failures */
+int ub_sync(UbEngine* e);
+int ub_recenter(UbEngine* e, int xy_only);     /* src/deriv_engine.cpp:37-48 */
+int ub_kinetic_energy(UbEngine* e, float* out /* n_replica, per atom */);
+
+/* CUDA stream the engine launches on (cudaStream_t), for timing with CUDA events on that stream */
+void* ub_stream(UbEngine* e);
+/* number of kernels the engine launches per evaluation / per MD round (for the bench's gpu_launches claim) */
+int ub_launches_per_eval(UbEngine* e);
+
+/* known-answer access to the device RNG (src/random.h:19-66): threefry bits, normal3 and u01(word0) */
+int ub_rng_probe(uint32_t seed, uint32_t stream, uint32_t atom, uint64_t timestep, uint32_t* bits4, float* normal3_u01);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

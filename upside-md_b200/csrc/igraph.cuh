@@ -1,0 +1,248 @@
+// InteractionGraph for the B200 engine - a gather-form, atomics-free re-design of the reference's
+// PairlistComputation + InteractionGraph (src/interaction_graph.h:31-557).
+//
+// Reference: one global edge list per graph (Verlet-cached, SSE left-packed), per-edge value/deriv arrays, a serial
+// scatter-add of edge_sensitivity*edge_deriv.  Here, per replica, the pair list is held as ELL neighbour tables
+//     nbr1[B][n1][K1] : for each element of group 1 the indices of its partners in group 2 (ascending)
+//     nbr2[B][n2][K2] : the transpose (for a symmetric graph a single full table is used for both)
+// built by one thread per element scanning shared-memory tiles of the other group.  Every consumer then works in
+// gather form - a small lane group per element walks its row, evaluates the pair term, and reduces with warp
+// shuffles - so forces need no atomics and are summed in a fixed order (bit-reproducible run to run).  Pair-term
+// derivatives are recomputed in the backward pass instead of being stored: at B200's flop:byte ratio ~300 flops is
+// cheaper than writing and re-reading 52 bytes per edge from HBM.
+//
+// The pair predicate is the reference's (pinned build): fp32, no FMA, ((dx*dx+dy*dy)+dz*dz) < cutoff^2 with
+// dx = pos1[i1]-pos2[i2], plus the interaction's id exclusion and, for symmetric graphs, i1<i2
+// (interaction_graph.h:122-158,223-244).  The reference's emission order is recovered on request by sorting.
+#pragma once
+#include "common.cuh"
+#include "engine.h"
+
+namespace ub {
+
+enum Exclusion { EXCL_NONE = 0, EXCL_ROTAMER = 1, EXCL_SEQ2 = 2, EXCL_SEQ1 = 3 };
+
+__device__ __forceinline__ bool acceptable_id_pair(int excl, int id1, int id2) {
+    switch (excl) {
+        case EXCL_ROTAMER: return (((unsigned)id1) >> 4) != (((unsigned)id2) >> 4);   // bead_interaction.h:195-197
+        case EXCL_SEQ2: return (id1 - id2 > 2) || (id2 - id1 > 2);                     // hbond.cpp:254-259
+        case EXCL_SEQ1: return (id1 - id2 > 1) || (id2 - id1 > 1);                     // backbone_steric.cpp:32-35
+        default: return true;
+    }
+}
+
+struct IGraphSide {
+    const float* out;   // node output [B][n_node][wp]
+    float* sens;
+    int n_node, wp;
+    const int *loc, *type, *id;   // per element of the group
+    int n;
+};
+
+struct IGraphDev {
+    IGraphSide s1, s2;
+    const float* param;   // [n_type1][n_type2][n_param]
+    int n_type1, n_type2, n_param;
+    float cutoff, cutoff2;
+    int symmetric, excl;
+    unsigned short* nbr1; int* cnt1; int K1;
+    unsigned short* nbr2; int* cnt2; int K2;
+    int* error_flag;
+};
+
+// Build the ELL rows of group A against group B.  grid (ceil(nA/TILE), B), block TILE.
+template <int TILE>
+__global__ void k_pairlist(IGraphSide A, IGraphSide Bs, unsigned short* __restrict__ nbr, int* __restrict__ cnt, int K,
+                           float cutoff2, int excl, int same_group, int a_is_first, int* error_flag) {
+    __shared__ float4 tile[TILE];   // x,y,z, id (bit-cast)
+    int r = blockIdx.y;
+    int i = blockIdx.x * TILE + threadIdx.x;
+    bool active = i < A.n;
+    float xi = 0.f, yi = 0.f, zi = 0.f;
+    int idi = 0;
+    if (active) {
+        const float* p = A.out + (size_t(r) * A.n_node + A.loc[i]) * A.wp;
+        xi = p[0]; yi = p[1]; zi = p[2];
+        idi = A.id[i];
+    }
+    int n = 0;
+    unsigned short* row = nbr + (size_t(r) * A.n + (active ? i : 0)) * K;
+    for (int j0 = 0; j0 < Bs.n; j0 += TILE) {
+        int j = j0 + threadIdx.x;
+        __syncthreads();
+        if (j < Bs.n) {
+            const float* p = Bs.out + (size_t(r) * Bs.n_node + Bs.loc[j]) * Bs.wp;
+            tile[threadIdx.x] = make_float4(p[0], p[1], p[2], __int_as_float(Bs.id[j]));
+        }
+        __syncthreads();
+        if (!active) continue;
+        int jn = min(TILE, Bs.n - j0);
+        for (int jj = 0; jj < jn; ++jj) {
+            float4 t = tile[jj];
+            // pos1 - pos2 with group 1 first, as in the reference refine step; squares make the order immaterial
+            float dx = a_is_first ? xi - t.x : t.x - xi;
+            float dy = a_is_first ? yi - t.y : t.y - yi;
+            float dz = a_is_first ? zi - t.z : t.z - zi;
+            float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+            bool hit = d2 < cutoff2 && acceptable_id_pair(excl, idi, __float_as_int(t.w)) && !(same_group && (j0 + jj) == i);
+            if (hit) {
+                if (n < K) row[n] = (unsigned short)(j0 + jj);
+                ++n;
+            }
+        }
+    }
+    if (active) {
+        if (n > K) { atomicExch(error_flag, 1); n = K; }
+        cnt[size_t(r) * A.n + i] = n;
+    }
+}
+
+// ---- element loads ------------------------------------------------------------------------------------
+__device__ __forceinline__ const float* elem_ptr(const IGraphSide& s, int r, int e) {
+    return s.out + (size_t(r) * s.n_node + s.loc[e]) * s.wp;
+}
+__device__ __forceinline__ float* elem_sens_ptr(const IGraphSide& s, int r, int e) {
+    return s.sens + (size_t(r) * s.n_node + s.loc[e]) * s.wp;
+}
+__device__ __forceinline__ void load8(const float* p, float* x) {   // rows are 32-byte aligned when wp == 8
+    float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
+    x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+}
+
+// ---- pair terms ---------------------------------------------------------------------------------------
+// quadspline: V = wide(r) + ang1(cos1)*ang2(cos2)*narrow(r); reference bead_interaction.h:30-84.
+// x1,x2: (pos, unit direction).  Outputs: value, d/dx1[0..5], d/dx2[0..5].
+struct QuadSplineShape { int nka, nk; float inv_dtheta, inv_dx; };
+
+__device__ __forceinline__ float quadspline_edge(const float* __restrict__ p, const QuadSplineShape& q, const float* x1,
+                                                 const float* x2, float* d1, float* d2) {
+    f3 displace = mk3(x2[0] - x1[0], x2[1] - x1[1], x2[2] - x1[2]);
+    f3 rvec1 = mk3(x1[3], x1[4], x1[5]), rvec2 = mk3(x2[3], x2[4], x2[5]);
+    float dist2 = mag2(displace);
+    float inv_dist = rsqrtf(dist2);
+    float dist_coord = dist2 * (inv_dist * q.inv_dx);
+    f3 u = inv_dist * displace;
+    float cos1 = dot(rvec1, u), cos2 = -dot(rvec2, u);
+    float a1v, a1d, a2v, a2d, wv, wd, nv, nd;
+    deboor_vd(p, q.nka, (cos1 + 1.f) * q.inv_dtheta + 1.f, a1v, a1d);
+    deboor_vd(p + q.nka, q.nka, (cos2 + 1.f) * q.inv_dtheta + 1.f, a2v, a2d);
+    clamped_deboor_vd(p + 2 * q.nka, q.nk, dist_coord, wv, wd);
+    clamped_deboor_vd(p + 2 * q.nka + q.nk, q.nk, dist_coord, nv, nd);
+    float angular_weight = a1v * a2v;
+    float radial_deriv = q.inv_dx * (wd + angular_weight * nd);
+    float ang_d1 = q.inv_dtheta * a1d * a2v * nv;
+    float ang_d2 = q.inv_dtheta * a1v * a2d * nv;
+    f3 rXX = ang_d1 * rvec1 - ang_d2 * rvec2;
+    f3 deriv_dir = inv_dist * (rXX - dot(u, rXX) * u);
+    f3 d_displace = radial_deriv * u + deriv_dir;
+    d1[0] = -d_displace.x; d1[1] = -d_displace.y; d1[2] = -d_displace.z;
+    d1[3] = ang_d1 * u.x;  d1[4] = ang_d1 * u.y;  d1[5] = ang_d1 * u.z;
+    d2[0] = d_displace.x;  d2[1] = d_displace.y;  d2[2] = d_displace.z;
+    d2[3] = -ang_d2 * u.x; d2[4] = -ang_d2 * u.y; d2[5] = -ang_d2 * u.z;
+    return wv + angular_weight * nv;
+}
+
+// HBondCoverageInteraction (hbond.cpp:241-286): quadspline scaled by (1-hb)^2, hb = x1[6]; d1 has 7 components
+__device__ __forceinline__ float hbond_coverage_edge(const float* __restrict__ p, const QuadSplineShape& q, const float* x1,
+                                                     const float* x2, float* d1, float* d2) {
+    float cov = quadspline_edge(p, q, x1, x2, d1, d2);
+    float one_m = 1.f - x1[6];
+    float pre = one_m * one_m;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { d1[k] *= pre; d2[k] *= pre; }
+    d1[6] = -cov * one_m * 2.f;
+    return pre * cov;
+}
+
+// ProteinHBondInteraction (hbond.cpp:152-238).  x1 = (H, rHN), x2 = (O, rOC); returns -log(1-hb) and its derivatives.
+// The reference evaluates the angular gate per group of four SIMD lanes (an edge that fails the gate still gets the
+// ~1e-6 sigmoid tail when a lane-mate passes); here the gate is per edge, a difference far below tolerance.
+__device__ __forceinline__ float protein_hbond_edge(const float* __restrict__ p, const float* x1, const float* x2, float* d1,
+                                                    float* d2) {
+    f3 H = mk3(x1[0], x1[1], x1[2]), O = mk3(x2[0], x2[1], x2[2]);
+    f3 rHN = mk3(x1[3], x1[4], x1[5]), rOC = mk3(x2[3], x2[4], x2[5]);
+    f3 HO = H - O;
+    float m2 = mag2(HO) + 1e-6f;
+    float inv = rsqrtf(m2);
+    float mHO = m2 * inv;
+    f3 rHO = inv * HO;
+    float dotHOC = dot(rHO, rOC), dotOHN = -dot(rHO, rHN);
+    f3 dH = mk3(0.f, 0.f, 0.f), drHN = dH, drOC = dH;
+    float hb = 0.f;
+    if (dotHOC > 0.f && dotOHN > 0.f) {
+        float p0 = __ldg(p), p1 = __ldg(p + 1), p2 = __ldg(p + 2), p3 = __ldg(p + 3), p4 = __ldg(p + 4), p5 = __ldg(p + 5);
+        float ov, od, iv, id_;
+        sigmoid_vd((p2 - mHO) * p3, ov, od);   // outer
+        sigmoid_vd((mHO - p0) * p1, iv, id_);  // inner
+        float rad = ov * iv, rad_d = -p3 * od * iv + p1 * id_ * ov;
+        float a1v, a1d, a2v, a2d;
+        sigmoid_vd((dotHOC - p4) * p5, a1v, a1d); a1d *= p5;
+        sigmoid_vd((dotOHN - p4) * p5, a2v, a2d); a2d *= p5;
+        hb = rad * a1v * a2v;
+        float c0 = rad_d * a1v * a2v, c1 = rad * a1d * a2v, c2 = -rad * a1v * a2d;
+        drOC = c1 * rHO;
+        drHN = c2 * rHO;
+        dH = c0 * rHO + (c1 * inv) * (rOC - dotHOC * rHO) + (c2 * inv) * (rHN + dotOHN * rHO);
+    }
+    float hb_log = (hb >= 1.f) ? 100.f : -logf(1.f - hb);
+    float pre = fminf(1.f / (1.f - hb), 1e5f);
+    d1[0] = dH.x * pre; d1[1] = dH.y * pre; d1[2] = dH.z * pre;
+    d1[3] = drHN.x * pre; d1[4] = drHN.y * pre; d1[5] = drHN.z * pre;
+    d2[0] = -dH.x * pre; d2[1] = -dH.y * pre; d2[2] = -dH.z * pre;
+    d2[3] = drOC.x * pre; d2[4] = drOC.y * pre; d2[5] = drOC.z * pre;
+    return hb_log;
+}
+
+// EnvironmentCoverageInteraction (environment.cpp:12-68).  x1 = (CB pos, dir), x2 = (bead pos, weight);
+// d1 has 6 components, d2 has 4.
+__device__ __forceinline__ float environment_edge(const float* __restrict__ p, const float* x1, const float* x2, float* d1,
+                                                  float* d2) {
+    f3 displace = mk3(x2[0] - x1[0], x2[1] - x1[1], x2[2] - x1[2]);
+    f3 rvec1 = mk3(x1[3], x1[4], x1[5]);
+    float prob = x2[3];
+    float dist2 = mag2(displace);
+    float inv_dist = rsqrtf(dist2);
+    float dist = dist2 * inv_dist;
+    f3 u = inv_dist * displace;
+    float r0 = __ldg(p), r_sharp = __ldg(p + 1), dot0 = __ldg(p + 2), dot_sharp = __ldg(p + 3);
+    float dp = dot(u, rvec1);
+    float rv, rd, av, ad;
+    compact_sigmoid(dist - r0, r_sharp, rv, rd);
+    compact_sigmoid(dot0 - dp, dot_sharp, av, ad);
+    f3 d_displace = prob * ((rd * av) * u - (rv * ad * inv_dist) * (rvec1 - dp * u));
+    float s = -prob * rv * ad;
+    d1[0] = -d_displace.x; d1[1] = -d_displace.y; d1[2] = -d_displace.z;
+    d1[3] = s * u.x; d1[4] = s * u.y; d1[5] = s * u.z;
+    d2[0] = d_displace.x; d2[1] = d_displace.y; d2[2] = d_displace.z;
+    float score = rv * av;
+    d2[3] = score;
+    return prob * score;
+}
+
+// ---- host side --------------------------------------------------------------------------------------------
+struct IGraphHost {
+    bool symmetric;
+    int excl;
+    CoordNode *node1, *node2;
+    int n1, n2, n_type1, n_type2, n_param;
+    float cutoff;
+    std::vector<int> loc1, loc2, type1, type2, id1, id2;
+    std::vector<float> h_param;
+    DevBuf<int> d_loc1, d_loc2, d_type1, d_type2, d_id1, d_id2;
+    DevBuf<float> d_param;
+    DevBuf<unsigned short> nbr1, nbr2;
+    DevBuf<int> cnt1, cnt2;
+    int K1 = 0, K2 = 0;
+    Engine* engine = nullptr;
+
+    // reads index/type/id(+1/2) and interaction_param (n_type1,n_type2,n_param): interaction_graph.h:305-381
+    IGraphHost(const h5l::Node& grp, bool symmetric_, int excl_, int n_dim1, int n_dim2, CoordNode* p1, CoordNode* p2);
+    void allocate(Engine* e);          // after cutoff is known
+    IGraphDev dev() const;
+    void build(cudaStream_t s);        // enqueue the pair-list kernels
+    std::vector<float> count_edges_by_type(int replica);
+    bool pairlist(int replica, std::vector<int>& i1, std::vector<int>& i2);
+    void set_param(const std::vector<float>& p);
+};
+
+}  // namespace ub

@@ -1,0 +1,466 @@
+// InteractionGraph host side + the three pair-term coordinate nodes that are plain sums over edges:
+// protein_hbond (hbond.cpp:290-368), hbond_coverage (hbond.cpp:371-414), environment_coverage
+// (environment.cpp:71-109).  All kernels are gather-form over the ELL neighbour tables of igraph.cuh.
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+
+#include "igraph.cuh"
+
+namespace ub {
+
+// ================================================================================================ IGraphHost
+static int neighbor_capacity(float cutoff, int n_other) {
+    double scale = 1.0;
+    if (const char* s = getenv("UPSIDE_B200_NEIGHBOR_SCALE")) scale = std::max(0.05, atof(s));
+    double k = scale * (8. + 0.55 * double(cutoff) * cutoff * cutoff);
+    int K = (int)std::min<double>(n_other, std::ceil(k));
+    return std::max(K, 1);
+}
+
+IGraphHost::IGraphHost(const h5l::Node& grp, bool symmetric_, int excl_, int n_dim1, int n_dim2, CoordNode* p1, CoordNode* p2)
+    : symmetric(symmetric_), excl(excl_), node1(p1), node2(symmetric_ ? p1 : p2) {
+    if (!(symmetric ^ bool(p2))) throw std::string("second node must be null iff symmetric interaction");
+    auto sfx = [&](const char* b) { return std::string(b) + (symmetric ? "" : "1"); };
+    n1 = (int)h5_dims(grp, sfx("index"), 1)[0];
+    n2 = symmetric ? n1 : (int)h5_dims(grp, "index2", 1)[0];
+    auto pd = h5_dims(grp, "interaction_param", 3);
+    n_type1 = (int)pd[0]; n_type2 = (int)pd[1]; n_param = (int)pd[2];
+    check_elem_width_lower_bound(*node1, n_dim1);
+    if (!symmetric) check_elem_width_lower_bound(*node2, n_dim2);
+    if (n1 >= 65536 || n2 >= 65536) throw std::string("interaction graph groups are limited to 65535 elements");
+    h_param = h5_read<float>(grp, "interaction_param");
+    h5_check_size(grp, sfx("type"), {(uint64_t)n1});
+    h5_check_size(grp, sfx("id"), {(uint64_t)n1});
+    loc1 = h5_read<int>(grp, sfx("index"));
+    type1 = h5_read<int>(grp, sfx("type"));
+    id1 = h5_read<int>(grp, sfx("id"));
+    if (!symmetric) {
+        h5_check_size(grp, "type2", {(uint64_t)n2});
+        h5_check_size(grp, "id2", {(uint64_t)n2});
+        loc2 = h5_read<int>(grp, "index2");
+        type2 = h5_read<int>(grp, "type2");
+        id2 = h5_read<int>(grp, "id2");
+    } else { loc2 = loc1; type2 = type1; id2 = id1; }
+    for (int v : loc1) if (v < 0 || v >= node1->n_elem) throw std::string("index out of range for first interaction group");
+    for (int v : loc2) if (v < 0 || v >= node2->n_elem) throw std::string("index out of range for second interaction group");
+    for (int v : type1) if (v < 0 || v >= n_type1) throw std::string("type out of range for first interaction group");
+    for (int v : type2) if (v < 0 || v >= n_type2) throw std::string("type out of range for second interaction group");
+    d_loc1.upload(loc1); d_type1.upload(type1); d_id1.upload(id1);
+    d_loc2.upload(loc2); d_type2.upload(type2); d_id2.upload(id2);
+    d_param.upload(h_param);
+}
+
+void IGraphHost::allocate(Engine* e) {
+    engine = e;
+    K1 = neighbor_capacity(cutoff, n2);
+    K2 = symmetric ? K1 : neighbor_capacity(cutoff, n1);
+    nbr1.alloc(size_t(e->n_rep) * n1 * K1);
+    cnt1.alloc(size_t(e->n_rep) * n1);
+    if (!symmetric) {
+        nbr2.alloc(size_t(e->n_rep) * n2 * K2);
+        cnt2.alloc(size_t(e->n_rep) * n2);
+    }
+}
+
+IGraphDev IGraphHost::dev() const {
+    IGraphDev d;
+    d.s1 = IGraphSide{node1->output, node1->sens, node1->n_elem, node1->wp, d_loc1.p, d_type1.p, d_id1.p, n1};
+    d.s2 = IGraphSide{node2->output, node2->sens, node2->n_elem, node2->wp, d_loc2.p, d_type2.p, d_id2.p, n2};
+    d.param = d_param.p;
+    d.n_type1 = n_type1; d.n_type2 = n_type2; d.n_param = n_param;
+    d.cutoff = cutoff; d.cutoff2 = cutoff * cutoff;
+    d.symmetric = symmetric; d.excl = excl;
+    d.nbr1 = nbr1.p; d.cnt1 = cnt1.p; d.K1 = K1;
+    d.nbr2 = symmetric ? nbr1.p : nbr2.p; d.cnt2 = symmetric ? cnt1.p : cnt2.p; d.K2 = symmetric ? K1 : K2;
+    d.error_flag = engine->error_flag.p;
+    return d;
+}
+
+void IGraphHost::build(cudaStream_t s) {
+    IGraphDev d = dev();
+    constexpr int TILE = 128;
+    if (!n1 || !n2) return;
+    k_pairlist<TILE><<<dim3((n1 + TILE - 1) / TILE, engine->n_rep), TILE, 0, s>>>(d.s1, d.s2, d.nbr1, d.cnt1, d.K1, d.cutoff2,
+                                                                                   d.excl, symmetric, 1, d.error_flag);
+    if (!symmetric)
+        k_pairlist<TILE><<<dim3((n2 + TILE - 1) / TILE, engine->n_rep), TILE, 0, s>>>(d.s2, d.s1, d.nbr2, d.cnt2, d.K2,
+                                                                                       d.cutoff2, d.excl, 0, 0, d.error_flag);
+}
+
+bool IGraphHost::pairlist(int replica, std::vector<int>& i1, std::vector<int>& i2) {
+    if (replica < 0 || replica >= engine->n_rep) throw std::string("replica out of range");
+    engine->sync_and_check();
+    std::vector<unsigned short> rows(size_t(n1) * K1);
+    std::vector<int> cnt(n1);
+    UB_CUDA(cudaMemcpy(rows.data(), nbr1.p + size_t(replica) * n1 * K1, rows.size() * sizeof(unsigned short), cudaMemcpyDeviceToHost));
+    UB_CUDA(cudaMemcpy(cnt.data(), cnt1.p + size_t(replica) * n1, cnt.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    i1.clear();
+    i2.clear();
+    for (int i = 0; i < n1; ++i)
+        for (int k = 0; k < cnt[i]; ++k) {
+            int j = rows[size_t(i) * K1 + k];
+            if (symmetric && !(i < j)) continue;   // the reference keeps i1<i2 only (interaction_graph.h:142-144)
+            i1.push_back(i);
+            i2.push_back(j);
+        }
+    sort_reference_order(i1, i2);
+    return true;
+}
+
+std::vector<float> IGraphHost::count_edges_by_type(int replica) {
+    std::vector<int> i1, i2;
+    pairlist(replica, i1, i2);
+    std::vector<float> ret(size_t(n_type1) * n_type2, 0.f);
+    for (size_t e = 0; e < i1.size(); ++e) ret[type1[i1[e]] * n_type2 + type2[i2[e]]] += 1.f;
+    return ret;
+}
+
+void IGraphHost::set_param(const std::vector<float>& p) {
+    if (p.size() != h_param.size())
+        throw "Bad param size, got " + std::to_string(p.size()) + " params, but expected " + std::to_string(h_param.size()) +
+            " params of shape (" + std::to_string(n_type1) + ", " + std::to_string(n_type2) + ", " + std::to_string(n_param) + ")";
+    h_param = p;
+    d_param.upload(h_param);
+}
+
+namespace {
+
+constexpr int TPB = 128;
+constexpr int G = 8;   // lanes cooperating on one element's neighbour row
+inline dim3 group_grid(int n_elem, int n_rep) { return dim3((n_elem * G + TPB - 1) / TPB, n_rep); }
+
+// ================================================================================================ ProteinHBond
+__global__ void k_protein_hbond(IGraphDev g, const float* __restrict__ infer, float* __restrict__ out, int n_donor, int n_virtual) {
+    int r = blockIdx.y;
+    int e = (blockIdx.x * blockDim.x + threadIdx.x) / G, lane = threadIdx.x % G;
+    bool active = e < n_virtual;
+    float acc = 0.f;
+    float xs[8];
+    if (active) {
+        bool donor = e < n_donor;
+        int me = donor ? e : e - n_donor;
+        const IGraphSide& mine = donor ? g.s1 : g.s2;
+        const IGraphSide& other = donor ? g.s2 : g.s1;
+        load8(elem_ptr(mine, r, me), xs);
+        const unsigned short* row = donor ? g.nbr1 + (size_t(r) * g.s1.n + me) * g.K1 : g.nbr2 + (size_t(r) * g.s2.n + me) * g.K2;
+        int cnt = donor ? g.cnt1[size_t(r) * g.s1.n + me] : g.cnt2[size_t(r) * g.s2.n + me];
+        for (int k = lane; k < cnt; k += G) {
+            int o = row[k];
+            float xo[8], d1[6], d2[6];
+            load8(elem_ptr(other, r, o), xo);
+            acc += donor ? protein_hbond_edge(g.param, xs, xo, d1, d2) : protein_hbond_edge(g.param, xo, xs, d1, d2);
+        }
+    }
+    acc = group_sum<G>(acc);
+    if (active && lane == 0) {
+        const float* src = infer + (size_t(r) * n_virtual + e) * 8;
+        float* o = out + (size_t(r) * n_virtual + e) * 8;
+        float4 a = reinterpret_cast<const float4*>(src)[0], b = reinterpret_cast<const float4*>(src)[1];
+        reinterpret_cast<float4*>(o)[0] = a;
+        reinterpret_cast<float4*>(o)[1] = make_float4(b.x, b.y, 1.f - expf(-acc), 0.f);
+    }
+}
+__global__ void k_protein_hbond_deriv(IGraphDev g, const float* __restrict__ out, const float* __restrict__ sens, int n_donor,
+                                      int n_virtual) {
+    int r = blockIdx.y;
+    int e = (blockIdx.x * blockDim.x + threadIdx.x) / G, lane = threadIdx.x % G;
+    bool active = e < n_virtual;
+    float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    bool donor = e < n_donor;
+    int me = donor ? e : e - n_donor;
+    if (active) {
+        const IGraphSide& mine = donor ? g.s1 : g.s2;
+        const IGraphSide& other = donor ? g.s2 : g.s1;
+        float xs[8];
+        load8(elem_ptr(mine, r, me), xs);
+        const float* o_me = out + (size_t(r) * n_virtual + e) * 8;
+        const float* s_me = sens + (size_t(r) * n_virtual + e) * 8;
+        float ss_me = s_me[6] * (1.f - o_me[6]);
+        const unsigned short* row = donor ? g.nbr1 + (size_t(r) * g.s1.n + me) * g.K1 : g.nbr2 + (size_t(r) * g.s2.n + me) * g.K2;
+        int cnt = donor ? g.cnt1[size_t(r) * g.s1.n + me] : g.cnt2[size_t(r) * g.s2.n + me];
+        for (int k = lane; k < cnt; k += G) {
+            int o = row[k];
+            int eo = donor ? n_donor + o : o;
+            float ss_o = sens[(size_t(r) * n_virtual + eo) * 8 + 6] * (1.f - out[(size_t(r) * n_virtual + eo) * 8 + 6]);
+            float es = ss_me + ss_o;
+            float xo[8], d1[6], d2[6];
+            load8(elem_ptr(other, r, o), xo);
+            if (donor) protein_hbond_edge(g.param, xs, xo, d1, d2); else protein_hbond_edge(g.param, xo, xs, d1, d2);
+            const float* d = donor ? d1 : d2;
+#pragma unroll
+            for (int c = 0; c < 6; ++c) acc[c] += es * d[c];
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 6; ++c) acc[c] = group_sum<G>(acc[c]);
+    if (active && lane == 0) {
+        const IGraphSide& mine = donor ? g.s1 : g.s2;
+        const float* s_me = sens + (size_t(r) * n_virtual + e) * 8;
+        float* dst = elem_sens_ptr(mine, r, me);
+#pragma unroll
+        for (int c = 0; c < 6; ++c) dst[c] += acc[c] + s_me[c];   // + pass-through of the six copied components
+    }
+}
+struct ProteinHBond : CoordNode {
+    CoordNode& infer;
+    IGraphHost ig;
+    int n_donor, n_acceptor, n_virtual;
+    ProteinHBond(Engine&, const h5l::Node& g, CoordNode& infer_)
+        : CoordNode((int)(h5_dims(g, "index1", 1)[0] + h5_dims(g, "index2", 1)[0]), 7), infer(infer_),
+          ig(g, false, EXCL_NONE, 6, 6, &infer_, &infer_) {
+        if (ig.n_param != 8) throw std::string("protein_hbond expects 8 interaction parameters");
+        n_donor = ig.n1; n_acceptor = ig.n2; n_virtual = n_donor + n_acceptor;
+        if (n_virtual != infer.n_elem) throw std::string("protein_hbond expects one element per virtual site");
+        ig.cutoff = sqrtf(3.5f * 3.5f);   // hbond.cpp:124,158-160
+    }
+    void finalize() override { ig.allocate(engine); }
+    void compute_value(cudaStream_t s, ComputeMode) override {
+        if (!n_virtual) return;
+        ig.build(s);
+        k_protein_hbond<<<group_grid(n_virtual, engine->n_rep), TPB, 0, s>>>(ig.dev(), infer.output, output, n_donor, n_virtual);
+    }
+    void propagate_deriv(cudaStream_t s) override {
+        if (!n_virtual) return;
+        k_protein_hbond_deriv<<<group_grid(n_virtual, engine->n_rep), TPB, 0, s>>>(ig.dev(), output, sens, n_donor, n_virtual);
+    }
+    bool get_pairlist(int replica, std::vector<int>& i1, std::vector<int>& i2) override { return ig.pairlist(replica, i1, i2); }
+    std::vector<float> get_param() const override { return ig.h_param; }
+    void set_param(const std::vector<float>& p) override { ig.set_param(p); }
+};
+RegisterNodeType<ProteinHBond, 1> protein_hbond_node("protein_hbond");
+
+// ================================================================================================ HBondCoverage
+// forward: per bead (group 2) sum of the coverage of every H/O site (group 1) in range
+__global__ void k_hbond_coverage(IGraphDev g, QuadSplineShape q, float* __restrict__ out) {
+    int r = blockIdx.y;
+    int j = (blockIdx.x * blockDim.x + threadIdx.x) / G, lane = threadIdx.x % G;
+    bool active = j < g.s2.n;
+    float acc = 0.f;
+    if (active) {
+        float x2[8];
+        load8(elem_ptr(g.s2, r, j), x2);
+        int t2 = g.s2.type[j];
+        const unsigned short* row = g.nbr2 + (size_t(r) * g.s2.n + j) * g.K2;
+        int cnt = g.cnt2[size_t(r) * g.s2.n + j];
+        for (int k = lane; k < cnt; k += G) {
+            int i = row[k];
+            float x1[8], d1[7], d2[6];
+            load8(elem_ptr(g.s1, r, i), x1);
+            acc += hbond_coverage_edge(g.param + (size_t(g.s1.type[i]) * g.n_type2 + t2) * g.n_param, q, x1, x2, d1, d2);
+        }
+    }
+    acc = group_sum<G>(acc);
+    if (active && lane == 0) out[size_t(r) * g.s2.n + j] = acc;
+}
+// backward, bead side: sens[j] * sum_i dV/d(bead j)
+__global__ void k_hbond_coverage_deriv2(IGraphDev g, QuadSplineShape q, const float* __restrict__ sens) {
+    int r = blockIdx.y;
+    int j = (blockIdx.x * blockDim.x + threadIdx.x) / G, lane = threadIdx.x % G;
+    bool active = j < g.s2.n;
+    float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float sj = 0.f;
+    if (active) {
+        sj = sens[size_t(r) * g.s2.n + j];
+        float x2[8];
+        load8(elem_ptr(g.s2, r, j), x2);
+        int t2 = g.s2.type[j];
+        const unsigned short* row = g.nbr2 + (size_t(r) * g.s2.n + j) * g.K2;
+        int cnt = (sj != 0.f) ? g.cnt2[size_t(r) * g.s2.n + j] : 0;
+        for (int k = lane; k < cnt; k += G) {
+            int i = row[k];
+            float x1[8], d1[7], d2[6];
+            load8(elem_ptr(g.s1, r, i), x1);
+            hbond_coverage_edge(g.param + (size_t(g.s1.type[i]) * g.n_type2 + t2) * g.n_param, q, x1, x2, d1, d2);
+#pragma unroll
+            for (int c = 0; c < 6; ++c) acc[c] += d2[c];
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 6; ++c) acc[c] = group_sum<G>(acc[c]);
+    if (active && lane == 0) {
+        float* dst = elem_sens_ptr(g.s2, r, j);
+#pragma unroll
+        for (int c = 0; c < 6; ++c) dst[c] += sj * acc[c];
+    }
+}
+// backward, site side: sum_j sens[j] * dV/d(site i)   (7 components, the last is d/d hb)
+__global__ void k_hbond_coverage_deriv1(IGraphDev g, QuadSplineShape q, const float* __restrict__ sens) {
+    int r = blockIdx.y;
+    int i = (blockIdx.x * blockDim.x + threadIdx.x) / G, lane = threadIdx.x % G;
+    bool active = i < g.s1.n;
+    float acc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (active) {
+        float x1[8];
+        load8(elem_ptr(g.s1, r, i), x1);
+        int t1 = g.s1.type[i];
+        const unsigned short* row = g.nbr1 + (size_t(r) * g.s1.n + i) * g.K1;
+        int cnt = g.cnt1[size_t(r) * g.s1.n + i];
+        for (int k = lane; k < cnt; k += G) {
+            int j = row[k];
+            float sj = sens[size_t(r) * g.s2.n + j];
+            float x2[8], d1[7], d2[6];
+            load8(elem_ptr(g.s2, r, j), x2);
+            hbond_coverage_edge(g.param + (size_t(t1) * g.n_type2 + g.s2.type[j]) * g.n_param, q, x1, x2, d1, d2);
+#pragma unroll
+            for (int c = 0; c < 7; ++c) acc[c] += sj * d1[c];
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 7; ++c) acc[c] = group_sum<G>(acc[c]);
+    if (active && lane == 0) {
+        float* dst = elem_sens_ptr(g.s1, r, i);
+#pragma unroll
+        for (int c = 0; c < 7; ++c) dst[c] += acc[c];
+    }
+}
+struct HBondCoverage : CoordNode {
+    IGraphHost ig;
+    int nka = 15, nk = 12;
+    float knot_spacing = 0.5f;
+    HBondCoverage(Engine&, const h5l::Node& g, CoordNode& hb, CoordNode& sc)
+        : CoordNode((int)h5_dims(g, "index2", 1)[0], 1), ig(g, false, EXCL_SEQ2, 7, 6, &hb, &sc) {
+        if (hb.wp != 8 || sc.wp != 8) throw std::string("hbond_coverage expects 8-float rows on both arguments");
+        // knot counts are compile-time in the reference (bead_interaction.h:12-27); here they follow the table shape:
+        // n_param = 2*n_knot_angular + 2*n_knot_radial with (angular, radial, spacing) of the three reference builds
+        if (ig.n_param == 2 * 15 + 2 * 12) { nka = 15; nk = 12; knot_spacing = 0.5f; }
+        else if (ig.n_param == 2 * 8 + 2 * 12) { nka = 8; nk = 12; knot_spacing = 1.f; }
+        else if (ig.n_param == 2 * 8 + 2 * 7) { nka = 8; nk = 7; knot_spacing = 1.f; }
+        else throw "unsupported hbond_coverage parameter count " + std::to_string(ig.n_param);
+        ig.cutoff = float((nk - 2 - 1e-6) / double(1.f / knot_spacing));   // hbond.cpp:250-252
+    }
+    void finalize() override { ig.allocate(engine); }
+    QuadSplineShape shape() const { QuadSplineShape q; q.nka = nka; q.nk = nk; q.inv_dx = 1.f / knot_spacing; q.inv_dtheta = (nka - 3) / 2.f; return q; }
+    void compute_value(cudaStream_t s, ComputeMode) override {
+        if (!n_elem) return;
+        ig.build(s);
+        k_hbond_coverage<<<group_grid(ig.n2, engine->n_rep), TPB, 0, s>>>(ig.dev(), shape(), output);
+    }
+    void propagate_deriv(cudaStream_t s) override {
+        if (!n_elem) return;
+        k_hbond_coverage_deriv2<<<group_grid(ig.n2, engine->n_rep), TPB, 0, s>>>(ig.dev(), shape(), sens);
+        if (ig.n1) k_hbond_coverage_deriv1<<<group_grid(ig.n1, engine->n_rep), TPB, 0, s>>>(ig.dev(), shape(), sens);
+    }
+    bool get_pairlist(int replica, std::vector<int>& i1, std::vector<int>& i2) override { return ig.pairlist(replica, i1, i2); }
+    std::vector<float> get_param() const override { return ig.h_param; }
+    void set_param(const std::vector<float>& p) override { ig.set_param(p); }
+    std::vector<float> get_value_by_name(int replica, const char* nm) override {
+        if (std::string(nm) == "count_edges_by_type") return ig.count_edges_by_type(replica);
+        throw std::string("Value ") + nm + " not implemented";
+    }
+};
+RegisterNodeType<HBondCoverage, 2> coverage_node("hbond_coverage");
+
+// ================================================================================================ EnvironmentCoverage
+__global__ void k_env_coverage(IGraphDev g, float* __restrict__ out) {
+    int r = blockIdx.y;
+    int i = (blockIdx.x * blockDim.x + threadIdx.x) / G, lane = threadIdx.x % G;
+    bool active = i < g.s1.n;
+    float acc = 0.f;
+    if (active) {
+        float x1[8];
+        load8(elem_ptr(g.s1, r, i), x1);
+        const float* p = g.param + size_t(g.s1.type[i]) * g.n_type2 * g.n_param;
+        const unsigned short* row = g.nbr1 + (size_t(r) * g.s1.n + i) * g.K1;
+        int cnt = g.cnt1[size_t(r) * g.s1.n + i];
+        for (int k = lane; k < cnt; k += G) {
+            int j = row[k];
+            float4 v = *reinterpret_cast<const float4*>(elem_ptr(g.s2, r, j));
+            float x2[4] = {v.x, v.y, v.z, v.w}, d1[6], d2[4];
+            acc += environment_edge(p + size_t(g.s2.type[j]) * g.n_param, x1, x2, d1, d2);
+        }
+    }
+    acc = group_sum<G>(acc);
+    if (active && lane == 0) out[size_t(r) * g.s1.n + i] = acc;
+}
+__global__ void k_env_coverage_deriv1(IGraphDev g, const float* __restrict__ sens) {
+    int r = blockIdx.y;
+    int i = (blockIdx.x * blockDim.x + threadIdx.x) / G, lane = threadIdx.x % G;
+    bool active = i < g.s1.n;
+    float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float si = 0.f;
+    if (active) {
+        si = sens[size_t(r) * g.s1.n + i];
+        float x1[8];
+        load8(elem_ptr(g.s1, r, i), x1);
+        const float* p = g.param + size_t(g.s1.type[i]) * g.n_type2 * g.n_param;
+        const unsigned short* row = g.nbr1 + (size_t(r) * g.s1.n + i) * g.K1;
+        int cnt = (si != 0.f) ? g.cnt1[size_t(r) * g.s1.n + i] : 0;
+        for (int k = lane; k < cnt; k += G) {
+            int j = row[k];
+            float4 v = *reinterpret_cast<const float4*>(elem_ptr(g.s2, r, j));
+            float x2[4] = {v.x, v.y, v.z, v.w}, d1[6], d2[4];
+            environment_edge(p + size_t(g.s2.type[j]) * g.n_param, x1, x2, d1, d2);
+#pragma unroll
+            for (int c = 0; c < 6; ++c) acc[c] += d1[c];
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 6; ++c) acc[c] = group_sum<G>(acc[c]);
+    if (active && lane == 0) {
+        float* dst = elem_sens_ptr(g.s1, r, i);
+#pragma unroll
+        for (int c = 0; c < 6; ++c) dst[c] += si * acc[c];
+    }
+}
+__global__ void k_env_coverage_deriv2(IGraphDev g, const float* __restrict__ sens) {
+    int r = blockIdx.y;
+    int j = (blockIdx.x * blockDim.x + threadIdx.x) / G, lane = threadIdx.x % G;
+    bool active = j < g.s2.n;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    if (active) {
+        float4 v = *reinterpret_cast<const float4*>(elem_ptr(g.s2, r, j));
+        float x2[4] = {v.x, v.y, v.z, v.w};
+        int t2 = g.s2.type[j];
+        const unsigned short* row = g.nbr2 + (size_t(r) * g.s2.n + j) * g.K2;
+        int cnt = g.cnt2[size_t(r) * g.s2.n + j];
+        for (int k = lane; k < cnt; k += G) {
+            int i = row[k];
+            float si = sens[size_t(r) * g.s1.n + i];
+            float x1[8], d1[6], d2[4];
+            load8(elem_ptr(g.s1, r, i), x1);
+            environment_edge(g.param + (size_t(g.s1.type[i]) * g.n_type2 + t2) * g.n_param, x1, x2, d1, d2);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[c] += si * d2[c];
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[c] = group_sum<G>(acc[c]);
+    if (active && lane == 0) {
+        float* dst = elem_sens_ptr(g.s2, r, j);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) dst[c] += acc[c];
+    }
+}
+struct EnvironmentCoverage : CoordNode {
+    IGraphHost ig;
+    EnvironmentCoverage(Engine&, const h5l::Node& g, CoordNode& cb, CoordNode& wsc)
+        : CoordNode((int)h5_dims(g, "index1", 1)[0], 1), ig(g, false, EXCL_SEQ2, 6, 4, &cb, &wsc) {
+        if (ig.n_param != 4) throw std::string("environment_coverage expects 4 interaction parameters");
+        if (cb.wp != 8 || wsc.wp != 4) throw std::string("environment_coverage expects (8,4)-float rows");
+        update_cutoff();
+    }
+    void update_cutoff() {
+        float c = 0.f;   // environment.cpp:18-20 with compact_sigmoid_cutoff = 1/sharpness
+        for (int t = 0; t < ig.n_type1 * ig.n_type2; ++t) c = std::max(c, ig.h_param[t * 4 + 0] + 1.f / ig.h_param[t * 4 + 1]);
+        ig.cutoff = c;
+    }
+    void finalize() override { ig.allocate(engine); }
+    void compute_value(cudaStream_t s, ComputeMode) override {
+        if (!n_elem) return;
+        ig.build(s);
+        k_env_coverage<<<group_grid(ig.n1, engine->n_rep), TPB, 0, s>>>(ig.dev(), output);
+    }
+    void propagate_deriv(cudaStream_t s) override {
+        if (!n_elem) return;
+        k_env_coverage_deriv1<<<group_grid(ig.n1, engine->n_rep), TPB, 0, s>>>(ig.dev(), sens);
+        if (ig.n2) k_env_coverage_deriv2<<<group_grid(ig.n2, engine->n_rep), TPB, 0, s>>>(ig.dev(), sens);
+    }
+    bool get_pairlist(int replica, std::vector<int>& i1, std::vector<int>& i2) override { return ig.pairlist(replica, i1, i2); }
+    std::vector<float> get_param() const override { return ig.h_param; }
+    void set_param(const std::vector<float>& p) override { ig.set_param(p); }   // cutoff change needs a new engine
+};
+RegisterNodeType<EnvironmentCoverage, 2> environment_coverage_node("environment_coverage");
+
+}  // namespace
+}  // namespace ub
