@@ -49,6 +49,54 @@ def align_quat_sign(a, b):
     return b
 
 
+def igraph_specs(cfg):
+    """(node, group-1 node, group-2 node, index1, id1, index2, id2, cutoff, exclusion, symmetric) of every pair list,
+    read from the configuration exactly as the reference constructors do"""
+    pot = h5lite.load(cfg)['input/potential']
+    f32 = np.float32
+    specs = {}
+    def two(name, kind, cutoff):
+        g = pot[name]
+        a = [_s(x) for x in g.attrs['arguments']]
+        specs[name] = (a[0], a[1] if len(a) > 1 else a[0], g['index1'].data, g['id1'].data, g['index2'].data, g['id2'].data,
+                       f32(cutoff), kind, False)
+    g = pot['rotamer/pair_interaction']
+    sc = _s(pot['rotamer'].attrs['arguments'][0])
+    specs['rotamer'] = (sc, sc, g['index'].data, g['id'].data, g['index'].data, g['id'].data, f32((16 - 2 - 1e-6) / 2.0), 'rotamer', True)
+    two('hbond_coverage', 'seq2', (12 - 2 - 1e-6) / 2.0)
+    two('hbond_coverage_hydrophobe', 'seq2', (12 - 2 - 1e-6) / 2.0)
+    prm = pot['environment_coverage/interaction_param'].data.astype('f4')
+    two('environment_coverage', 'seq2', (prm[..., 0] + f32(1.) / prm[..., 1]).max())
+    two('protein_hbond', 'none', np.sqrt(f32(3.5 * 3.5)))
+    bb = pot['backbone_pairs']
+    ref = bb['ref_pos'].data.astype('f4'); na = bb['n_atom'].data
+    dev = max(np.sqrt((ref[i, a] ** 2).sum(dtype='f4')) for i in range(len(na)) for a in range(na[i]))
+    cut = f32(2) * f32(dev) + np.sqrt(f32(3.) * f32(3.) + f32(0.1) * f32(3.))
+    specs['backbone_pairs'] = ('affine_alignment', 'affine_alignment', bb['id'].data, bb['id'].data, bb['id'].data, bb['id'].data, f32(cut), 'seq1', True)
+    return specs
+
+
+def _s(x):
+    return x.decode() if isinstance(x, bytes) else str(x)
+
+
+def restated_pairlist(spec, out1, out2):
+    """the reference predicate + emission order (oracle/restate.py) applied to given node outputs"""
+    from oracle import restate
+    n1, n2, i1, id1, i2, id2, cutoff, kind, sym = spec
+    return restate.pairlist(out1[i1][:, :3], id1, out2[i2][:, :3], id2, cutoff, kind, sym)
+
+
+def boundary_gap(spec, out1, out2, edges):
+    """largest |dist - cutoff| over the given edges (edges that differ between two engines must sit on the cutoff)"""
+    if not len(edges):
+        return 0.0
+    n1, n2, i1, id1, i2, id2, cutoff, kind, sym = spec
+    e = np.array(sorted(edges))
+    d = np.linalg.norm(out1[i1][e[:, 0], :3].astype('f8') - out2[i2][e[:, 1], :3].astype('f8'), axis=1)
+    return float(np.abs(d - float(cutoff)).max())
+
+
 def compare_engines(cfg, pos, verbose=True):
     """returns dict of per-node max abs differences (output, sens), potentials, pair-list equality, for each replica"""
     n_rep, n_atom = pos.shape[0], pos.shape[1]
@@ -56,6 +104,7 @@ def compare_engines(cfg, pos, verbose=True):
     en, deriv = be.evaluate(pos)
     ref = ref_engine.RefEngine(cfg, n_atom, 'pinned')
     report = []
+    specs = igraph_specs(cfg)
     for r in range(n_rep):
         e_ref = ref.energy(pos[r])
         d_ref = ref.deriv(pos[r])
@@ -80,8 +129,14 @@ def compare_engines(cfg, pos, verbose=True):
             pg, pr = be.pairlist(name, r), ref.pairlist(name)
             same = pg.shape == pr.shape and bool((pg == pr).all())
             sg, sr = set(map(tuple, pg)), set(map(tuple, pr))
+            sp = specs[name]
+            o1, o2 = be.get_output(sp[0], r), be.get_output(sp[1], r)
+            restated = restated_pairlist(sp, o1, o2)
             rep['pairlists'][name] = dict(n_gpu=len(pg), n_ref=len(pr), identical=same, only_gpu=len(sg - sr),
-                                          only_ref=len(sr - sg))
+                                          only_ref=len(sr - sg),
+                                          # bit-exact given IDENTICAL coordinates: reference predicate on the GPU's own inputs
+                                          exact_given_same_coords=restated.shape == pg.shape and bool((restated == pg).all()),
+                                          boundary_gap=boundary_gap(sp, ref.get_output(sp[0]), ref.get_output(sp[1]), sg ^ sr))
         mg = be.get_value_by_name('rotamer', 'bead_marginal', r)
         mr = ref.rotamer_bead_marginals()
         rep['marginal_maxabs'] = float(np.abs(mg - mr).max())
@@ -107,8 +162,8 @@ def print_report(rep):
         else:
             print('   %-40s out %.2e (/%.1f)  sens %.2e (/%.1f)' % (name, d['out'], d['out_scale'], d['sens'], d['sens_scale']))
     for name, d in rep['pairlists'].items():
-        print('   pairlist %-32s gpu %d ref %d identical %s only_gpu %d only_ref %d' % (
-            name, d['n_gpu'], d['n_ref'], d['identical'], d['only_gpu'], d['only_ref']))
+        print('   pairlist %-32s gpu %d ref %d identical %s only_gpu %d only_ref %d exact_given_same_coords %s gap %.1e' % (
+            name, d['n_gpu'], d['n_ref'], d['identical'], d['only_gpu'], d['only_ref'], d['exact_given_same_coords'], d['boundary_gap']))
 
 
 if __name__ == '__main__':

@@ -25,7 +25,11 @@ def _check_report(rep):
         assert r['deriv_maxabs'] <= F_RTOL * max(1.0, r['deriv_scale']), (r['deriv_maxabs'], r['deriv_scale'])
         assert r['marginal_maxabs'] <= MARG_ATOL
         for name, d in r['pairlists'].items():
-            assert d['identical'], (name, d)
+            # bit-exact (edges and order) given identical inputs to the pair-list stage: the reference predicate applied
+            # to the GPU's own node outputs.  End to end the two engines' bead coordinates differ by ~1e-5 A of upstream
+            # rounding, so a pair sitting exactly on the cutoff may flip; such edges must be on the cutoff.
+            assert d['exact_given_same_coords'], (name, d)
+            assert d['identical'] or d['boundary_gap'] < 2e-4, (name, d)
         for name, d in r['nodes'].items():
             if 'pot' in d:
                 a, b = d['pot']
@@ -136,7 +140,9 @@ def test_full_batch_invariants():
     be = ue.BatchEngine(parity.CONFIGS[3], B)
     en, dv = be.evaluate(pos)
     assert (en[0::2] == en[0]).all() and (en[1::2] == en[1]).all()
-    assert (dv[0::2] == dv[0]).all() and (dv[1::2] == dv[1]).all()
+    # pair terms are gather-form (fixed summation order); the small element-wise nodes scatter with float atomics, so
+    # forces of identical replicas agree to rounding, not bit for bit
+    assert np.abs(dv[0::2] - dv[0]).max() < 1e-3 and np.abs(dv[1::2] - dv[1]).max() < 1e-3
     np.testing.assert_allclose(en[:2], g['energy'], rtol=E_RTOL)
     net = dv.sum(axis=1)
     assert np.abs(net).max() < 2e-2          # no external field in config 3: net force vanishes (fp32 accumulation)
