@@ -189,7 +189,7 @@ def gpu_arm(args):
                     e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=bytes_io, d2h_bytes_per_step=bytes_io, steps=e2e_steps),
                     gpu_launches=int((launches * 3 + 3 + 2) * args.steps), roofline=roof,
                     cpu_baseline=({k: cpu[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')} if cpu else None))
-        print(json.dumps(line))
+        print(json.dumps(line, default=float))
     eng.close()
     if world > 1:
         dist.destroy_process_group()
@@ -240,7 +240,7 @@ def reference_arm(args):
                 us_per_force_eval=cpu['us_per_force_eval'],
                 cpu_baseline={k: cpu[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')},
                 e2e=dict(value=cpu['value'], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
-    print(json.dumps(line))
+    print(json.dumps(line, default=float))
 
 
 def main():
