@@ -1,16 +1,20 @@
-// RotamerSidechain on the B200: one CTA per replica runs the whole node - 1-body energies, bead-pair energies,
-// residue-pair graph construction, damped loopy belief propagation, Bethe free energy and the backward pass -
-// with the BP state (beliefs, residue adjacency bitmap) resident in shared memory.
+// RotamerSidechain on the B200 (reference src/rotamer.cpp).  Four kernels per evaluation, all batched over replicas:
 //
-// Reference: src/rotamer.cpp: fill_holders :793-852, solve_for_marginals :1005-1061, EdgeHolder::update_beliefs
-// :453-522, NodeHolder::standardize_belief_update :258-273, calculate_marginals :275-281,403-429, free energies
-// :292-302,431-451, propagate_derivatives :956-985.  Bead ids encode (residue k << 8 | n_rot << 4 | rot)
-// (upside_config.py:976-983).
+//   k_rot_prep    one CTA per replica: residue adjacency bitmap (shared memory) from the bead ELL rows -> a slot for
+//                 every residue pair by prefix popcount, incidence lists, a per-neighbour-entry "code" saying where the
+//                 pair energy goes / where its sensitivity comes from, 1-body node energies.
+//   k_rot_energy  throughput-shaped: beads + the B-spline table staged in shared memory, 8 lanes walk each bead's row,
+//                 pair energies -> residue-pair matrices; partners with a single rotamer state are folded into the
+//                 bead's node energy (fill_holders, rotamer.cpp:793-852).
+//   k_rot_bp      one CTA per replica, state resident in shared memory (pair matrices, messages, beliefs): damped
+//                 loopy belief propagation (solve_for_marginals :1005-1061, update_beliefs :453-522,
+//                 standardize_belief_update :258-273), marginals (:275-281,403-429), Bethe free energy (:292-302,431-451).
+//   k_rot_deriv   throughput-shaped: per bead, sum over partners of marginal * dV/d(bead) with the pair term recomputed
+//                 (propagate_derivatives :956-985), node marginals into the 1-body sens.
 //
-// Differences of formulation (not of result): the reference keys residue pairs through an open-addressed table
-// (EdgeLocator :134-206) in bead-pair emission order; here a residue-adjacency bitmap in shared memory gives every
-// residue pair a slot by prefix popcount, so the pair -> slot map needs no hashing and is deterministic.  Messages are
-// L1-normalised with an exact reciprocal instead of the 12-bit rcpps (:513); both only rescale messages.
+// Bead ids encode (residue k << 8 | n_rot << 4 | rot) (upside_config.py:976-983).  Differences of formulation, not of
+// result: residue pairs get slots from an adjacency bitmap instead of the reference's open-addressed EdgeLocator
+// (:134-206); messages are L1-normalised with an exact reciprocal instead of the 12-bit rcpps (:513).
 #include <algorithm>
 #include <cmath>
 
@@ -19,27 +23,45 @@
 namespace ub {
 namespace {
 
-constexpr int MAXR = 6;           // most rotamer states per residue (UPPER_ROT-1 in the reference)
-constexpr int RTPB = 256;         // threads per replica CTA
-constexpr int RG = 8;             // lanes per bead row
+constexpr int MAXR = 6;            // most rotamer states per residue (UPPER_ROT-1 in the reference)
+constexpr int PREP_TPB = 128;
+constexpr int EDGE_TPB = 256;
+constexpr int BP_TPB = 256;
+constexpr int RG = 8;              // lanes per bead row
 constexpr int MAX_PROB_NODES = 4;
+constexpr int CODE_FOLD = -1;      // (multi-state bead, single-state partner)
+constexpr int CODE_SS = INT_MIN;   // (single, single)
+// code >= 0: index into the replica's pair-matrix array (slot*36 + a*6 + b); code <= -2: (single bead, multi partner),
+// -2-code = partner's node index res*6+rot
+
+struct BeadRec {   // 32 bytes, staged in shared memory by the edge kernels
+    float x, y, z, dx, dy, dz;
+    int type;
+    int res_rot;   // res << 3 | rot
+};
 
 struct RotamerDev {
     IGraphDev g;
     QuadSplineShape q;
-    int n_bead, n_res, n_words;
+    int n_bead, n_res, n_words, n_type;
     const int *bead_res, *bead_rot, *res_nrot;
+    const float* table;   // symmetric-compressed B-spline table: rows (t1<=t2), n_param floats each
     int n_prob;
     const float* prob_out[MAX_PROB_NODES];
     float* prob_sens[MAX_PROB_NODES];
     int prob_wp[MAX_PROB_NODES], prob_n[MAX_PROB_NODES];
     float damping, tol;
-    int max_iter, chunk, max_pairs;
+    int max_iter, chunk, max_pairs, smem_pairs, multi_bead_states, n_chunk;
     // per-replica scratch in global memory
-    float* pmat;              // [B][max_pairs][36]  pair energy -> probability -> marginal
-    float* msg;               // [B][2][max_pairs][12]
+    int* code;                // [B][n_bead][K1]
+    int* lower;               // [B][n_bead]  number of partners with a smaller bead index
+    float* enode;             // [B][n_res][6]  1-body energy per (residue, state)
+    float* fold;              // [B][n_bead]    energy of single-state partners
+    float* e11;               // [B]
+    float* pmat;              // [B][max_pairs][36]  pair energy -> marginal
     unsigned short* pair_ab;  // [B][max_pairs][2]
     int* inc;                 // [B][2*max_pairs]
+    int* istart;              // [B][n_res+1]
     float* node_marg;         // [B][n_res][6]
     int* stats;               // [B][4]: n_iter, n_pair, converged, -
     float* potential;
@@ -60,169 +82,79 @@ __device__ __forceinline__ int rank_between(const unsigned* row, int nW, int lo,
     return cnt;
 }
 
-// value only (forward); ordering (lo,hi) as the reference's i1<i2 edge
-__device__ __forceinline__ float bead_pair_value(const RotamerDev& P, int r, int lo, int hi) {
-    float x1[8], x2[8], d1[6], d2[6];
-    load8(elem_ptr(P.g.s1, r, lo), x1);
-    load8(elem_ptr(P.g.s1, r, hi), x2);
-    const float* prm = P.g.param + (size_t(P.g.s1.type[lo]) * P.g.n_type2 + P.g.s1.type[hi]) * P.g.n_param;
-    return quadspline_edge(prm, P.q, x1, x2, d1, d2);
-}
-
-__device__ __forceinline__ float block_max_bcast(float v, float* red) {
-    v = warp_max(v);
-    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    __syncthreads();
-    if (lane == 0) red[w] = v;
-    __syncthreads();
-    float m = red[0];
-    for (int k = 1; k < RTPB / 32; ++k) m = fmaxf(m, red[k]);
-    return m;
-}
-
-// one message sweep over all residue-pair edges: old beliefs/messages -> new messages (rotamer.cpp:468-520)
-__device__ __forceinline__ void bp_messages(const RotamerDev& P, int n_pair, const unsigned short* pair_ab, const float* pmat,
-                                            const float* bel_old, const float* msg_old, float* msg_new) {
-    for (int e = threadIdx.x; e < n_pair; e += RTPB) {
-        int A = pair_ab[2 * e], B = pair_ab[2 * e + 1];
-        int nA = P.res_nrot[A], nB = P.res_nrot[B];
-        float v1[MAXR], v2[MAXR];
-#pragma unroll
-        for (int a = 0; a < MAXR; ++a) {
-            v1[a] = a < nA ? bel_old[A * MAXR + a] / (1e-10f + msg_old[e * 12 + a]) : 0.f;
-            v2[a] = a < nB ? bel_old[B * MAXR + a] / (1e-10f + msg_old[e * 12 + 6 + a]) : 0.f;
-        }
-        const float* M = pmat + size_t(e) * 36;
-        float m1[MAXR], m2[MAXR];
-#pragma unroll
-        for (int a = 0; a < MAXR; ++a) { m1[a] = 0.f; m2[a] = 0.f; }
-#pragma unroll
-        for (int a = 0; a < MAXR; ++a) {
-            if (a < nA) {
-#pragma unroll
-                for (int b = 0; b < MAXR; ++b) {
-                    if (b < nB) {
-                        float p = M[a * 6 + b];
-                        m1[a] = fmaf(p, v2[b], m1[a]);   // apply_left : message to A
-                        m2[b] = fmaf(v1[a], p, m2[b]);   // apply_right: message to B
-                    }
-                }
-            }
-        }
-        float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-        for (int a = 0; a < MAXR; ++a) { s1 += m1[a]; s2 += m2[a]; }
-        float i1 = 1.f / s1, i2 = 1.f / s2;
-#pragma unroll
-        for (int a = 0; a < MAXR; ++a) { msg_new[e * 12 + a] = m1[a] * i1; msg_new[e * 12 + 6 + a] = m2[a] * i2; }
-    }
-}
-
-// node update: belief = prob * prod(incoming messages), max-normalised and damped (rotamer.cpp:488-499,258-273);
-// returns this thread's largest signed deviation cur-old
-__device__ __forceinline__ float bp_nodes(const RotamerDev& P, const int* istart, const int* inc, const float* prob,
-                                          const float* msg_new, const float* bel_old, float* bel_new, float damping) {
-    float dev = 0.f;
-    for (int A = threadIdx.x; A < P.n_res; A += RTPB) {
-        int nA = P.res_nrot[A];
-        if (nA < 2) continue;
-        float b[MAXR];
-#pragma unroll
-        for (int a = 0; a < MAXR; ++a) b[a] = prob[A * MAXR + a];
-        for (int t = istart[A]; t < istart[A + 1]; ++t) {
-            int code = inc[t];
-            const float* m = msg_new + (code >> 1) * 12 + (code & 1) * 6;
-            float s = 0.f;
-#pragma unroll
-            for (int a = 0; a < MAXR; ++a) { b[a] *= m[a]; s += b[a]; }
-            float is = 1.f / s;
-#pragma unroll
-            for (int a = 0; a < MAXR; ++a) b[a] *= is;
-        }
-        float mx = b[0];
-#pragma unroll
-        for (int a = 1; a < MAXR; ++a) mx = fmaxf(mx, b[a]);
-        float imx = 1.f / mx;
-#pragma unroll
-        for (int a = 0; a < MAXR; ++a) {
-            float o = bel_old[A * MAXR + a];
-            float n = (damping != 0.f) ? (1.f - damping) * imx * b[a] + damping * o : imx * b[a];
-            if (a < nA) dev = fmaxf(dev, n - o);
-            bel_new[A * MAXR + a] = n;
-        }
-    }
-    return dev;
-}
-
-__global__ void __launch_bounds__(RTPB) k_rotamer(RotamerDev P, int want_pot) {
-    extern __shared__ float smem[];
+// ================================================================================================ prep
+__global__ void __launch_bounds__(PREP_TPB) k_rot_prep(RotamerDev P) {
+    extern __shared__ unsigned smem_u[];
     const int r = blockIdx.x, tid = threadIdx.x;
-    const int nR = P.n_res, nW = P.n_words;
-    float* Enode = smem;                       // [nR][6] energy, then unused
-    float* prob = Enode + nR * MAXR;           // [nR][6]
-    float* bel0 = prob + nR * MAXR;            // [nR][6]
-    float* bel1 = bel0 + nR * MAXR;            // [nR][6]
-    float* offs = bel1 + nR * MAXR;            // [nR]
-    unsigned* bitmap = reinterpret_cast<unsigned*>(offs + nR);   // [nR][nW] symmetric residue adjacency
+    const int nR = P.n_res, nW = P.n_words, K = P.g.K1;
+    unsigned* bitmap = smem_u;                                   // [nR][nW] symmetric residue adjacency (multi-state only)
     int* estart = reinterpret_cast<int*>(bitmap + nR * nW);      // [nR+1] first slot of pairs (A,B>A)
-    int* istart = estart + nR + 1;                                // [nR+1] incidence CSR
-    float* red = reinterpret_cast<float*>(istart + nR + 1);      // [32]
-
-    float* pmat = P.pmat + size_t(r) * P.max_pairs * 36;
-    float* msg0 = P.msg + size_t(r) * 2 * P.max_pairs * 12;
-    float* msg1 = msg0 + size_t(P.max_pairs) * 12;
-    unsigned short* pair_ab = P.pair_ab + size_t(r) * P.max_pairs * 2;
-    int* inc = P.inc + size_t(r) * 2 * P.max_pairs;
-    float* node_marg = P.node_marg + size_t(r) * nR * MAXR;
-    const unsigned short* nbr = P.g.nbr1 + size_t(r) * P.n_bead * P.g.K1;
+    int* istart = estart + nR + 1;                               // [nR+1]
+    float* en = reinterpret_cast<float*>(istart + nR + 1);       // [nR*6]
+    const unsigned short* nbr = P.g.nbr1 + size_t(r) * P.n_bead * K;
     const int* cnt = P.g.cnt1 + size_t(r) * P.n_bead;
+    int* code = P.code + size_t(r) * P.n_bead * K;
 
-    // ---- 1. one-body energies and residue adjacency -------------------------------------------------------
-    for (int i = tid; i < nR * MAXR; i += RTPB) Enode[i] = 0.f;
-    for (int i = tid; i < nR * nW; i += RTPB) bitmap[i] = 0u;
+    for (int i = tid; i < nR * nW; i += PREP_TPB) bitmap[i] = 0u;
+    for (int i = tid; i < nR * MAXR; i += PREP_TPB) en[i] = 0.f;
     __syncthreads();
-    for (int i = tid; i < P.n_bead; i += RTPB) {
+    for (int i = tid; i < P.n_bead; i += PREP_TPB) {
         float e = 0.f;
         int loc = P.g.s1.loc[i];
         for (int p = 0; p < P.n_prob; ++p) e += P.prob_out[p][(size_t(r) * P.prob_n[p] + loc) * P.prob_wp[p]];
-        atomicAdd(&Enode[P.bead_res[i] * MAXR + P.bead_rot[i]], e);
         int A = P.bead_res[i];
-        if (P.res_nrot[A] > 1) {
-            const unsigned short* row = nbr + size_t(i) * P.g.K1;
-            for (int k = 0; k < cnt[i]; ++k) {
-                int Bq = P.bead_res[row[k]];
+        atomicAdd(&en[A * MAXR + P.bead_rot[i]], e);   // one contributor per state unless several beads share a state
+        const unsigned short* row = nbr + size_t(i) * K;
+        int c = cnt[i], lo = 0;
+        bool multi = P.res_nrot[A] > 1;
+        for (int k = 0; k < c; ++k) {
+            int j = row[k];
+            lo += j < i;
+            if (multi) {
+                int Bq = P.bead_res[j];
                 if (P.res_nrot[Bq] > 1) atomicOr(&bitmap[A * nW + (Bq >> 5)], 1u << (Bq & 31));
             }
         }
+        P.lower[size_t(r) * P.n_bead + i] = lo;
     }
     __syncthreads();
-    for (int A = tid; A < nR; A += RTPB) {   // energy offset = smallest 1-body energy (convert_energy_to_prob :239-256)
-        float m = Enode[A * MAXR];
-        for (int a = 1; a < P.res_nrot[A]; ++a) m = fminf(m, Enode[A * MAXR + a]);
-        offs[A] = m;
-    }
-    if (tid == 0) {
-        int eu = 0, ei = 0;
-        for (int A = 0; A < nR; ++A) {
-            estart[A] = eu;
-            istart[A] = ei;
+    if (tid < 32) {   // exclusive scans of upper degree (pair slots) and full degree (incidence lists), one warp
+        int per = (nR + 31) / 32, a0 = tid * per, a1 = min(nR, a0 + per);
+        int su = 0, sf = 0;
+        for (int A = a0; A < a1; ++A) {
             const unsigned* row = bitmap + A * nW;
             int deg = 0;
             for (int w = 0; w < nW; ++w) deg += __popc(row[w]);
-            eu += rank_between(row, nW, A, nR);
-            ei += deg;
+            su += rank_between(row, nW, A, nR);
+            sf += deg;
         }
-        estart[nR] = eu;
-        istart[nR] = ei;
+        int pu = su, pf = sf;
+        for (int o = 1; o < 32; o <<= 1) {
+            int tu = __shfl_up_sync(UB_FULL_MASK, pu, o), tf = __shfl_up_sync(UB_FULL_MASK, pf, o);
+            if (tid >= o) { pu += tu; pf += tf; }
+        }
+        int eu = pu - su, ef = pf - sf;
+        for (int A = a0; A < a1; ++A) {
+            const unsigned* row = bitmap + A * nW;
+            int deg = 0;
+            for (int w = 0; w < nW; ++w) deg += __popc(row[w]);
+            estart[A] = eu; istart[A] = ef;
+            eu += rank_between(row, nW, A, nR);
+            ef += deg;
+        }
+        if (tid == 31) { estart[nR] = pu; istart[nR] = pf; }
     }
     __syncthreads();
     const int n_pair = estart[nR];
+    if (tid == 0) { P.stats[size_t(r) * 4 + 1] = n_pair; P.e11[r] = 0.f; }
     if (n_pair > P.max_pairs) {   // uniform across the block
-        if (tid == 0) atomicExch(P.error_flag, 2);
+        if (tid == 0) { atomicExch(P.error_flag, 2); P.stats[size_t(r) * 4 + 1] = 0; }
         return;
     }
-    // ---- 2. pair slots, incidence lists, zeroed pair energies -----------------------------------------------
-    for (int A = tid; A < nR; A += RTPB) {
+    unsigned short* pair_ab = P.pair_ab + size_t(r) * P.max_pairs * 2;
+    int* inc = P.inc + size_t(r) * 2 * P.max_pairs;
+    for (int A = tid; A <= nR; A += PREP_TPB) P.istart[size_t(r) * (nR + 1) + A] = istart[A];
+    for (int A = tid; A < nR; A += PREP_TPB) {
         const unsigned* row = bitmap + A * nW;
         int t = istart[A], up = 0;
         for (int w = 0; w < nW; ++w) {
@@ -236,100 +168,388 @@ __global__ void __launch_bounds__(RTPB) k_rotamer(RotamerDev P, int want_pot) {
                     pair_ab[2 * e + 1] = (unsigned short)C;
                     inc[t++] = 2 * e;
                 } else {
-                    int e = estart[C] + rank_between(bitmap + C * nW, nW, C, A);
-                    inc[t++] = 2 * e + 1;
+                    inc[t++] = 2 * (estart[C] + rank_between(bitmap + C * nW, nW, C, A)) + 1;
                 }
             }
         }
     }
-    for (int i = tid; i < n_pair * 36; i += RTPB) pmat[i] = 0.f;
+    for (int i = tid; i < nR * MAXR; i += PREP_TPB) P.enode[size_t(r) * nR * MAXR + i] = en[i];
+    float* pmat = P.pmat + size_t(r) * P.max_pairs * 36;
+    for (int i = tid; i < n_pair * 36; i += PREP_TPB) pmat[i] = 0.f;
+    // per-entry codes
+    for (int i = tid; i < P.n_bead; i += PREP_TPB) {
+        int A = P.bead_res[i], ra = P.bead_rot[i];
+        bool mA = P.res_nrot[A] > 1;
+        const unsigned short* row = nbr + size_t(i) * K;
+        int c = cnt[i];
+        for (int k = 0; k < c; ++k) {
+            int j = row[k];
+            int Bq = P.bead_res[j], rb = P.bead_rot[j];
+            bool mB = P.res_nrot[Bq] > 1;
+            int cd;
+            if (mA && mB) {
+                if (A < Bq) cd = (estart[A] + rank_between(bitmap + A * nW, nW, A, Bq)) * 36 + ra * 6 + rb;
+                else cd = (estart[Bq] + rank_between(bitmap + Bq * nW, nW, Bq, A)) * 36 + rb * 6 + ra;
+            } else if (mA) cd = CODE_FOLD;
+            else if (mB) cd = -2 - (Bq * MAXR + rb);
+            else cd = CODE_SS;
+            code[size_t(i) * K + k] = cd;
+        }
+    }
+}
+
+// ================================================================================================ edge kernels
+// row (t1,t2) of the symmetric-compressed table; swap = angular blocks exchanged (bead_interaction.h:209-218)
+__device__ __forceinline__ int sym_row(int t1, int t2, int nT, bool& swap) {
+    swap = t1 > t2;
+    int a = swap ? t2 : t1, b = swap ? t1 : t2;
+    return a * nT - (a * (a - 1)) / 2 + (b - a);
+}
+
+__device__ __forceinline__ void stage_shared(const RotamerDev& P, int r, BeadRec* beads, float* table) {
+    const int n_tab = (P.n_type * (P.n_type + 1) / 2) * P.g.n_param;
+    for (int i = threadIdx.x; i < n_tab; i += blockDim.x) table[i] = P.table[i];
+    for (int i = threadIdx.x; i < P.n_bead; i += blockDim.x) {
+        const float* p = elem_ptr(P.g.s1, r, i);
+        float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
+        BeadRec br;
+        br.x = a.x; br.y = a.y; br.z = a.z; br.dx = a.w; br.dy = b.x; br.dz = b.y;
+        br.type = P.g.s1.type[i];
+        br.res_rot = (P.bead_res[i] << 3) | P.bead_rot[i];
+        beads[i] = br;
+    }
     __syncthreads();
-    // ---- 3. bead-pair energies: residue-pair matrices, single-state partners folded into node energies -------
-    float e11 = 0.f;   // energy of (1-state, 1-state) pairs, needed only for the potential
+}
+
+// quadspline on shared-memory operands, (lo,hi) ordering as the reference's i1<i2 edge
+template <bool DERIV>
+__device__ __forceinline__ float pair_term(const RotamerDev& P, const BeadRec& b1, const BeadRec& b2, const float* table,
+                                           float* d1, float* d2) {
+    bool swap;
+    const float* row = table + sym_row(b1.type, b2.type, P.n_type, swap) * P.g.n_param;
+    const float* ang1 = row + (swap ? P.q.nka : 0);
+    const float* ang2 = row + (swap ? 0 : P.q.nka);
+    const float* wide = row + 2 * P.q.nka;
+    const float* narrow = wide + P.q.nk;
+    f3 displace = mk3(b2.x - b1.x, b2.y - b1.y, b2.z - b1.z);
+    f3 rvec1 = mk3(b1.dx, b1.dy, b1.dz), rvec2 = mk3(b2.dx, b2.dy, b2.dz);
+    float dist2 = mag2(displace);
+    float inv_dist = rsqrtf(dist2);
+    float dist_coord = dist2 * (inv_dist * P.q.inv_dx);
+    f3 u = inv_dist * displace;
+    float cos1 = dot(rvec1, u), cos2 = -dot(rvec2, u);
+    float a1v, a1d, a2v, a2d, wv, wd, nv, nd;
     {
-        const int grp = tid / RG, lane = tid % RG;
-        for (int i0 = 0; i0 < P.n_bead; i0 += RTPB / RG) {
-            int i = i0 + grp;
-            float fold = 0.f;
-            int A = 0, ra = 0, nA = 0;
-            if (i < P.n_bead) {
-                A = P.bead_res[i]; ra = P.bead_rot[i]; nA = P.res_nrot[A];
-                const unsigned short* row = nbr + size_t(i) * P.g.K1;
-                int c = cnt[i];
-                for (int k = lane; k < c; k += RG) {
-                    int j = row[k];
-                    int Bq = P.bead_res[j], rb = P.bead_rot[j], nB = P.res_nrot[Bq];
-                    if (nA > 1 && nB > 1) {
-                        if (j > i) {
-                            float V = bead_pair_value(P, r, i, j);
-                            int e, idx;
-                            if (A < Bq) { e = estart[A] + rank_between(bitmap + A * nW, nW, A, Bq); idx = ra * 6 + rb; }
-                            else { e = estart[Bq] + rank_between(bitmap + Bq * nW, nW, Bq, A); idx = rb * 6 + ra; }
-                            atomicAdd(&pmat[size_t(e) * 36 + idx], V);
-                        }
-                    } else if (nA > 1) {
-                        fold += bead_pair_value(P, r, min(i, j), max(i, j));
-                    } else if (nB == 1 && j > i) {
-                        if (want_pot) e11 += bead_pair_value(P, r, i, j);
-                    }
-                }
-            }
-            fold = group_sum<RG>(fold);
-            if (i < P.n_bead && lane == 0 && nA > 1) atomicAdd(&Enode[A * MAXR + ra], fold);
+        float x = (cos1 + 1.f) * P.q.inv_dtheta + 1.f;
+        int b = max(1, min((int)x, P.q.nka - 3));
+        deboor_core(ang1[b - 1], ang1[b], ang1[b + 1], ang1[b + 2], x - (float)b, a1v, a1d);
+        x = (cos2 + 1.f) * P.q.inv_dtheta + 1.f;
+        b = max(1, min((int)x, P.q.nka - 3));
+        deboor_core(ang2[b - 1], ang2[b], ang2[b + 1], ang2[b + 2], x - (float)b, a2v, a2d);
+    }
+    {   // both radial splines share the knot interval (clamped rule of spline.h:275-310)
+        float x = dist_coord;
+        int nk = P.q.nk;
+        if (x < 1.f) {
+            wv = (1.f / 6.f) * wide[0] + (2.f / 3.f) * wide[1] + (1.f / 6.f) * wide[2];
+            nv = (1.f / 6.f) * narrow[0] + (2.f / 3.f) * narrow[1] + (1.f / 6.f) * narrow[2];
+            wd = nd = 0.f;
+        } else if (x >= (float)(nk - 2)) {
+            wv = (1.f / 6.f) * wide[nk - 3] + (2.f / 3.f) * wide[nk - 2] + (1.f / 6.f) * wide[nk - 1];
+            nv = (1.f / 6.f) * narrow[nk - 3] + (2.f / 3.f) * narrow[nk - 2] + (1.f / 6.f) * narrow[nk - 1];
+            wd = nd = 0.f;
+        } else {
+            int b = (int)x;
+            float y = x - (float)b;
+            deboor_core(wide[b - 1], wide[b], wide[b + 1], wide[b + 2], y, wv, wd);
+            deboor_core(narrow[b - 1], narrow[b], narrow[b + 1], narrow[b + 2], y, nv, nd);
         }
     }
+    float angular_weight = a1v * a2v;
+    if (DERIV) {
+        float radial_deriv = P.q.inv_dx * (wd + angular_weight * nd);
+        float ang_d1 = P.q.inv_dtheta * a1d * a2v * nv;
+        float ang_d2 = P.q.inv_dtheta * a1v * a2d * nv;
+        f3 rXX = ang_d1 * rvec1 - ang_d2 * rvec2;
+        f3 deriv_dir = inv_dist * (rXX - dot(u, rXX) * u);
+        f3 dd = radial_deriv * u + deriv_dir;
+        d1[0] = -dd.x; d1[1] = -dd.y; d1[2] = -dd.z; d1[3] = ang_d1 * u.x; d1[4] = ang_d1 * u.y; d1[5] = ang_d1 * u.z;
+        d2[0] = dd.x; d2[1] = dd.y; d2[2] = dd.z; d2[3] = -ang_d2 * u.x; d2[4] = -ang_d2 * u.y; d2[5] = -ang_d2 * u.z;
+    }
+    return wv + angular_weight * nv;
+}
+
+__global__ void __launch_bounds__(EDGE_TPB) k_rot_energy(RotamerDev P, int want_pot) {
+    extern __shared__ float4 smem4[];
+    BeadRec* beads = reinterpret_cast<BeadRec*>(smem4);
+    float* table = reinterpret_cast<float*>(beads + P.n_bead);
+    const int r = blockIdx.y, K = P.g.K1;
+    stage_shared(P, r, beads, table);
+    const unsigned short* nbr = P.g.nbr1 + size_t(r) * P.n_bead * K;
+    const int* cnt = P.g.cnt1 + size_t(r) * P.n_bead;
+    const int* code = P.code + size_t(r) * P.n_bead * K;
+    const int* lower = P.lower + size_t(r) * P.n_bead;
+    float* pmat = P.pmat + size_t(r) * P.max_pairs * 36;
+    const int grp = threadIdx.x / RG, lane = threadIdx.x % RG, n_grp = EDGE_TPB / RG;
+    float e11 = 0.f;
+    for (int i0 = blockIdx.x * n_grp; i0 < P.n_bead; i0 += gridDim.x * n_grp) {
+        int i = i0 + grp;
+        float fold = 0.f;
+        bool multi = false;
+        if (i < P.n_bead) {
+            BeadRec bi = beads[i];
+            multi = P.res_nrot[bi.res_rot >> 3] > 1;
+            const unsigned short* row = nbr + size_t(i) * K;
+            const int* crow = code + size_t(i) * K;
+            int c = cnt[i], lo = lower[i];
+            // partners with a smaller index only matter when they have a single state (their energy folds into bead i)
+            if (multi)
+                for (int k = lane; k < lo; k += RG)
+                    if (crow[k] == CODE_FOLD) fold += pair_term<false>(P, beads[row[k]], bi, table, nullptr, nullptr);
+            for (int k = lo + lane; k < c; k += RG) {
+                int cd = crow[k];
+                if (cd <= -2 && cd != CODE_SS) continue;   // (single, multi): handled from the partner's row
+                if (cd == CODE_SS && !want_pot) continue;
+                float V = pair_term<false>(P, bi, beads[row[k]], table, nullptr, nullptr);
+                if (cd >= 0) { if (P.multi_bead_states) atomicAdd(&pmat[cd], V); else pmat[cd] = V; }
+                else if (cd == CODE_FOLD) fold += V;
+                else e11 += V;
+            }
+        }
+        fold = group_sum<RG>(fold);
+        if (i < P.n_bead && lane == 0) P.fold[size_t(r) * P.n_bead + i] = fold;
+    }
+    if (want_pot) {
+        e11 = warp_sum(e11);
+        if ((threadIdx.x & 31) == 0 && e11 != 0.f) atomicAdd(&P.e11[r], e11);
+    }
+}
+
+__global__ void __launch_bounds__(EDGE_TPB) k_rot_deriv(RotamerDev P) {
+    extern __shared__ float4 smem4[];
+    BeadRec* beads = reinterpret_cast<BeadRec*>(smem4);
+    float* table = reinterpret_cast<float*>(beads + P.n_bead);
+    const int r = blockIdx.y, K = P.g.K1;
+    stage_shared(P, r, beads, table);
+    const unsigned short* nbr = P.g.nbr1 + size_t(r) * P.n_bead * K;
+    const int* cnt = P.g.cnt1 + size_t(r) * P.n_bead;
+    const int* code = P.code + size_t(r) * P.n_bead * K;
+    const float* pmat = P.pmat + size_t(r) * P.max_pairs * 36;
+    const float* nm = P.node_marg + size_t(r) * P.n_res * MAXR;
+    const int grp = threadIdx.x / RG, lane = threadIdx.x % RG, n_grp = EDGE_TPB / RG;
+    for (int i0 = blockIdx.x * n_grp; i0 < P.n_bead; i0 += gridDim.x * n_grp) {
+        int i = i0 + grp;
+        float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        float my_marg = 0.f;
+        if (i < P.n_bead) {
+            BeadRec bi = beads[i];
+            my_marg = nm[(bi.res_rot >> 3) * MAXR + (bi.res_rot & 7)];
+            const unsigned short* row = nbr + size_t(i) * K;
+            const int* crow = code + size_t(i) * K;
+            int c = cnt[i];
+            for (int k = lane; k < c; k += RG) {
+                int j = row[k], cd = crow[k];
+                float s = cd >= 0 ? pmat[cd] : (cd == CODE_FOLD ? my_marg : (cd == CODE_SS ? 1.f : nm[-2 - cd]));
+                float d1[6], d2[6];
+                if (i < j) {
+                    pair_term<true>(P, bi, beads[j], table, d1, d2);
+#pragma unroll
+                    for (int q = 0; q < 6; ++q) acc[q] += s * d1[q];
+                } else {
+                    pair_term<true>(P, beads[j], bi, table, d1, d2);
+#pragma unroll
+                    for (int q = 0; q < 6; ++q) acc[q] += s * d2[q];
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 6; ++q) acc[q] = group_sum<RG>(acc[q]);
+        if (i < P.n_bead && lane == 0) {
+            float* dst = elem_sens_ptr(P.g.s1, r, i);
+            float4 a = reinterpret_cast<float4*>(dst)[0], b = reinterpret_cast<float4*>(dst)[1];
+            a.x += acc[0]; a.y += acc[1]; a.z += acc[2]; a.w += acc[3]; b.x += acc[4]; b.y += acc[5];
+            reinterpret_cast<float4*>(dst)[0] = a;
+            reinterpret_cast<float4*>(dst)[1] = b;
+            int loc = P.g.s1.loc[i];
+            for (int p = 0; p < P.n_prob; ++p) P.prob_sens[p][(size_t(r) * P.prob_n[p] + loc) * P.prob_wp[p]] += my_marg;
+        }
+    }
+}
+
+// ================================================================================================ belief propagation
+__device__ __forceinline__ float block_max_bcast(float v, float* red) {
+    v = warp_max(v);
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     __syncthreads();
-    // ---- 4. energies -> probabilities --------------------------------------------------------------------------
-    for (int i = tid; i < nR * MAXR; i += RTPB) {
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    float m = red[0];
+    for (int k = 1; k < BP_TPB / 32; ++k) m = fmaxf(m, red[k]);
+    return m;
+}
+
+// messages of every residue pair from old beliefs and old messages, in place (rotamer.cpp:468-520): the new message to A
+// needs only the old message to B of the same pair, so one thread updates both directions of its pair without a copy
+__device__ __forceinline__ void bp_messages(const int* res_nrot, int n_pair, const unsigned short* pair_ab, const float* Pm,
+                                            const float* bel, float* msg) {
+    for (int e = threadIdx.x; e < n_pair; e += BP_TPB) {
+        int A = pair_ab[2 * e], B = pair_ab[2 * e + 1];
+        int nA = res_nrot[A], nB = res_nrot[B];
+        float v1[MAXR], v2[MAXR], m1[MAXR], m2[MAXR];
+#pragma unroll
+        for (int a = 0; a < MAXR; ++a) {
+            v1[a] = a < nA ? bel[A * MAXR + a] / (1e-10f + msg[e * 12 + a]) : 0.f;
+            v2[a] = a < nB ? bel[B * MAXR + a] / (1e-10f + msg[e * 12 + 6 + a]) : 0.f;
+            m1[a] = 0.f; m2[a] = 0.f;
+        }
+        const float* M = Pm + size_t(e) * 36;
+#pragma unroll
+        for (int a = 0; a < MAXR; ++a)
+#pragma unroll
+            for (int b = 0; b < MAXR; ++b) {
+                float p = M[a * 6 + b];            // entries outside (nA,nB) meet a zero cavity factor
+                m1[a] = fmaf(p, v2[b], m1[a]);     // apply_left : message to A
+                m2[b] = fmaf(v1[a], p, m2[b]);     // apply_right: message to B
+            }
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int a = 0; a < MAXR; ++a) { m1[a] = a < nA ? m1[a] : 0.f; m2[a] = a < nB ? m2[a] : 0.f; s1 += m1[a]; s2 += m2[a]; }
+        float i1 = 1.f / s1, i2 = 1.f / s2;
+#pragma unroll
+        for (int a = 0; a < MAXR; ++a) { msg[e * 12 + a] = m1[a] * i1; msg[e * 12 + 6 + a] = m2[a] * i2; }
+    }
+}
+
+// node update in place: belief = prob * prod(incoming messages), max-normalised and damped (rotamer.cpp:488-499,258-273)
+__device__ __forceinline__ float bp_nodes(const int* res_nrot, int n_res, const int* istart, const int* inc, const float* prob,
+                                          const float* msg, float* bel, float damping) {
+    float dev = 0.f;
+    for (int A = threadIdx.x; A < n_res; A += BP_TPB) {
+        int nA = res_nrot[A];
+        if (nA < 2) continue;
+        float b[MAXR];
+#pragma unroll
+        for (int a = 0; a < MAXR; ++a) b[a] = prob[A * MAXR + a];
+        for (int t = istart[A]; t < istart[A + 1]; ++t) {
+            int cd = inc[t];
+            const float* m = msg + (cd >> 1) * 12 + (cd & 1) * 6;
+            float s = 0.f;
+#pragma unroll
+            for (int a = 0; a < MAXR; ++a) { b[a] *= m[a]; s += b[a]; }
+            float is = 1.f / s;
+#pragma unroll
+            for (int a = 0; a < MAXR; ++a) b[a] *= is;
+        }
+        float mx = b[0];
+#pragma unroll
+        for (int a = 1; a < MAXR; ++a) mx = fmaxf(mx, b[a]);
+        float imx = 1.f / mx;
+#pragma unroll
+        for (int a = 0; a < MAXR; ++a) {
+            float o = bel[A * MAXR + a];
+            float n = (damping != 0.f) ? (1.f - damping) * imx * b[a] + damping * o : imx * b[a];
+            if (a < nA) dev = fmaxf(dev, n - o);
+            bel[A * MAXR + a] = n;
+        }
+    }
+    return dev;
+}
+
+__global__ void __launch_bounds__(BP_TPB) k_rot_bp(RotamerDev P, int want_pot) {
+    extern __shared__ float smem[];
+    const int r = blockIdx.x, tid = threadIdx.x;
+    const int nR = P.n_res;
+    const int n_pair = P.stats[size_t(r) * 4 + 1];
+    float* prob = smem;                         // [nR][6]
+    float* bel = prob + nR * MAXR;              // [nR][6]
+    float* offs = bel + nR * MAXR;              // [nR]
+    float* red = offs + nR;                     // [32]
+    int* istart = reinterpret_cast<int*>(red + 32);           // [nR+1]
+    int* nrot = istart + nR + 1;                               // [nR]
+    float* sm_msg = reinterpret_cast<float*>(nrot + nR);      // [smem_pairs][12]
+    float* sm_P = sm_msg + size_t(P.smem_pairs) * 12;         // [smem_pairs][36]
+    int* sm_inc = reinterpret_cast<int*>(sm_P + size_t(P.smem_pairs) * 36);   // [2*smem_pairs]
+    unsigned short* sm_ab = reinterpret_cast<unsigned short*>(sm_inc + 2 * P.smem_pairs);   // [2*smem_pairs]
+
+    float* g_pmat = P.pmat + size_t(r) * P.max_pairs * 36;
+    const bool in_smem = n_pair <= P.smem_pairs;
+    // replicas whose pair count exceeds the shared-memory budget run the same code on their global scratch
+    float* Pm = in_smem ? sm_P : g_pmat;
+    // messages of oversized replicas spill to the area allocated behind the node marginals
+    float* msg = in_smem ? sm_msg : P.node_marg + size_t(gridDim.x) * nR * MAXR + size_t(r) * P.max_pairs * 12;
+    const unsigned short* pair_ab = P.pair_ab + size_t(r) * P.max_pairs * 2;
+    const int* inc = P.inc + size_t(r) * 2 * P.max_pairs;
+    float* node_marg = P.node_marg + size_t(r) * nR * MAXR;
+
+    // ---- node energies -> probabilities (convert_energy_to_prob :239-256; single-state partners already folded) ----------
+    for (int i = tid; i < nR; i += BP_TPB) nrot[i] = P.res_nrot[i];
+    for (int i = tid; i <= nR; i += BP_TPB) istart[i] = P.istart[size_t(r) * (nR + 1) + i];
+    for (int i = tid; i < nR * MAXR; i += BP_TPB) bel[i] = P.enode[size_t(r) * nR * MAXR + i];   // 1-body energy
+    __syncthreads();
+    for (int A = tid; A < nR; A += BP_TPB) {   // energy offset = smallest 1-body energy
+        float m = bel[A * MAXR];
+        for (int a = 1; a < nrot[A]; ++a) m = fminf(m, bel[A * MAXR + a]);
+        offs[A] = m;
+    }
+    __syncthreads();
+    for (int i = tid; i < P.n_bead; i += BP_TPB) {
+        float f = P.fold[size_t(r) * P.n_bead + i];
+        if (f != 0.f) atomicAdd(&bel[P.bead_res[i] * MAXR + P.bead_rot[i]], f);
+    }
+    __syncthreads();
+    for (int i = tid; i < nR * MAXR; i += BP_TPB) {
         int A = i / MAXR, a = i % MAXR;
-        float p = a < P.res_nrot[A] ? __expf(offs[A] - Enode[i]) : 0.f;
+        float p = a < nrot[A] ? __expf(offs[A] - bel[i]) : 0.f;
         prob[i] = p;
-        bel0[i] = p;
     }
-    for (int i = tid; i < n_pair * 36; i += RTPB) pmat[i] = __expf(-pmat[i]);
-    for (int e = tid; e < n_pair; e += RTPB) {
-        int nA = P.res_nrot[pair_ab[2 * e]], nB = P.res_nrot[pair_ab[2 * e + 1]];
-        for (int a = 0; a < 6; ++a) { msg0[e * 12 + a] = a < nA ? 1.f : 0.f; msg0[e * 12 + 6 + a] = a < nB ? 1.f : 0.f; }
+    for (int i = tid; i < n_pair * 36; i += BP_TPB) Pm[i] = __expf(-g_pmat[i]);
+    if (in_smem) {
+        for (int i = tid; i < 2 * n_pair; i += BP_TPB) { sm_inc[i] = inc[i]; sm_ab[i] = pair_ab[i]; }
+        inc = sm_inc;
+        pair_ab = sm_ab;
     }
     __syncthreads();
-    // ---- 5. belief propagation ----------------------------------------------------------------------------------
+    for (int i = tid; i < nR * MAXR; i += BP_TPB) bel[i] = prob[i];
+    for (int e = tid; e < n_pair; e += BP_TPB) {
+        int nA = nrot[pair_ab[2 * e]], nB = nrot[pair_ab[2 * e + 1]];
+        for (int a = 0; a < 6; ++a) { msg[e * 12 + a] = a < nA ? 1.f : 0.f; msg[e * 12 + 6 + a] = a < nB ? 1.f : 0.f; }
+    }
+    __syncthreads();
+    // ---- belief propagation -----------------------------------------------------------------------------------------------
     // initial sweep: first messages from (prob, unit messages); node beliefs restart from prob/max (rotamer.cpp:1034)
-    bp_messages(P, n_pair, pair_ab, pmat, bel0, msg0, msg1);
-    for (int A = tid; A < nR; A += RTPB) {
+    bp_messages(nrot, n_pair, pair_ab, Pm, bel, msg);
+    __syncthreads();
+    for (int A = tid; A < nR; A += BP_TPB) {
         float mx = prob[A * MAXR];
         for (int a = 1; a < MAXR; ++a) mx = fmaxf(mx, prob[A * MAXR + a]);
         float imx = 1.f / mx;
-        for (int a = 0; a < MAXR; ++a) bel1[A * MAXR + a] = prob[A * MAXR + a] * imx;
+        for (int a = 0; a < MAXR; ++a) bel[A * MAXR + a] = prob[A * MAXR + a] * imx;
     }
     __syncthreads();
-    float* bel_cur = bel1; float* bel_old = bel0;
-    float* msg_cur = msg1; float* msg_old = msg0;
     float max_dev = 1e10f;
     int iter = 0;
     for (; max_dev > P.tol && iter < P.max_iter; iter += P.chunk) {
         float dev = 0.f;
         for (int j = 0; j < P.chunk; ++j) {
-            float* t = bel_cur; bel_cur = bel_old; bel_old = t;
-            t = msg_cur; msg_cur = msg_old; msg_old = t;
-            bp_messages(P, n_pair, pair_ab, pmat, bel_old, msg_old, msg_cur);
+            bp_messages(nrot, n_pair, pair_ab, Pm, bel, msg);
             __syncthreads();
-            dev = bp_nodes(P, istart, inc, prob, msg_cur, bel_old, bel_cur, P.damping);
+            dev = bp_nodes(nrot, nR, istart, inc, prob, msg, bel, P.damping);
             __syncthreads();
         }
         max_dev = block_max_bcast(dev, red);
     }
     if (tid == 0) {
         int* st = P.stats + size_t(r) * 4;
-        st[0] = iter; st[1] = n_pair; st[2] = max_dev <= P.tol;
+        st[0] = iter; st[2] = max_dev <= P.tol;
     }
-    // ---- 6. marginals (and Bethe free energy) ---------------------------------------------------------------------
-    float en = e11;
-    for (int A = tid; A < nR; A += RTPB) {
-        int nA = P.res_nrot[A];
+    // ---- marginals (and Bethe free energy) ----------------------------------------------------------------------------------
+    float en = 0.f;
+    for (int A = tid; A < nR; A += BP_TPB) {
+        int nA = nrot[A];
         float b[MAXR], s = 0.f;
-        for (int a = 0; a < MAXR; ++a) { b[a] = nA > 1 ? bel_cur[A * MAXR + a] : (a == 0 ? 1.f : 0.f); s += b[a]; }
+        for (int a = 0; a < MAXR; ++a) { b[a] = nA > 1 ? bel[A * MAXR + a] : (a == 0 ? 1.f : 0.f); s += b[a]; }
         float is = 1.f / s;
-        for (int a = 0; a < MAXR; ++a) { b[a] *= is; bel_cur[A * MAXR + a] = b[a]; node_marg[A * MAXR + a] = b[a]; }
+        for (int a = 0; a < MAXR; ++a) { b[a] *= is; bel[A * MAXR + a] = b[a]; node_marg[A * MAXR + a] = b[a]; }
         if (want_pot) {
             float e = offs[A];
             for (int a = 0; a < nA; ++a) e += b[a] * __logf((1e-10f + b[a]) / (1e-10f + prob[A * MAXR + a]));
@@ -337,15 +557,16 @@ __global__ void __launch_bounds__(RTPB) k_rotamer(RotamerDev P, int want_pot) {
         }
     }
     __syncthreads();
-    for (int e = tid; e < n_pair; e += RTPB) {
+    for (int e = tid; e < n_pair; e += BP_TPB) {
         int A = pair_ab[2 * e], Bq = pair_ab[2 * e + 1];
-        int nA = P.res_nrot[A], nB = P.res_nrot[Bq];
+        int nA = nrot[A], nB = nrot[Bq];
         float bc1[MAXR], bc2[MAXR];
         for (int a = 0; a < MAXR; ++a) {
-            bc1[a] = a < nA ? bel_cur[A * MAXR + a] / (1e-10f + msg_cur[e * 12 + a]) : 0.f;
-            bc2[a] = a < nB ? bel_cur[Bq * MAXR + a] / (1e-10f + msg_cur[e * 12 + 6 + a]) : 0.f;
+            bc1[a] = a < nA ? bel[A * MAXR + a] / (1e-10f + msg[e * 12 + a]) : 0.f;
+            bc2[a] = a < nB ? bel[Bq * MAXR + a] / (1e-10f + msg[e * 12 + 6 + a]) : 0.f;
         }
-        float* M = pmat + size_t(e) * 36;
+        const float* M = Pm + size_t(e) * 36;
+        float* out = g_pmat + size_t(e) * 36;
         float s = 0.f;
         for (int a = 0; a < nA; ++a) for (int b = 0; b < nB; ++b) s += M[a * 6 + b] * bc1[a] * bc2[b];
         float is = 1.f / s;
@@ -354,63 +575,13 @@ __global__ void __launch_bounds__(RTPB) k_rotamer(RotamerDev P, int want_pot) {
                 float pr = M[a * 6 + b];
                 float mg = (a < nA && b < nB) ? pr * bc1[a] * bc2[b] * is : 0.f;
                 if (want_pot && a < nA && b < nB)
-                    en += mg * __logf((1e-10f + mg) / (1e-10f + pr * bel_cur[A * MAXR + a] * bel_cur[Bq * MAXR + b]));
-                M[a * 6 + b] = mg;
+                    en += mg * __logf((1e-10f + mg) / (1e-10f + pr * bel[A * MAXR + a] * bel[Bq * MAXR + b]));
+                out[a * 6 + b] = mg;
             }
     }
     if (want_pot) {
         float tot = block_sum(en, red);
-        if (tid == 0) P.potential[r] = tot;
-    }
-    __syncthreads();
-    // ---- 7. backward: d/d(bead) = sum over partners of marginal * dV/d(bead); 1-body sens += node marginal ---------
-    {
-        const int grp = tid / RG, lane = tid % RG;
-        for (int i0 = 0; i0 < P.n_bead; i0 += RTPB / RG) {
-            int i = i0 + grp;
-            float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            if (i < P.n_bead) {
-                int A = P.bead_res[i], ra = P.bead_rot[i], nA = P.res_nrot[A];
-                float xi[8];
-                load8(elem_ptr(P.g.s1, r, i), xi);
-                int ti = P.g.s1.type[i];
-                const unsigned short* row = nbr + size_t(i) * P.g.K1;
-                int c = cnt[i];
-                for (int k = lane; k < c; k += RG) {
-                    int j = row[k];
-                    int Bq = P.bead_res[j], rb = P.bead_rot[j], nB = P.res_nrot[Bq];
-                    float s;
-                    if (nA > 1 && nB > 1) {
-                        if (A < Bq) s = pmat[size_t(estart[A] + rank_between(bitmap + A * nW, nW, A, Bq)) * 36 + ra * 6 + rb];
-                        else s = pmat[size_t(estart[Bq] + rank_between(bitmap + Bq * nW, nW, Bq, A)) * 36 + rb * 6 + ra];
-                    } else if (nA > 1) s = bel_cur[A * MAXR + ra];
-                    else if (nB > 1) s = bel_cur[Bq * MAXR + rb];
-                    else s = 1.f;
-                    float xj[8], d1[6], d2[6];
-                    load8(elem_ptr(P.g.s1, r, j), xj);
-                    int tj = P.g.s1.type[j];
-                    if (i < j) {
-                        quadspline_edge(P.g.param + (size_t(ti) * P.g.n_type2 + tj) * P.g.n_param, P.q, xi, xj, d1, d2);
-#pragma unroll
-                        for (int q = 0; q < 6; ++q) acc[q] += s * d1[q];
-                    } else {
-                        quadspline_edge(P.g.param + (size_t(tj) * P.g.n_type2 + ti) * P.g.n_param, P.q, xj, xi, d1, d2);
-#pragma unroll
-                        for (int q = 0; q < 6; ++q) acc[q] += s * d2[q];
-                    }
-                }
-            }
-#pragma unroll
-            for (int q = 0; q < 6; ++q) acc[q] = group_sum<RG>(acc[q]);
-            if (i < P.n_bead && lane == 0) {
-                float* dst = elem_sens_ptr(P.g.s1, r, i);
-#pragma unroll
-                for (int q = 0; q < 6; ++q) dst[q] += acc[q];
-                float m = bel_cur[P.bead_res[i] * MAXR + P.bead_rot[i]];
-                int loc = P.g.s1.loc[i];
-                for (int p = 0; p < P.n_prob; ++p) P.prob_sens[p][(size_t(r) * P.prob_n[p] + loc) * P.prob_wp[p]] += m;
-            }
-        }
+        if (tid == 0) P.potential[r] = tot + P.e11[r];
     }
 }
 
@@ -419,14 +590,14 @@ struct RotamerSidechain : PotentialNode {
     IGraphHost ig;
     int nka = 15, nk = 16;
     float knot_spacing = 0.5f;
-    int n_res = 0, n_words = 0, max_pairs = 0;
+    int n_res = 0, n_words = 0, max_pairs = 0, smem_pairs = 0, multi_bead_states = 0;
     std::vector<int> bead_res, bead_rot, res_nrot, res_key;
-    DevBuf<int> d_bead_res, d_bead_rot, d_res_nrot, inc, stats;
-    DevBuf<float> pmat, msg, node_marg;
+    DevBuf<int> d_bead_res, d_bead_rot, d_res_nrot, inc, istart, stats, code, lower;
+    DevBuf<float> pmat, node_marg, enode, fold, e11, table;
     DevBuf<unsigned short> pair_ab;
     float damping, tol;
     int max_iter, chunk;
-    size_t smem_bytes = 0;
+    size_t smem_prep = 0, smem_edge = 0, smem_bp = 0;
 
     RotamerSidechain(Engine&, const h5l::Node& g, const ArgList& args)
         : prob_nodes(args.begin() + 1, args.end()), ig(h5_child(g, "pair_interaction"), true, EXCL_ROTAMER, 6, 6, args[0], nullptr) {
@@ -442,13 +613,14 @@ struct RotamerSidechain : PotentialNode {
         else if (ig.n_param == 2 * 8 + 2 * 9) { nka = 8; nk = 9; knot_spacing = 1.f; }
         else throw "unsupported rotamer pair_interaction parameter count " + std::to_string(ig.n_param);
         ig.cutoff = float((nk - 2 - 1e-6) / double(1.f / knot_spacing));   // bead_interaction.h:191-193
-        check_compatible();
+        upload_table();
         damping = h5_attr<float>(g, ".", "damping");
         max_iter = h5_attr<int>(g, ".", "max_iter");
         tol = h5_attr<float>(g, ".", "tol");
         chunk = std::max(1, h5_attr<int>(g, ".", "iteration_chunk_size"));
         // residues = distinct (n_rot, k) in order of first appearance
         std::map<int, int> key_to_res;
+        std::map<int, int> state_count;
         for (int b = 0; b < ig.n1; ++b) {
             unsigned id = (unsigned)ig.id1[b];
             int rot = id & 15, n_rot = (id >> 4) & 15, key = id >> 4;
@@ -462,6 +634,7 @@ struct RotamerSidechain : PotentialNode {
             }
             bead_res.push_back(it->second);
             bead_rot.push_back(rot);
+            if (++state_count[it->second * 8 + rot] > 1) multi_bead_states = 1;
         }
         n_res = (int)res_nrot.size();
         n_words = (n_res + 31) / 32;
@@ -476,8 +649,9 @@ struct RotamerSidechain : PotentialNode {
         d_bead_rot.upload(bead_rot);
         d_res_nrot.upload(res_nrot);
     }
-    void check_compatible() {
-        // symmetric tables must satisfy p(t1,t2).ang1 == p(t2,t1).ang2 and equal radial parts (bead_interaction.h:209-218)
+    // symmetric tables must satisfy p(t1,t2).ang1 == p(t2,t1).ang2 and equal radial parts (bead_interaction.h:209-218);
+    // that lets the device keep only the rows t1<=t2
+    void upload_table() {
         int n = ig.n_type1, np = ig.n_param;
         if (ig.n_type1 != ig.n_type2) throw std::string("incompatible parameters");
         for (int a = 0; a < n; ++a)
@@ -489,45 +663,76 @@ struct RotamerSidechain : PotentialNode {
                 for (int k = 0; k < 2 * nk; ++k)
                     if (p1[2 * nka + k] != p2[2 * nka + k]) throw std::string("incompatible parameters");
             }
+        std::vector<float> t;
+        for (int a = 0; a < n; ++a)
+            for (int b = a; b < n; ++b) t.insert(t.end(), &ig.h_param[(size_t(a) * n + b) * np], &ig.h_param[(size_t(a) * n + b) * np] + np);
+        table.upload(t);
     }
     void finalize() override {
         ig.allocate(engine);
         size_t B = engine->n_rep;
+        int device_smem = 0;
+        UB_CUDA(cudaDeviceGetAttribute(&device_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, engine->device));
+        // BP kernel: fixed part + 204 bytes per pair; aim for two resident CTAs per SM, never more pairs than can occur
+        size_t fixed_bp = sizeof(float) * (size_t(n_res) * MAXR * 2 + n_res + 32) + sizeof(int) * (2 * n_res + 1);
+        size_t per_pair = 12 * 4 + 36 * 4 + 2 * 4 + 2 * 2;
+        size_t budget = std::min<size_t>(device_smem, 110 * 1024);
+        smem_pairs = budget > fixed_bp ? (int)std::min<size_t>(max_pairs, (budget - fixed_bp) / per_pair) : 0;
+        smem_bp = fixed_bp + size_t(smem_pairs) * per_pair + 16;
+        smem_prep = sizeof(unsigned) * size_t(n_res) * n_words + sizeof(int) * 2 * (n_res + 1) + sizeof(float) * n_res * MAXR;
+        smem_edge = sizeof(BeadRec) * size_t(ig.n1) + sizeof(float) * table.n;
+        if (smem_prep > (size_t)device_smem || smem_edge > (size_t)device_smem || fixed_bp > (size_t)device_smem)
+            throw std::string("rotamer node: system too large for the shared-memory kernels");
+        UB_CUDA(cudaFuncSetAttribute(k_rot_prep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_prep));
+        UB_CUDA(cudaFuncSetAttribute(k_rot_energy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_edge));
+        UB_CUDA(cudaFuncSetAttribute(k_rot_deriv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_edge));
+        UB_CUDA(cudaFuncSetAttribute(k_rot_bp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bp));
         pmat.alloc(B * max_pairs * 36);
-        msg.alloc(B * 2 * max_pairs * 12);
         pair_ab.alloc(B * max_pairs * 2);
         inc.alloc(B * 2 * max_pairs);
-        node_marg.alloc(B * n_res * MAXR);
+        istart.alloc(B * (n_res + 1));
+        node_marg.alloc(B * n_res * MAXR + B * size_t(max_pairs) * 12);   // + message spill area for oversized replicas
+        enode.alloc(B * n_res * MAXR);
+        fold.alloc(B * ig.n1);
+        e11.alloc(B);
         stats.alloc(B * 4);
-        smem_bytes = sizeof(float) * (size_t(n_res) * MAXR * 4 + n_res + 32) + sizeof(unsigned) * size_t(n_res) * n_words +
-                     sizeof(int) * 2 * (n_res + 1);
-        if (smem_bytes > 200 * 1024) throw std::string("rotamer node: system too large for the shared-memory BP kernel");
-        UB_CUDA(cudaFuncSetAttribute(k_rotamer, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        code.alloc(B * size_t(ig.n1) * ig.K1);
+        lower.alloc(B * ig.n1);
     }
     RotamerDev dev() {
         RotamerDev P;
         P.g = ig.dev();
         P.q.nka = nka; P.q.nk = nk; P.q.inv_dx = 1.f / knot_spacing; P.q.inv_dtheta = (nka - 3) / 2.f;
-        P.n_bead = ig.n1; P.n_res = n_res; P.n_words = n_words;
+        P.n_bead = ig.n1; P.n_res = n_res; P.n_words = n_words; P.n_type = ig.n_type1;
         P.bead_res = d_bead_res.p; P.bead_rot = d_bead_rot.p; P.res_nrot = d_res_nrot.p;
+        P.table = table.p;
         P.n_prob = (int)prob_nodes.size();
         for (int i = 0; i < P.n_prob; ++i) {
             P.prob_out[i] = prob_nodes[i]->output; P.prob_sens[i] = prob_nodes[i]->sens;
             P.prob_wp[i] = prob_nodes[i]->wp; P.prob_n[i] = prob_nodes[i]->n_elem;
         }
         P.damping = damping; P.tol = tol; P.max_iter = max_iter; P.chunk = chunk; P.max_pairs = max_pairs;
-        P.pmat = pmat.p; P.msg = msg.p; P.pair_ab = pair_ab.p; P.inc = inc.p; P.node_marg = node_marg.p; P.stats = stats.p;
+        P.smem_pairs = smem_pairs; P.multi_bead_states = multi_bead_states;
+        // split a replica's beads over several CTAs only when the batch alone cannot fill the GPU
+        P.n_chunk = std::max(1, std::min(8, 600 / std::max(1, engine->n_rep)));
+        P.code = code.p; P.lower = lower.p; P.enode = enode.p; P.fold = fold.p; P.e11 = e11.p;
+        P.pmat = pmat.p; P.pair_ab = pair_ab.p; P.inc = inc.p; P.istart = istart.p; P.node_marg = node_marg.p; P.stats = stats.p;
         P.potential = potential; P.error_flag = engine->error_flag.p;
         return P;
     }
     void compute_value(cudaStream_t s, ComputeMode mode) override {
         if (!ig.n1) return;
         ig.build(s);
-        k_rotamer<<<engine->n_rep, RTPB, smem_bytes, s>>>(dev(), mode == PotentialAndDerivMode);
+        RotamerDev P = dev();
+        int want = mode == PotentialAndDerivMode;
+        k_rot_prep<<<engine->n_rep, PREP_TPB, smem_prep, s>>>(P);
+        k_rot_energy<<<dim3(P.n_chunk, engine->n_rep), EDGE_TPB, smem_edge, s>>>(P, want);
+        k_rot_bp<<<engine->n_rep, BP_TPB, smem_bp, s>>>(P, want);
+        k_rot_deriv<<<dim3(P.n_chunk, engine->n_rep), EDGE_TPB, smem_edge, s>>>(P);
     }
     bool get_pairlist(int replica, std::vector<int>& i1, std::vector<int>& i2) override { return ig.pairlist(replica, i1, i2); }
     std::vector<float> get_param() const override { return ig.h_param; }
-    void set_param(const std::vector<float>& p) override { ig.set_param(p); check_compatible(); }
+    void set_param(const std::vector<float>& p) override { ig.set_param(p); upload_table(); }
 
     std::vector<float> get_value_by_name(int replica, const char* log_name) override {
         std::string nm(log_name);
