@@ -87,20 +87,20 @@ __device__ __forceinline__ void deboor_vd(const float* __restrict__ c, int n, fl
     int b = (int)x;
     b = max(1, min(b, n - 3));
     float y = x - (float)b;
-    deboor_core(__ldg(c + b - 1), __ldg(c + b), __ldg(c + b + 1), __ldg(c + b + 2), y, val, der);
+    deboor_core((*(c + b - 1)), (*(c + b)), (*(c + b + 1)), (*(c + b + 2)), y, val, der);
 }
 // clamped spline, Float4 flavour of the reference (spline.h:275-310): x<1 -> left value, x>=n-2 -> right value
 __device__ __forceinline__ void clamped_deboor_vd(const float* __restrict__ c, int n, float x, float& val, float& der) {
     if (x < 1.f) {
-        val = (1.f / 6.f) * __ldg(c) + (2.f / 3.f) * __ldg(c + 1) + (1.f / 6.f) * __ldg(c + 2);
+        val = (1.f / 6.f) * (*(c)) + (2.f / 3.f) * (*(c + 1)) + (1.f / 6.f) * (*(c + 2));
         der = 0.f;
     } else if (x >= (float)(n - 2)) {
-        val = (1.f / 6.f) * __ldg(c + n - 3) + (2.f / 3.f) * __ldg(c + n - 2) + (1.f / 6.f) * __ldg(c + n - 1);
+        val = (1.f / 6.f) * (*(c + n - 3)) + (2.f / 3.f) * (*(c + n - 2)) + (1.f / 6.f) * (*(c + n - 1));
         der = 0.f;
     } else {
         int b = (int)x;
         float y = x - (float)b;
-        deboor_core(__ldg(c + b - 1), __ldg(c + b), __ldg(c + b + 1), __ldg(c + b + 2), y, val, der);
+        deboor_core((*(c + b - 1)), (*(c + b)), (*(c + b + 1)), (*(c + b + 2)), y, val, der);
     }
 }
 

@@ -50,51 +50,149 @@ struct IGraphDev {
     int* error_flag;
 };
 
-// Build the ELL rows of group A against group B.  grid (ceil(nA/TILE), B), block TILE.
+// Build the ELL rows of group A against group B.  grid (ceil(nA/TILE), G), block TILE.  With rep_list == nullptr
+// blockIdx.y is the replica; otherwise the CTAs with the same blockIdx.x stride over the compacted list of replicas that
+// need their Verlet cache rebuilt (rep_list[0..*n_list)).
 template <int TILE>
 __global__ void k_pairlist(IGraphSide A, IGraphSide Bs, unsigned short* __restrict__ nbr, int* __restrict__ cnt, int K,
-                           float cutoff2, int excl, int same_group, int a_is_first, int* error_flag) {
+                           float cutoff2, int excl, int same_group, int a_is_first, int* error_flag,
+                           const int* __restrict__ rep_list, const int* __restrict__ n_list, int colmajor) {
     __shared__ float4 tile[TILE];   // x,y,z, id (bit-cast)
-    int r = blockIdx.y;
-    int i = blockIdx.x * TILE + threadIdx.x;
-    bool active = i < A.n;
-    float xi = 0.f, yi = 0.f, zi = 0.f;
-    int idi = 0;
-    if (active) {
-        const float* p = A.out + (size_t(r) * A.n_node + A.loc[i]) * A.wp;
-        xi = p[0]; yi = p[1]; zi = p[2];
-        idi = A.id[i];
-    }
-    int n = 0;
-    unsigned short* row = nbr + (size_t(r) * A.n + (active ? i : 0)) * K;
-    for (int j0 = 0; j0 < Bs.n; j0 += TILE) {
-        int j = j0 + threadIdx.x;
-        __syncthreads();
-        if (j < Bs.n) {
-            const float* p = Bs.out + (size_t(r) * Bs.n_node + Bs.loc[j]) * Bs.wp;
-            tile[threadIdx.x] = make_float4(p[0], p[1], p[2], __int_as_float(Bs.id[j]));
+    const int n_rep_todo = rep_list ? *n_list : gridDim.y;
+    for (int ridx = blockIdx.y; ridx < n_rep_todo; ridx += gridDim.y) {
+        const int r = rep_list ? rep_list[ridx] : ridx;
+        int i = blockIdx.x * TILE + threadIdx.x;
+        bool active = i < A.n;
+        float xi = 0.f, yi = 0.f, zi = 0.f;
+        int idi = 0;
+        if (active) {
+            const float* p = A.out + (size_t(r) * A.n_node + A.loc[i]) * A.wp;
+            xi = p[0]; yi = p[1]; zi = p[2];
+            idi = A.id[i];
+        }
+        int n = 0;
+        // row-major rows [i][k] for the exact tables, column-major [k][i] for the Verlet candidates (coalesced when one
+        // thread owns one row, as here and in k_refine)
+        unsigned short* row = colmajor ? nbr + size_t(r) * K * A.n + (active ? i : 0) : nbr + (size_t(r) * A.n + (active ? i : 0)) * K;
+        const size_t rstride = colmajor ? (size_t)A.n : 1;
+        for (int j0 = 0; j0 < Bs.n; j0 += TILE) {
+            int j = j0 + threadIdx.x;
+            __syncthreads();
+            if (j < Bs.n) {
+                const float* p = Bs.out + (size_t(r) * Bs.n_node + Bs.loc[j]) * Bs.wp;
+                tile[threadIdx.x] = make_float4(p[0], p[1], p[2], __int_as_float(Bs.id[j]));
+            }
+            __syncthreads();
+            if (!active) continue;
+            int jn = min(TILE, Bs.n - j0);
+            for (int jj = 0; jj < jn; ++jj) {
+                float4 t = tile[jj];
+                // pos1 - pos2 with group 1 first, as in the reference refine step; squares make the order immaterial
+                float dx = a_is_first ? xi - t.x : t.x - xi;
+                float dy = a_is_first ? yi - t.y : t.y - yi;
+                float dz = a_is_first ? zi - t.z : t.z - zi;
+                float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+                bool hit = d2 < cutoff2 && acceptable_id_pair(excl, idi, __float_as_int(t.w)) && !(same_group && (j0 + jj) == i);
+                if (hit) {
+                    if (n < K) row[n * rstride] = (unsigned short)(j0 + jj);
+                    ++n;
+                }
+            }
+        }
+        if (active) {
+            if (n > K) { atomicExch(error_flag, 1); n = K; }
+            cnt[size_t(r) * A.n + i] = n;
         }
         __syncthreads();
-        if (!active) continue;
-        int jn = min(TILE, Bs.n - j0);
-        for (int jj = 0; jj < jn; ++jj) {
-            float4 t = tile[jj];
-            // pos1 - pos2 with group 1 first, as in the reference refine step; squares make the order immaterial
-            float dx = a_is_first ? xi - t.x : t.x - xi;
-            float dy = a_is_first ? yi - t.y : t.y - yi;
-            float dz = a_is_first ? zi - t.z : t.z - zi;
-            float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-            bool hit = d2 < cutoff2 && acceptable_id_pair(excl, idi, __float_as_int(t.w)) && !(same_group && (j0 + jj) == i);
-            if (hit) {
-                if (n < K) row[n] = (unsigned short)(j0 + jj);
-                ++n;
+    }
+}
+
+// Verlet cache (reference PairlistComputation::ensure_cache_valid, interaction_graph.h:51-168): candidate rows are built
+// with cutoff + skin and reused until some element has moved more than skin/2 from where it was at build time.
+// k_cache_check: one CTA per replica; sets flag[r], appends r to the rebuild list and refreshes the cached positions.
+static __global__ void k_cache_check(IGraphSide A, IGraphSide Bs, int two_groups, float* __restrict__ cposA, float* __restrict__ cposB,
+                              float max_move2, int* __restrict__ flag, int* __restrict__ rep_list, int* __restrict__ n_list) {
+    __shared__ int moved;
+    const int r = blockIdx.x;
+    if (threadIdx.x == 0) moved = flag[r] == 2;   // 2 = never built
+    __syncthreads();
+    for (int pass = 0; pass < (two_groups ? 2 : 1); ++pass) {
+        const IGraphSide& S = pass ? Bs : A;
+        const float4* c = reinterpret_cast<const float4*>(pass ? cposB : cposA) + size_t(r) * S.n;
+        for (int i = threadIdx.x; i < S.n; i += blockDim.x) {
+            const float* p = S.out + (size_t(r) * S.n_node + S.loc[i]) * S.wp;
+            float4 q = c[i];
+            float dx = p[0] - q.x, dy = p[1] - q.y, dz = p[2] - q.z;
+            if (max_move2 < dx * dx + dy * dy + dz * dz) moved = 1;
+        }
+    }
+    __syncthreads();
+    if (moved) {
+        for (int pass = 0; pass < (two_groups ? 2 : 1); ++pass) {
+            const IGraphSide& S = pass ? Bs : A;
+            float4* c = reinterpret_cast<float4*>(pass ? cposB : cposA) + size_t(r) * S.n;
+            for (int i = threadIdx.x; i < S.n; i += blockDim.x) {
+                const float* p = S.out + (size_t(r) * S.n_node + S.loc[i]) * S.wp;
+                c[i] = make_float4(p[0], p[1], p[2], 0.f);
             }
         }
     }
-    if (active) {
-        if (n > K) { atomicExch(error_flag, 1); n = K; }
-        cnt[size_t(r) * A.n + i] = n;
+    if (threadIdx.x == 0) {
+        flag[r] = moved ? 1 : 0;
+        if (moved) rep_list[atomicAdd(n_list, 1)] = r;
     }
+}
+
+// k_refine: exact rows from candidate rows with the reference's refine predicate (interaction_graph.h:223-244).  One CTA
+// per replica stages the positions of both groups in shared memory, then G lanes walk each candidate row (ballot
+// compaction keeps the ascending order); for an asymmetric graph the transposed table is refined in the same launch.
+struct RefineTable { const unsigned short* cand; const int* ccnt; int Kc; unsigned short* nbr; int* cnt; int K; };
+
+// one thread per candidate row (column-major candidates => coalesced), sequential compaction keeps the ascending order
+template <int G>
+__device__ __forceinline__ void refine_rows(int r, int nA, const float4* posA, const float4* posB, RefineTable T, float cutoff2,
+                                            int a_is_first, int* error_flag) {
+    for (int i = threadIdx.x; i < nA; i += blockDim.x) {
+        const float4 pi = posA[i];
+        const int c = T.ccnt[size_t(r) * nA + i];
+        const unsigned short* ccol = T.cand + size_t(r) * T.Kc * nA + i;
+        unsigned short* row = T.nbr + (size_t(r) * nA + i) * T.K;
+        int n = 0;
+        for (int k = 0; k < c; ++k) {
+            int j = ccol[size_t(k) * nA];
+            float4 pj = posB[j];
+            float dx = a_is_first ? pi.x - pj.x : pj.x - pi.x;
+            float dy = a_is_first ? pi.y - pj.y : pj.y - pi.y;
+            float dz = a_is_first ? pi.z - pj.z : pj.z - pi.z;
+            float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+            if (d2 < cutoff2) {
+                if (n < T.K) row[n] = (unsigned short)j;
+                ++n;
+            }
+        }
+        if (n > T.K) { atomicExch(error_flag, 1); n = T.K; }
+        T.cnt[size_t(r) * nA + i] = n;
+    }
+}
+
+template <int G>
+__global__ void k_refine(IGraphSide A, IGraphSide Bs, int two_groups, RefineTable T1, RefineTable T2, float cutoff2, int* error_flag) {
+    extern __shared__ float4 sm_pos[];
+    const int r = blockIdx.x;
+    float4* posA = sm_pos;
+    float4* posB = two_groups ? sm_pos + A.n : sm_pos;
+    for (int i = threadIdx.x; i < A.n; i += blockDim.x) {
+        const float* p = A.out + (size_t(r) * A.n_node + A.loc[i]) * A.wp;
+        posA[i] = make_float4(p[0], p[1], p[2], 0.f);
+    }
+    if (two_groups)
+        for (int i = threadIdx.x; i < Bs.n; i += blockDim.x) {
+            const float* p = Bs.out + (size_t(r) * Bs.n_node + Bs.loc[i]) * Bs.wp;
+            posB[i] = make_float4(p[0], p[1], p[2], 0.f);
+        }
+    __syncthreads();
+    refine_rows<G>(r, A.n, posA, posB, T1, cutoff2, 1, error_flag);
+    if (two_groups) refine_rows<G>(r, Bs.n, posB, posA, T2, cutoff2, 0, error_flag);
 }
 
 // ---- element loads ------------------------------------------------------------------------------------
@@ -170,7 +268,7 @@ __device__ __forceinline__ float protein_hbond_edge(const float* __restrict__ p,
     f3 dH = mk3(0.f, 0.f, 0.f), drHN = dH, drOC = dH;
     float hb = 0.f;
     if (dotHOC > 0.f && dotOHN > 0.f) {
-        float p0 = __ldg(p), p1 = __ldg(p + 1), p2 = __ldg(p + 2), p3 = __ldg(p + 3), p4 = __ldg(p + 4), p5 = __ldg(p + 5);
+        float p0 = (*(p)), p1 = (*(p + 1)), p2 = (*(p + 2)), p3 = (*(p + 3)), p4 = (*(p + 4)), p5 = (*(p + 5));
         float ov, od, iv, id_;
         sigmoid_vd((p2 - mHO) * p3, ov, od);   // outer
         sigmoid_vd((mHO - p0) * p1, iv, id_);  // inner
@@ -204,7 +302,7 @@ __device__ __forceinline__ float environment_edge(const float* __restrict__ p, c
     float inv_dist = rsqrtf(dist2);
     float dist = dist2 * inv_dist;
     f3 u = inv_dist * displace;
-    float r0 = __ldg(p), r_sharp = __ldg(p + 1), dot0 = __ldg(p + 2), dot_sharp = __ldg(p + 3);
+    float r0 = (*(p)), r_sharp = (*(p + 1)), dot0 = (*(p + 2)), dot_sharp = (*(p + 3));
     float dp = dot(u, rvec1);
     float rv, rd, av, ad;
     compact_sigmoid(dist - r0, r_sharp, rv, rd);
@@ -233,6 +331,13 @@ struct IGraphHost {
     DevBuf<unsigned short> nbr1, nbr2;
     DevBuf<int> cnt1, cnt2;
     int K1 = 0, K2 = 0;
+    // Verlet cache: candidate rows (cutoff + skin), positions at build time, per-replica rebuild flag + compacted list
+    bool use_cache = true;
+    float skin = 0.f;
+    DevBuf<unsigned short> cand1, cand2;
+    DevBuf<int> ccnt1, ccnt2, flag, rep_list, n_list;
+    DevBuf<float> cpos1, cpos2;
+    int Kc1 = 0, Kc2 = 0;
     Engine* engine = nullptr;
 
     // reads index/type/id(+1/2) and interaction_param (n_type1,n_type2,n_param): interaction_graph.h:305-381

@@ -128,7 +128,7 @@ struct BackbonePairs : PotentialNode {
         IGraphSide S = side();
         constexpr int TILE = 128;
         k_pairlist<TILE><<<dim3((n_residue + TILE - 1) / TILE, engine->n_rep), TILE, 0, s>>>(
-            S, S, nbr.p, cnt.p, K, dist_cutoff * dist_cutoff, EXCL_SEQ1, 1, 1, engine->error_flag.p);
+            S, S, nbr.p, cnt.p, K, dist_cutoff * dist_cutoff, EXCL_SEQ1, 1, 1, engine->error_flag.p, nullptr, nullptr, 0);
         k_bb_atoms<<<dim3((n_residue + TPB - 1) / TPB, engine->n_rep), TPB, 0, s>>>(alignment.output, atoms.p, d_residue.p,
                                                                                     d_ref.p, n_residue, alignment.n_elem);
         k_backbone_pairs<<<dim3((n_residue * G + TPB - 1) / TPB, engine->n_rep), TPB, 0, s>>>(

@@ -61,6 +61,23 @@ void IGraphHost::allocate(Engine* e) {
         nbr2.alloc(size_t(e->n_rep) * n2 * K2);
         cnt2.alloc(size_t(e->n_rep) * n2);
     }
+    if (const char* s = getenv("UPSIDE_B200_NO_VERLET_CACHE")) use_cache = atoi(s) == 0;
+    if (use_cache) {
+        skin = 1.0f + 0.2f * cutoff;   // cache_buffer of the reference, interaction_graph.h:395-396
+        Kc1 = neighbor_capacity(cutoff + skin, n2);
+        Kc2 = symmetric ? Kc1 : neighbor_capacity(cutoff + skin, n1);
+        cand1.alloc(size_t(e->n_rep) * n1 * Kc1);
+        ccnt1.alloc(size_t(e->n_rep) * n1);
+        cpos1.alloc(size_t(e->n_rep) * n1 * 4);
+        if (!symmetric) {
+            cand2.alloc(size_t(e->n_rep) * n2 * Kc2);
+            ccnt2.alloc(size_t(e->n_rep) * n2);
+            cpos2.alloc(size_t(e->n_rep) * n2 * 4);
+        }
+        flag.upload(std::vector<int>(e->n_rep, 2));   // 2 = never built
+        rep_list.alloc(e->n_rep);
+        n_list.alloc(1);
+    }
 }
 
 IGraphDev IGraphHost::dev() const {
@@ -80,12 +97,32 @@ IGraphDev IGraphHost::dev() const {
 void IGraphHost::build(cudaStream_t s) {
     IGraphDev d = dev();
     constexpr int TILE = 128;
+    constexpr int RGL = 8;
     if (!n1 || !n2) return;
-    k_pairlist<TILE><<<dim3((n1 + TILE - 1) / TILE, engine->n_rep), TILE, 0, s>>>(d.s1, d.s2, d.nbr1, d.cnt1, d.K1, d.cutoff2,
-                                                                                   d.excl, symmetric, 1, d.error_flag);
+    const int B = engine->n_rep;
+    if (!use_cache) {
+        k_pairlist<TILE><<<dim3((n1 + TILE - 1) / TILE, B), TILE, 0, s>>>(d.s1, d.s2, d.nbr1, d.cnt1, d.K1, d.cutoff2, d.excl,
+                                                                          symmetric, 1, d.error_flag, nullptr, nullptr, 0);
+        if (!symmetric)
+            k_pairlist<TILE><<<dim3((n2 + TILE - 1) / TILE, B), TILE, 0, s>>>(d.s2, d.s1, d.nbr2, d.cnt2, d.K2, d.cutoff2, d.excl,
+                                                                              0, 0, d.error_flag, nullptr, nullptr, 0);
+        return;
+    }
+    const float cc = cutoff + skin;
+    const float max_move2 = (0.5f * skin) * (0.5f * skin);
+    UB_CUDA(cudaMemsetAsync(n_list.p, 0, sizeof(int), s));
+    k_cache_check<<<B, 128, 0, s>>>(d.s1, d.s2, symmetric ? 0 : 1, cpos1.p, cpos2.p, max_move2, flag.p, rep_list.p, n_list.p);
+    // rebuilds touch only the flagged replicas: a modest grid strides over the compacted list
+    const int gy = std::min(B, 592);
+    k_pairlist<TILE><<<dim3((n1 + TILE - 1) / TILE, gy), TILE, 0, s>>>(d.s1, d.s2, cand1.p, ccnt1.p, Kc1, cc * cc, d.excl, symmetric,
+                                                                       1, d.error_flag, rep_list.p, n_list.p, 1);
     if (!symmetric)
-        k_pairlist<TILE><<<dim3((n2 + TILE - 1) / TILE, engine->n_rep), TILE, 0, s>>>(d.s2, d.s1, d.nbr2, d.cnt2, d.K2,
-                                                                                       d.cutoff2, d.excl, 0, 0, d.error_flag);
+        k_pairlist<TILE><<<dim3((n2 + TILE - 1) / TILE, gy), TILE, 0, s>>>(d.s2, d.s1, cand2.p, ccnt2.p, Kc2, cc * cc, d.excl, 0, 0,
+                                                                           d.error_flag, rep_list.p, n_list.p, 1);
+    RefineTable T1{cand1.p, ccnt1.p, Kc1, d.nbr1, d.cnt1, d.K1};
+    RefineTable T2{cand2.p, ccnt2.p, Kc2, symmetric ? nullptr : d.nbr2, symmetric ? nullptr : d.cnt2, d.K2};
+    size_t smem = sizeof(float4) * size_t(symmetric ? n1 : n1 + n2);
+    k_refine<RGL><<<B, 256, smem, s>>>(d.s1, d.s2, symmetric ? 0 : 1, T1, T2, d.cutoff2, d.error_flag);
 }
 
 bool IGraphHost::pairlist(int replica, std::vector<int>& i1, std::vector<int>& i2) {
@@ -229,238 +266,6 @@ struct ProteinHBond : CoordNode {
     void set_param(const std::vector<float>& p) override { ig.set_param(p); }
 };
 RegisterNodeType<ProteinHBond, 1> protein_hbond_node("protein_hbond");
-
-// ================================================================================================ HBondCoverage
-// forward: per bead (group 2) sum of the coverage of every H/O site (group 1) in range
-__global__ void k_hbond_coverage(IGraphDev g, QuadSplineShape q, float* __restrict__ out) {
-    int r = blockIdx.y;
-    int j = (blockIdx.x * blockDim.x + threadIdx.x) / G, lane = threadIdx.x % G;
-    bool active = j < g.s2.n;
-    float acc = 0.f;
-    if (active) {
-        float x2[8];
-        load8(elem_ptr(g.s2, r, j), x2);
-        int t2 = g.s2.type[j];
-        const unsigned short* row = g.nbr2 + (size_t(r) * g.s2.n + j) * g.K2;
-        int cnt = g.cnt2[size_t(r) * g.s2.n + j];
-        for (int k = lane; k < cnt; k += G) {
-            int i = row[k];
-            float x1[8], d1[7], d2[6];
-            load8(elem_ptr(g.s1, r, i), x1);
-            acc += hbond_coverage_edge(g.param + (size_t(g.s1.type[i]) * g.n_type2 + t2) * g.n_param, q, x1, x2, d1, d2);
-        }
-    }
-    acc = group_sum<G>(acc);
-    if (active && lane == 0) out[size_t(r) * g.s2.n + j] = acc;
-}
-// backward, bead side: sens[j] * sum_i dV/d(bead j)
-__global__ void k_hbond_coverage_deriv2(IGraphDev g, QuadSplineShape q, const float* __restrict__ sens) {
-    int r = blockIdx.y;
-    int j = (blockIdx.x * blockDim.x + threadIdx.x) / G, lane = threadIdx.x % G;
-    bool active = j < g.s2.n;
-    float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    float sj = 0.f;
-    if (active) {
-        sj = sens[size_t(r) * g.s2.n + j];
-        float x2[8];
-        load8(elem_ptr(g.s2, r, j), x2);
-        int t2 = g.s2.type[j];
-        const unsigned short* row = g.nbr2 + (size_t(r) * g.s2.n + j) * g.K2;
-        int cnt = (sj != 0.f) ? g.cnt2[size_t(r) * g.s2.n + j] : 0;
-        for (int k = lane; k < cnt; k += G) {
-            int i = row[k];
-            float x1[8], d1[7], d2[6];
-            load8(elem_ptr(g.s1, r, i), x1);
-            hbond_coverage_edge(g.param + (size_t(g.s1.type[i]) * g.n_type2 + t2) * g.n_param, q, x1, x2, d1, d2);
-#pragma unroll
-            for (int c = 0; c < 6; ++c) acc[c] += d2[c];
-        }
-    }
-#pragma unroll
-    for (int c = 0; c < 6; ++c) acc[c] = group_sum<G>(acc[c]);
-    if (active && lane == 0) {
-        float* dst = elem_sens_ptr(g.s2, r, j);
-#pragma unroll
-        for (int c = 0; c < 6; ++c) dst[c] += sj * acc[c];
-    }
-}
-// backward, site side: sum_j sens[j] * dV/d(site i)   (7 components, the last is d/d hb)
-__global__ void k_hbond_coverage_deriv1(IGraphDev g, QuadSplineShape q, const float* __restrict__ sens) {
-    int r = blockIdx.y;
-    int i = (blockIdx.x * blockDim.x + threadIdx.x) / G, lane = threadIdx.x % G;
-    bool active = i < g.s1.n;
-    float acc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    if (active) {
-        float x1[8];
-        load8(elem_ptr(g.s1, r, i), x1);
-        int t1 = g.s1.type[i];
-        const unsigned short* row = g.nbr1 + (size_t(r) * g.s1.n + i) * g.K1;
-        int cnt = g.cnt1[size_t(r) * g.s1.n + i];
-        for (int k = lane; k < cnt; k += G) {
-            int j = row[k];
-            float sj = sens[size_t(r) * g.s2.n + j];
-            float x2[8], d1[7], d2[6];
-            load8(elem_ptr(g.s2, r, j), x2);
-            hbond_coverage_edge(g.param + (size_t(t1) * g.n_type2 + g.s2.type[j]) * g.n_param, q, x1, x2, d1, d2);
-#pragma unroll
-            for (int c = 0; c < 7; ++c) acc[c] += sj * d1[c];
-        }
-    }
-#pragma unroll
-    for (int c = 0; c < 7; ++c) acc[c] = group_sum<G>(acc[c]);
-    if (active && lane == 0) {
-        float* dst = elem_sens_ptr(g.s1, r, i);
-#pragma unroll
-        for (int c = 0; c < 7; ++c) dst[c] += acc[c];
-    }
-}
-struct HBondCoverage : CoordNode {
-    IGraphHost ig;
-    int nka = 15, nk = 12;
-    float knot_spacing = 0.5f;
-    HBondCoverage(Engine&, const h5l::Node& g, CoordNode& hb, CoordNode& sc)
-        : CoordNode((int)h5_dims(g, "index2", 1)[0], 1), ig(g, false, EXCL_SEQ2, 7, 6, &hb, &sc) {
-        if (hb.wp != 8 || sc.wp != 8) throw std::string("hbond_coverage expects 8-float rows on both arguments");
-        // knot counts are compile-time in the reference (bead_interaction.h:12-27); here they follow the table shape:
-        // n_param = 2*n_knot_angular + 2*n_knot_radial with (angular, radial, spacing) of the three reference builds
-        if (ig.n_param == 2 * 15 + 2 * 12) { nka = 15; nk = 12; knot_spacing = 0.5f; }
-        else if (ig.n_param == 2 * 8 + 2 * 12) { nka = 8; nk = 12; knot_spacing = 1.f; }
-        else if (ig.n_param == 2 * 8 + 2 * 7) { nka = 8; nk = 7; knot_spacing = 1.f; }
-        else throw "unsupported hbond_coverage parameter count " + std::to_string(ig.n_param);
-        ig.cutoff = float((nk - 2 - 1e-6) / double(1.f / knot_spacing));   // hbond.cpp:250-252
-    }
-    void finalize() override { ig.allocate(engine); }
-    QuadSplineShape shape() const { QuadSplineShape q; q.nka = nka; q.nk = nk; q.inv_dx = 1.f / knot_spacing; q.inv_dtheta = (nka - 3) / 2.f; return q; }
-    void compute_value(cudaStream_t s, ComputeMode) override {
-        if (!n_elem) return;
-        ig.build(s);
-        k_hbond_coverage<<<group_grid(ig.n2, engine->n_rep), TPB, 0, s>>>(ig.dev(), shape(), output);
-    }
-    void propagate_deriv(cudaStream_t s) override {
-        if (!n_elem) return;
-        k_hbond_coverage_deriv2<<<group_grid(ig.n2, engine->n_rep), TPB, 0, s>>>(ig.dev(), shape(), sens);
-        if (ig.n1) k_hbond_coverage_deriv1<<<group_grid(ig.n1, engine->n_rep), TPB, 0, s>>>(ig.dev(), shape(), sens);
-    }
-    bool get_pairlist(int replica, std::vector<int>& i1, std::vector<int>& i2) override { return ig.pairlist(replica, i1, i2); }
-    std::vector<float> get_param() const override { return ig.h_param; }
-    void set_param(const std::vector<float>& p) override { ig.set_param(p); }
-    std::vector<float> get_value_by_name(int replica, const char* nm) override {
-        if (std::string(nm) == "count_edges_by_type") return ig.count_edges_by_type(replica);
-        throw std::string("Value ") + nm + " not implemented";
-    }
-};
-RegisterNodeType<HBondCoverage, 2> coverage_node("hbond_coverage");
-
-// ================================================================================================ EnvironmentCoverage
-__global__ void k_env_coverage(IGraphDev g, float* __restrict__ out) {
-    int r = blockIdx.y;
-    int i = (blockIdx.x * blockDim.x + threadIdx.x) / G, lane = threadIdx.x % G;
-    bool active = i < g.s1.n;
-    float acc = 0.f;
-    if (active) {
-        float x1[8];
-        load8(elem_ptr(g.s1, r, i), x1);
-        const float* p = g.param + size_t(g.s1.type[i]) * g.n_type2 * g.n_param;
-        const unsigned short* row = g.nbr1 + (size_t(r) * g.s1.n + i) * g.K1;
-        int cnt = g.cnt1[size_t(r) * g.s1.n + i];
-        for (int k = lane; k < cnt; k += G) {
-            int j = row[k];
-            float4 v = *reinterpret_cast<const float4*>(elem_ptr(g.s2, r, j));
-            float x2[4] = {v.x, v.y, v.z, v.w}, d1[6], d2[4];
-            acc += environment_edge(p + size_t(g.s2.type[j]) * g.n_param, x1, x2, d1, d2);
-        }
-    }
-    acc = group_sum<G>(acc);
-    if (active && lane == 0) out[size_t(r) * g.s1.n + i] = acc;
-}
-__global__ void k_env_coverage_deriv1(IGraphDev g, const float* __restrict__ sens) {
-    int r = blockIdx.y;
-    int i = (blockIdx.x * blockDim.x + threadIdx.x) / G, lane = threadIdx.x % G;
-    bool active = i < g.s1.n;
-    float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    float si = 0.f;
-    if (active) {
-        si = sens[size_t(r) * g.s1.n + i];
-        float x1[8];
-        load8(elem_ptr(g.s1, r, i), x1);
-        const float* p = g.param + size_t(g.s1.type[i]) * g.n_type2 * g.n_param;
-        const unsigned short* row = g.nbr1 + (size_t(r) * g.s1.n + i) * g.K1;
-        int cnt = (si != 0.f) ? g.cnt1[size_t(r) * g.s1.n + i] : 0;
-        for (int k = lane; k < cnt; k += G) {
-            int j = row[k];
-            float4 v = *reinterpret_cast<const float4*>(elem_ptr(g.s2, r, j));
-            float x2[4] = {v.x, v.y, v.z, v.w}, d1[6], d2[4];
-            environment_edge(p + size_t(g.s2.type[j]) * g.n_param, x1, x2, d1, d2);
-#pragma unroll
-            for (int c = 0; c < 6; ++c) acc[c] += d1[c];
-        }
-    }
-#pragma unroll
-    for (int c = 0; c < 6; ++c) acc[c] = group_sum<G>(acc[c]);
-    if (active && lane == 0) {
-        float* dst = elem_sens_ptr(g.s1, r, i);
-#pragma unroll
-        for (int c = 0; c < 6; ++c) dst[c] += si * acc[c];
-    }
-}
-__global__ void k_env_coverage_deriv2(IGraphDev g, const float* __restrict__ sens) {
-    int r = blockIdx.y;
-    int j = (blockIdx.x * blockDim.x + threadIdx.x) / G, lane = threadIdx.x % G;
-    bool active = j < g.s2.n;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    if (active) {
-        float4 v = *reinterpret_cast<const float4*>(elem_ptr(g.s2, r, j));
-        float x2[4] = {v.x, v.y, v.z, v.w};
-        int t2 = g.s2.type[j];
-        const unsigned short* row = g.nbr2 + (size_t(r) * g.s2.n + j) * g.K2;
-        int cnt = g.cnt2[size_t(r) * g.s2.n + j];
-        for (int k = lane; k < cnt; k += G) {
-            int i = row[k];
-            float si = sens[size_t(r) * g.s1.n + i];
-            float x1[8], d1[6], d2[4];
-            load8(elem_ptr(g.s1, r, i), x1);
-            environment_edge(g.param + (size_t(g.s1.type[i]) * g.n_type2 + t2) * g.n_param, x1, x2, d1, d2);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) acc[c] += si * d2[c];
-        }
-    }
-#pragma unroll
-    for (int c = 0; c < 4; ++c) acc[c] = group_sum<G>(acc[c]);
-    if (active && lane == 0) {
-        float* dst = elem_sens_ptr(g.s2, r, j);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) dst[c] += acc[c];
-    }
-}
-struct EnvironmentCoverage : CoordNode {
-    IGraphHost ig;
-    EnvironmentCoverage(Engine&, const h5l::Node& g, CoordNode& cb, CoordNode& wsc)
-        : CoordNode((int)h5_dims(g, "index1", 1)[0], 1), ig(g, false, EXCL_SEQ2, 6, 4, &cb, &wsc) {
-        if (ig.n_param != 4) throw std::string("environment_coverage expects 4 interaction parameters");
-        if (cb.wp != 8 || wsc.wp != 4) throw std::string("environment_coverage expects (8,4)-float rows");
-        update_cutoff();
-    }
-    void update_cutoff() {
-        float c = 0.f;   // environment.cpp:18-20 with compact_sigmoid_cutoff = 1/sharpness
-        for (int t = 0; t < ig.n_type1 * ig.n_type2; ++t) c = std::max(c, ig.h_param[t * 4 + 0] + 1.f / ig.h_param[t * 4 + 1]);
-        ig.cutoff = c;
-    }
-    void finalize() override { ig.allocate(engine); }
-    void compute_value(cudaStream_t s, ComputeMode) override {
-        if (!n_elem) return;
-        ig.build(s);
-        k_env_coverage<<<group_grid(ig.n1, engine->n_rep), TPB, 0, s>>>(ig.dev(), output);
-    }
-    void propagate_deriv(cudaStream_t s) override {
-        if (!n_elem) return;
-        k_env_coverage_deriv1<<<group_grid(ig.n1, engine->n_rep), TPB, 0, s>>>(ig.dev(), sens);
-        if (ig.n2) k_env_coverage_deriv2<<<group_grid(ig.n2, engine->n_rep), TPB, 0, s>>>(ig.dev(), sens);
-    }
-    bool get_pairlist(int replica, std::vector<int>& i1, std::vector<int>& i2) override { return ig.pairlist(replica, i1, i2); }
-    std::vector<float> get_param() const override { return ig.h_param; }
-    void set_param(const std::vector<float>& p) override { ig.set_param(p); }   // cutoff change needs a new engine
-};
-RegisterNodeType<EnvironmentCoverage, 2> environment_coverage_node("environment_coverage");
 
 }  // namespace
 }  // namespace ub

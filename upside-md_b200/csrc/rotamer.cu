@@ -388,41 +388,45 @@ __device__ __forceinline__ float block_max_bcast(float v, float* red) {
     return m;
 }
 
+// Pair matrices and messages are addressed as (pair e, component k) -> e*se + k*sk: component-major in shared memory
+// (se=1: consecutive threads = consecutive pairs hit consecutive banks), pair-major in the global spill area (sk=1).
+struct Lay { int se, sk; };
+__device__ __forceinline__ int at(const Lay& l, int e, int k) { return e * l.se + k * l.sk; }
+
 // messages of every residue pair from old beliefs and old messages, in place (rotamer.cpp:468-520): the new message to A
 // needs only the old message to B of the same pair, so one thread updates both directions of its pair without a copy
 __device__ __forceinline__ void bp_messages(const int* res_nrot, int n_pair, const unsigned short* pair_ab, const float* Pm,
-                                            const float* bel, float* msg) {
+                                            Lay lp, const float* bel, float* msg, Lay lm) {
     for (int e = threadIdx.x; e < n_pair; e += BP_TPB) {
         int A = pair_ab[2 * e], B = pair_ab[2 * e + 1];
         int nA = res_nrot[A], nB = res_nrot[B];
         float v1[MAXR], v2[MAXR], m1[MAXR], m2[MAXR];
 #pragma unroll
         for (int a = 0; a < MAXR; ++a) {
-            v1[a] = a < nA ? bel[A * MAXR + a] / (1e-10f + msg[e * 12 + a]) : 0.f;
-            v2[a] = a < nB ? bel[B * MAXR + a] / (1e-10f + msg[e * 12 + 6 + a]) : 0.f;
+            v1[a] = a < nA ? __fdividef(bel[A * MAXR + a], 1e-10f + msg[at(lm, e, a)]) : 0.f;
+            v2[a] = a < nB ? __fdividef(bel[B * MAXR + a], 1e-10f + msg[at(lm, e, 6 + a)]) : 0.f;
             m1[a] = 0.f; m2[a] = 0.f;
         }
-        const float* M = Pm + size_t(e) * 36;
 #pragma unroll
         for (int a = 0; a < MAXR; ++a)
 #pragma unroll
             for (int b = 0; b < MAXR; ++b) {
-                float p = M[a * 6 + b];            // entries outside (nA,nB) meet a zero cavity factor
-                m1[a] = fmaf(p, v2[b], m1[a]);     // apply_left : message to A
-                m2[b] = fmaf(v1[a], p, m2[b]);     // apply_right: message to B
+                float p = Pm[at(lp, e, a * 6 + b)];   // entries outside (nA,nB) meet a zero cavity factor
+                m1[a] = fmaf(p, v2[b], m1[a]);         // apply_left : message to A
+                m2[b] = fmaf(v1[a], p, m2[b]);         // apply_right: message to B
             }
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int a = 0; a < MAXR; ++a) { m1[a] = a < nA ? m1[a] : 0.f; m2[a] = a < nB ? m2[a] : 0.f; s1 += m1[a]; s2 += m2[a]; }
-        float i1 = 1.f / s1, i2 = 1.f / s2;
+        float i1 = __fdividef(1.f, s1), i2 = __fdividef(1.f, s2);
 #pragma unroll
-        for (int a = 0; a < MAXR; ++a) { msg[e * 12 + a] = m1[a] * i1; msg[e * 12 + 6 + a] = m2[a] * i2; }
+        for (int a = 0; a < MAXR; ++a) { msg[at(lm, e, a)] = m1[a] * i1; msg[at(lm, e, 6 + a)] = m2[a] * i2; }
     }
 }
 
 // node update in place: belief = prob * prod(incoming messages), max-normalised and damped (rotamer.cpp:488-499,258-273)
 __device__ __forceinline__ float bp_nodes(const int* res_nrot, int n_res, const int* istart, const int* inc, const float* prob,
-                                          const float* msg, float* bel, float damping) {
+                                          const float* msg, Lay lm, float* bel, float damping) {
     float dev = 0.f;
     for (int A = threadIdx.x; A < n_res; A += BP_TPB) {
         int nA = res_nrot[A];
@@ -430,20 +434,25 @@ __device__ __forceinline__ float bp_nodes(const int* res_nrot, int n_res, const 
         float b[MAXR];
 #pragma unroll
         for (int a = 0; a < MAXR; ++a) b[a] = prob[A * MAXR + a];
-        for (int t = istart[A]; t < istart[A + 1]; ++t) {
+        int t0 = istart[A], t1 = istart[A + 1];
+        for (int t = t0; t < t1; ++t) {
             int cd = inc[t];
-            const float* m = msg + (cd >> 1) * 12 + (cd & 1) * 6;
+            int e = cd >> 1, k0 = (cd & 1) * 6;
             float s = 0.f;
 #pragma unroll
-            for (int a = 0; a < MAXR; ++a) { b[a] *= m[a]; s += b[a]; }
-            float is = 1.f / s;
+            for (int a = 0; a < MAXR; ++a) { b[a] *= msg[at(lm, e, k0 + a)]; s += b[a]; }
+            // renormalise (pure rescaling, rotamer.cpp:492-493) often enough that a product of <=4 L1-normalised
+            // messages cannot underflow
+            if (((t - t0) & 3) == 3 || t == t1 - 1) {
+                float is = __fdividef(1.f, s);
 #pragma unroll
-            for (int a = 0; a < MAXR; ++a) b[a] *= is;
+                for (int a = 0; a < MAXR; ++a) b[a] *= is;
+            }
         }
         float mx = b[0];
 #pragma unroll
         for (int a = 1; a < MAXR; ++a) mx = fmaxf(mx, b[a]);
-        float imx = 1.f / mx;
+        float imx = __fdividef(1.f, mx);
 #pragma unroll
         for (int a = 0; a < MAXR; ++a) {
             float o = bel[A * MAXR + a];
@@ -458,7 +467,7 @@ __device__ __forceinline__ float bp_nodes(const int* res_nrot, int n_res, const 
 __global__ void __launch_bounds__(BP_TPB) k_rot_bp(RotamerDev P, int want_pot) {
     extern __shared__ float smem[];
     const int r = blockIdx.x, tid = threadIdx.x;
-    const int nR = P.n_res;
+    const int nR = P.n_res, SP = P.smem_pairs;
     const int n_pair = P.stats[size_t(r) * 4 + 1];
     float* prob = smem;                         // [nR][6]
     float* bel = prob + nR * MAXR;              // [nR][6]
@@ -466,17 +475,19 @@ __global__ void __launch_bounds__(BP_TPB) k_rot_bp(RotamerDev P, int want_pot) {
     float* red = offs + nR;                     // [32]
     int* istart = reinterpret_cast<int*>(red + 32);           // [nR+1]
     int* nrot = istart + nR + 1;                               // [nR]
-    float* sm_msg = reinterpret_cast<float*>(nrot + nR);      // [smem_pairs][12]
-    float* sm_P = sm_msg + size_t(P.smem_pairs) * 12;         // [smem_pairs][36]
-    int* sm_inc = reinterpret_cast<int*>(sm_P + size_t(P.smem_pairs) * 36);   // [2*smem_pairs]
-    unsigned short* sm_ab = reinterpret_cast<unsigned short*>(sm_inc + 2 * P.smem_pairs);   // [2*smem_pairs]
+    float* sm_msg = reinterpret_cast<float*>(nrot + nR);      // [12][SP]
+    float* sm_P = sm_msg + size_t(SP) * 12;                   // [36][SP]
+    int* sm_inc = reinterpret_cast<int*>(sm_P + size_t(SP) * 36);           // [2*SP]
+    unsigned short* sm_ab = reinterpret_cast<unsigned short*>(sm_inc + 2 * SP);   // [2*SP]
 
     float* g_pmat = P.pmat + size_t(r) * P.max_pairs * 36;
-    const bool in_smem = n_pair <= P.smem_pairs;
-    // replicas whose pair count exceeds the shared-memory budget run the same code on their global scratch
+    const bool in_smem = n_pair <= SP;
+    // replicas whose pair count exceeds the shared-memory budget run the same code on their global scratch; their
+    // messages spill to the area allocated behind the node marginals
     float* Pm = in_smem ? sm_P : g_pmat;
-    // messages of oversized replicas spill to the area allocated behind the node marginals
     float* msg = in_smem ? sm_msg : P.node_marg + size_t(gridDim.x) * nR * MAXR + size_t(r) * P.max_pairs * 12;
+    const Lay lp = in_smem ? Lay{1, SP} : Lay{36, 1};
+    const Lay lm = in_smem ? Lay{1, SP} : Lay{12, 1};
     const unsigned short* pair_ab = P.pair_ab + size_t(r) * P.max_pairs * 2;
     const int* inc = P.inc + size_t(r) * 2 * P.max_pairs;
     float* node_marg = P.node_marg + size_t(r) * nR * MAXR;
@@ -502,7 +513,7 @@ __global__ void __launch_bounds__(BP_TPB) k_rot_bp(RotamerDev P, int want_pot) {
         float p = a < nrot[A] ? __expf(offs[A] - bel[i]) : 0.f;
         prob[i] = p;
     }
-    for (int i = tid; i < n_pair * 36; i += BP_TPB) Pm[i] = __expf(-g_pmat[i]);
+    for (int i = tid; i < n_pair * 36; i += BP_TPB) Pm[at(lp, i / 36, i % 36)] = __expf(-g_pmat[i]);
     if (in_smem) {
         for (int i = tid; i < 2 * n_pair; i += BP_TPB) { sm_inc[i] = inc[i]; sm_ab[i] = pair_ab[i]; }
         inc = sm_inc;
@@ -512,12 +523,12 @@ __global__ void __launch_bounds__(BP_TPB) k_rot_bp(RotamerDev P, int want_pot) {
     for (int i = tid; i < nR * MAXR; i += BP_TPB) bel[i] = prob[i];
     for (int e = tid; e < n_pair; e += BP_TPB) {
         int nA = nrot[pair_ab[2 * e]], nB = nrot[pair_ab[2 * e + 1]];
-        for (int a = 0; a < 6; ++a) { msg[e * 12 + a] = a < nA ? 1.f : 0.f; msg[e * 12 + 6 + a] = a < nB ? 1.f : 0.f; }
+        for (int a = 0; a < 6; ++a) { msg[at(lm, e, a)] = a < nA ? 1.f : 0.f; msg[at(lm, e, 6 + a)] = a < nB ? 1.f : 0.f; }
     }
     __syncthreads();
     // ---- belief propagation -----------------------------------------------------------------------------------------------
     // initial sweep: first messages from (prob, unit messages); node beliefs restart from prob/max (rotamer.cpp:1034)
-    bp_messages(nrot, n_pair, pair_ab, Pm, bel, msg);
+    bp_messages(nrot, n_pair, pair_ab, Pm, lp, bel, msg, lm);
     __syncthreads();
     for (int A = tid; A < nR; A += BP_TPB) {
         float mx = prob[A * MAXR];
@@ -531,9 +542,9 @@ __global__ void __launch_bounds__(BP_TPB) k_rot_bp(RotamerDev P, int want_pot) {
     for (; max_dev > P.tol && iter < P.max_iter; iter += P.chunk) {
         float dev = 0.f;
         for (int j = 0; j < P.chunk; ++j) {
-            bp_messages(nrot, n_pair, pair_ab, Pm, bel, msg);
+            bp_messages(nrot, n_pair, pair_ab, Pm, lp, bel, msg, lm);
             __syncthreads();
-            dev = bp_nodes(nrot, nR, istart, inc, prob, msg, bel, P.damping);
+            dev = bp_nodes(nrot, nR, istart, inc, prob, msg, lm, bel, P.damping);
             __syncthreads();
         }
         max_dev = block_max_bcast(dev, red);
@@ -562,17 +573,16 @@ __global__ void __launch_bounds__(BP_TPB) k_rot_bp(RotamerDev P, int want_pot) {
         int nA = nrot[A], nB = nrot[Bq];
         float bc1[MAXR], bc2[MAXR];
         for (int a = 0; a < MAXR; ++a) {
-            bc1[a] = a < nA ? bel[A * MAXR + a] / (1e-10f + msg[e * 12 + a]) : 0.f;
-            bc2[a] = a < nB ? bel[Bq * MAXR + a] / (1e-10f + msg[e * 12 + 6 + a]) : 0.f;
+            bc1[a] = a < nA ? bel[A * MAXR + a] / (1e-10f + msg[at(lm, e, a)]) : 0.f;
+            bc2[a] = a < nB ? bel[Bq * MAXR + a] / (1e-10f + msg[at(lm, e, 6 + a)]) : 0.f;
         }
-        const float* M = Pm + size_t(e) * 36;
         float* out = g_pmat + size_t(e) * 36;
         float s = 0.f;
-        for (int a = 0; a < nA; ++a) for (int b = 0; b < nB; ++b) s += M[a * 6 + b] * bc1[a] * bc2[b];
+        for (int a = 0; a < nA; ++a) for (int b = 0; b < nB; ++b) s += Pm[at(lp, e, a * 6 + b)] * bc1[a] * bc2[b];
         float is = 1.f / s;
         for (int a = 0; a < MAXR; ++a)
             for (int b = 0; b < MAXR; ++b) {
-                float pr = M[a * 6 + b];
+                float pr = Pm[at(lp, e, a * 6 + b)];
                 float mg = (a < nA && b < nB) ? pr * bc1[a] * bc2[b] * is : 0.f;
                 if (want_pot && a < nA && b < nB)
                     en += mg * __logf((1e-10f + mg) / (1e-10f + pr * bel[A * MAXR + a] * bel[Bq * MAXR + b]));
