@@ -17,6 +17,11 @@ for ln in dis.splitlines():
     if m and cur: addr2line[int(m.group(1), 16)] = cur
 out = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '--print-source', 'sass'], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
+# the page holds one section per profiled kernel: pick the one whose 'Kernel Name' row matches
+starts = [i for i, r in enumerate(rows) if r and r[0] == 'Kernel Name']
+sec = next((i for i in starts if kern in rows[i][1]), starts[0] if starts else 0)
+end = next((i for i in starts if i > sec), len(rows))
+rows = rows[sec:end]
 hi = next(i for i, r in enumerate(rows) if r and r[0] == 'Address')
 h = rows[hi]
 ci = {k: h.index(k) for k in ('Address', '# Samples', 'Instructions Executed', 'Thread Instructions Executed', 'stall_long_sb', 'stall_barrier', 'stall_wait', 'stall_short_sb', 'stall_math')}

@@ -158,16 +158,22 @@ __device__ __forceinline__ void refine_rows(int r, int nA, const float4* posA, c
         const unsigned short* ccol = T.cand + size_t(r) * T.Kc * nA + i;
         unsigned short* row = T.nbr + (size_t(r) * nA + i) * T.K;
         int n = 0;
-        for (int k = 0; k < c; ++k) {
-            int j = ccol[size_t(k) * nA];
-            float4 pj = posB[j];
-            float dx = a_is_first ? pi.x - pj.x : pj.x - pi.x;
-            float dy = a_is_first ? pi.y - pj.y : pj.y - pi.y;
-            float dz = a_is_first ? pi.z - pj.z : pj.z - pi.z;
-            float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-            if (d2 < cutoff2) {
-                if (n < T.K) row[n] = (unsigned short)j;
-                ++n;
+        for (int k0 = 0; k0 < c; k0 += 8) {   // eight candidate loads in flight per step
+            int js[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) js[u] = k0 + u < c ? (int)ccol[size_t(k0 + u) * nA] : -1;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                if (js[u] < 0) continue;
+                float4 pj = posB[js[u]];
+                float dx = a_is_first ? pi.x - pj.x : pj.x - pi.x;
+                float dy = a_is_first ? pi.y - pj.y : pj.y - pi.y;
+                float dz = a_is_first ? pi.z - pj.z : pj.z - pi.z;
+                float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+                if (d2 < cutoff2) {
+                    if (n < T.K) row[n] = (unsigned short)js[u];
+                    ++n;
+                }
             }
         }
         if (n > T.K) { atomicExch(error_flag, 1); n = T.K; }
@@ -193,6 +199,33 @@ __global__ void k_refine(IGraphSide A, IGraphSide Bs, int two_groups, RefineTabl
     __syncthreads();
     refine_rows<G>(r, A.n, posA, posB, T1, cutoff2, 1, error_flag);
     if (two_groups) refine_rows<G>(r, Bs.n, posB, posA, T2, cutoff2, 0, error_flag);
+}
+
+// ---- row scheduling ---------------------------------------------------------------------------------------
+// Counting sort of n rows by descending key (row length, clipped to 255) into order[0..n).  Lane groups that take
+// consecutive entries of `order` then walk rows of similar length, so a warp's groups finish together.  Results do not
+// depend on the processing order (every row is reduced inside its own lane group).  All threads of the CTA must call;
+// hist: 256 ints of shared memory.
+template <typename KeyF>
+__device__ __forceinline__ void sort_rows_desc(int n, KeyF key, int* order, int* hist) {
+    for (int b = threadIdx.x; b < 256; b += blockDim.x) hist[b] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&hist[min(max(key(i), 0), 255)], 1);
+    __syncthreads();
+    if (threadIdx.x < 32) {   // offsets for descending keys: bin b starts after all larger bins
+        int lane = threadIdx.x, sum = 0, v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { v[u] = hist[255 - (lane * 8 + u)]; sum += v[u]; }
+        int incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(UB_FULL_MASK, incl, o); if (lane >= o) incl += t; }
+        int run = incl - sum;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { hist[255 - (lane * 8 + u)] = run; run += v[u]; }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) order[atomicAdd(&hist[min(max(key(i), 0), 255)], 1)] = i;
+    __syncthreads();
 }
 
 // ---- element loads ------------------------------------------------------------------------------------

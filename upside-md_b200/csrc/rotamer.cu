@@ -24,9 +24,9 @@ namespace ub {
 namespace {
 
 constexpr int MAXR = 6;            // most rotamer states per residue (UPPER_ROT-1 in the reference)
-constexpr int PREP_TPB = 128;
+constexpr int PREP_TPB = 256;
 constexpr int EDGE_TPB = 256;
-constexpr int BP_TPB = 256;
+constexpr int BP_TPB = 384;
 constexpr int RG = 8;              // lanes per bead row
 constexpr int MAX_PROB_NODES = 4;
 constexpr int CODE_FOLD = -1;      // (multi-state bead, single-state partner)
@@ -98,24 +98,32 @@ __global__ void __launch_bounds__(PREP_TPB) k_rot_prep(RotamerDev P) {
     for (int i = tid; i < nR * nW; i += PREP_TPB) bitmap[i] = 0u;
     for (int i = tid; i < nR * MAXR; i += PREP_TPB) en[i] = 0.f;
     __syncthreads();
+    int* rr = reinterpret_cast<int*>(en + nR * MAXR);   // [n_bead] res << 4 | rot << 1 | multi-state
     for (int i = tid; i < P.n_bead; i += PREP_TPB) {
         float e = 0.f;
         int loc = P.g.s1.loc[i];
         for (int p = 0; p < P.n_prob; ++p) e += P.prob_out[p][(size_t(r) * P.prob_n[p] + loc) * P.prob_wp[p]];
-        int A = P.bead_res[i];
-        atomicAdd(&en[A * MAXR + P.bead_rot[i]], e);   // one contributor per state unless several beads share a state
-        const unsigned short* row = nbr + size_t(i) * K;
-        int c = cnt[i], lo = 0;
-        bool multi = P.res_nrot[A] > 1;
-        for (int k = 0; k < c; ++k) {
-            int j = row[k];
-            lo += j < i;
-            if (multi) {
-                int Bq = P.bead_res[j];
-                if (P.res_nrot[Bq] > 1) atomicOr(&bitmap[A * nW + (Bq >> 5)], 1u << (Bq & 31));
+        int A = P.bead_res[i], ra = P.bead_rot[i];
+        atomicAdd(&en[A * MAXR + ra], e);   // one contributor per state unless several beads share a state
+        rr[i] = (A << 4) | (ra << 1) | (P.res_nrot[A] > 1 ? 1 : 0);
+    }
+    __syncthreads();
+    const int grp = tid / RG, lane = tid % RG, n_grp = PREP_TPB / RG;
+    for (int i0 = 0; i0 < P.n_bead; i0 += n_grp) {   // RG lanes per bead row: adjacency bits and the count of lower partners
+        int i = i0 + grp, lo = 0;
+        if (i < P.n_bead) {
+            const unsigned short* row = nbr + size_t(i) * K;
+            int c = cnt[i], me = rr[i];
+            for (int k = lane; k < c; k += RG) {
+                int j = row[k];
+                lo += j < i;
+                int other = rr[j];
+                if (me & other & 1) atomicOr(&bitmap[(me >> 4) * nW + (other >> 9)], 1u << ((other >> 4) & 31));
             }
         }
-        P.lower[size_t(r) * P.n_bead + i] = lo;
+#pragma unroll
+        for (int o = RG / 2; o > 0; o >>= 1) lo += __shfl_xor_sync(UB_FULL_MASK, lo, o);
+        if (i < P.n_bead && lane == 0) P.lower[size_t(r) * P.n_bead + i] = lo;
     }
     __syncthreads();
     if (tid < 32) {   // exclusive scans of upper degree (pair slots) and full degree (incidence lists), one warp
@@ -177,15 +185,16 @@ __global__ void __launch_bounds__(PREP_TPB) k_rot_prep(RotamerDev P) {
     float* pmat = P.pmat + size_t(r) * P.max_pairs * 36;
     for (int i = tid; i < n_pair * 36; i += PREP_TPB) pmat[i] = 0.f;
     // per-entry codes
-    for (int i = tid; i < P.n_bead; i += PREP_TPB) {
-        int A = P.bead_res[i], ra = P.bead_rot[i];
-        bool mA = P.res_nrot[A] > 1;
+    for (int i0 = 0; i0 < P.n_bead; i0 += n_grp) {
+        int i = i0 + grp;
+        if (i >= P.n_bead) continue;
+        int me = rr[i], A = me >> 4, ra = (me >> 1) & 7;
+        bool mA = me & 1;
         const unsigned short* row = nbr + size_t(i) * K;
         int c = cnt[i];
-        for (int k = 0; k < c; ++k) {
-            int j = row[k];
-            int Bq = P.bead_res[j], rb = P.bead_rot[j];
-            bool mB = P.res_nrot[Bq] > 1;
+        for (int k = lane; k < c; k += RG) {
+            int other = rr[row[k]], Bq = other >> 4, rb = (other >> 1) & 7;
+            bool mB = other & 1;
             int cd;
             if (mA && mB) {
                 if (A < Bq) cd = (estart[A] + rank_between(bitmap + A * nW, nW, A, Bq)) * 36 + ra * 6 + rb;
@@ -350,16 +359,14 @@ __global__ void __launch_bounds__(EDGE_TPB) k_rot_deriv(RotamerDev P) {
             for (int k = lane; k < c; k += RG) {
                 int j = row[k], cd = crow[k];
                 float s = cd >= 0 ? pmat[cd] : (cd == CODE_FOLD ? my_marg : (cd == CODE_SS ? 1.f : nm[-2 - cd]));
+                // one evaluation with the operands in (lower index, higher index) order, as the reference's i1<i2 edge;
+                // selecting operands and results instead of branching keeps the warp converged
                 float d1[6], d2[6];
-                if (i < j) {
-                    pair_term<true>(P, bi, beads[j], table, d1, d2);
+                const bool first = i < j;
+                BeadRec bj = beads[j];
+                pair_term<true>(P, first ? bi : bj, first ? bj : bi, table, d1, d2);
 #pragma unroll
-                    for (int q = 0; q < 6; ++q) acc[q] += s * d1[q];
-                } else {
-                    pair_term<true>(P, beads[j], bi, table, d1, d2);
-#pragma unroll
-                    for (int q = 0; q < 6; ++q) acc[q] += s * d2[q];
-                }
+                for (int q = 0; q < 6; ++q) acc[q] += s * (first ? d1[q] : d2[q]);
             }
         }
 #pragma unroll
@@ -435,19 +442,24 @@ __device__ __forceinline__ float bp_nodes(const int* res_nrot, int n_res, const 
 #pragma unroll
         for (int a = 0; a < MAXR; ++a) b[a] = prob[A * MAXR + a];
         int t0 = istart[A], t1 = istart[A + 1];
-        for (int t = t0; t < t1; ++t) {
-            int cd = inc[t];
-            int e = cd >> 1, k0 = (cd & 1) * 6;
+        // four incident pairs per step: the index loads and the 24 message loads of a step are independent, so the
+        // serial chain per node is one shared-memory round trip per four pairs instead of two per pair
+        for (int t = t0; t < t1; t += 4) {
+            int cd[4];
+            float m[4][MAXR];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) cd[u] = t + u < t1 ? inc[t + u] : -1;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int a = 0; a < MAXR; ++a) m[u][a] = cd[u] >= 0 ? msg[at(lm, cd[u] >> 1, (cd[u] & 1) * 6 + a)] : 1.f;
             float s = 0.f;
 #pragma unroll
-            for (int a = 0; a < MAXR; ++a) { b[a] *= msg[at(lm, e, k0 + a)]; s += b[a]; }
-            // renormalise (pure rescaling, rotamer.cpp:492-493) often enough that a product of <=4 L1-normalised
-            // messages cannot underflow
-            if (((t - t0) & 3) == 3 || t == t1 - 1) {
-                float is = __fdividef(1.f, s);
+            for (int a = 0; a < MAXR; ++a) { b[a] *= (m[0][a] * m[1][a]) * (m[2][a] * m[3][a]); s += b[a]; }
+            // renormalise (pure rescaling, rotamer.cpp:492-493): a product of four L1-normalised messages cannot underflow
+            float is = __fdividef(1.f, s);
 #pragma unroll
-                for (int a = 0; a < MAXR; ++a) b[a] *= is;
-            }
+            for (int a = 0; a < MAXR; ++a) b[a] *= is;
         }
         float mx = b[0];
 #pragma unroll
@@ -513,7 +525,15 @@ __global__ void __launch_bounds__(BP_TPB) k_rot_bp(RotamerDev P, int want_pot) {
         float p = a < nrot[A] ? __expf(offs[A] - bel[i]) : 0.f;
         prob[i] = p;
     }
-    for (int i = tid; i < n_pair * 36; i += BP_TPB) Pm[at(lp, i / 36, i % 36)] = __expf(-g_pmat[i]);
+    {   // pair energies -> probabilities, 16-byte loads (36 floats per pair = 9 float4, rows are 16-byte aligned)
+        const float4* src = reinterpret_cast<const float4*>(g_pmat);
+        for (int i = tid; i < n_pair * 9; i += BP_TPB) {
+            float4 v = src[i];
+            int e = i / 9, k = (i % 9) * 4;
+            Pm[at(lp, e, k)] = __expf(-v.x); Pm[at(lp, e, k + 1)] = __expf(-v.y);
+            Pm[at(lp, e, k + 2)] = __expf(-v.z); Pm[at(lp, e, k + 3)] = __expf(-v.w);
+        }
+    }
     if (in_smem) {
         for (int i = tid; i < 2 * n_pair; i += BP_TPB) { sm_inc[i] = inc[i]; sm_ab[i] = pair_ab[i]; }
         inc = sm_inc;
@@ -689,8 +709,8 @@ struct RotamerSidechain : PotentialNode {
         size_t budget = std::min<size_t>(device_smem, 110 * 1024);
         smem_pairs = budget > fixed_bp ? (int)std::min<size_t>(max_pairs, (budget - fixed_bp) / per_pair) : 0;
         smem_bp = fixed_bp + size_t(smem_pairs) * per_pair + 16;
-        smem_prep = sizeof(unsigned) * size_t(n_res) * n_words + sizeof(int) * 2 * (n_res + 1) + sizeof(float) * n_res * MAXR;
-        smem_edge = sizeof(BeadRec) * size_t(ig.n1) + sizeof(float) * table.n;
+        smem_prep = sizeof(unsigned) * size_t(n_res) * n_words + sizeof(int) * 2 * (n_res + 1) + sizeof(float) * n_res * MAXR + sizeof(int) * ig.n1;
+        smem_edge = sizeof(BeadRec) * size_t(ig.n1) + sizeof(float) * table.n + sizeof(int) * (ig.n1 + 256);
         if (smem_prep > (size_t)device_smem || smem_edge > (size_t)device_smem || fixed_bp > (size_t)device_smem)
             throw std::string("rotamer node: system too large for the shared-memory kernels");
         UB_CUDA(cudaFuncSetAttribute(k_rot_prep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_prep));
