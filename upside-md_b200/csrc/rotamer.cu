@@ -215,9 +215,15 @@ __device__ __forceinline__ int sym_row(int t1, int t2, int nT, bool& swap) {
     return a * nT - (a * (a - 1)) / 2 + (b - a);
 }
 
-__device__ __forceinline__ void stage_shared(const RotamerDev& P, int r, BeadRec* beads, float* table) {
-    const int n_tab = (P.n_type * (P.n_type + 1) / 2) * P.g.n_param;
-    for (int i = threadIdx.x; i < n_tab; i += blockDim.x) table[i] = P.table[i];
+// the B-spline table is staged once per CTA (CTAs are persistent over replicas), beads once per replica
+__device__ __forceinline__ void stage_table(const RotamerDev& P, float* table) {
+    const int n4 = ((P.n_type * (P.n_type + 1) / 2) * P.g.n_param) / 4;   // n_param is even and rows come in pairs: multiple of 4
+    const float4* src = reinterpret_cast<const float4*>(P.table);
+    float4* dst = reinterpret_cast<float4*>(table);
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) dst[i] = src[i];
+    for (int i = n4 * 4 + threadIdx.x; i < (P.n_type * (P.n_type + 1) / 2) * P.g.n_param; i += blockDim.x) table[i] = P.table[i];
+}
+__device__ __forceinline__ void stage_beads(const RotamerDev& P, int r, BeadRec* beads) {
     for (int i = threadIdx.x; i < P.n_bead; i += blockDim.x) {
         const float* p = elem_ptr(P.g.s1, r, i);
         float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
@@ -227,7 +233,6 @@ __device__ __forceinline__ void stage_shared(const RotamerDev& P, int r, BeadRec
         br.res_rot = (P.bead_res[i] << 3) | P.bead_rot[i];
         beads[i] = br;
     }
-    __syncthreads();
 }
 
 // quadspline on shared-memory operands, (lo,hi) ordering as the reference's i1<i2 edge
@@ -288,97 +293,142 @@ __device__ __forceinline__ float pair_term(const RotamerDev& P, const BeadRec& b
     return wv + angular_weight * nv;
 }
 
-__global__ void __launch_bounds__(EDGE_TPB) k_rot_energy(RotamerDev P, int want_pot) {
+constexpr int PF = 4;   // row entries prefetched per lane: the index/code/marginal loads of a batch are independent
+
+__global__ void __launch_bounds__(EDGE_TPB, 3) k_rot_energy(RotamerDev P, int want_pot, int n_rep) {
     extern __shared__ float4 smem4[];
     BeadRec* beads = reinterpret_cast<BeadRec*>(smem4);
     float* table = reinterpret_cast<float*>(beads + P.n_bead);
-    const int r = blockIdx.y, K = P.g.K1;
-    stage_shared(P, r, beads, table);
-    const unsigned short* nbr = P.g.nbr1 + size_t(r) * P.n_bead * K;
-    const int* cnt = P.g.cnt1 + size_t(r) * P.n_bead;
-    const int* code = P.code + size_t(r) * P.n_bead * K;
-    const int* lower = P.lower + size_t(r) * P.n_bead;
-    float* pmat = P.pmat + size_t(r) * P.max_pairs * 36;
+    const int K = P.g.K1;
     const int grp = threadIdx.x / RG, lane = threadIdx.x % RG, n_grp = EDGE_TPB / RG;
-    float e11 = 0.f;
-    for (int i0 = blockIdx.x * n_grp; i0 < P.n_bead; i0 += gridDim.x * n_grp) {
-        int i = i0 + grp;
-        float fold = 0.f;
-        bool multi = false;
-        if (i < P.n_bead) {
-            BeadRec bi = beads[i];
-            multi = P.res_nrot[bi.res_rot >> 3] > 1;
-            const unsigned short* row = nbr + size_t(i) * K;
-            const int* crow = code + size_t(i) * K;
-            int c = cnt[i], lo = lower[i];
-            // partners with a smaller index only matter when they have a single state (their energy folds into bead i)
-            if (multi)
-                for (int k = lane; k < lo; k += RG)
-                    if (crow[k] == CODE_FOLD) fold += pair_term<false>(P, beads[row[k]], bi, table, nullptr, nullptr);
-            for (int k = lo + lane; k < c; k += RG) {
-                int cd = crow[k];
-                if (cd <= -2 && cd != CODE_SS) continue;   // (single, multi): handled from the partner's row
-                if (cd == CODE_SS && !want_pot) continue;
-                float V = pair_term<false>(P, bi, beads[row[k]], table, nullptr, nullptr);
-                if (cd >= 0) { if (P.multi_bead_states) atomicAdd(&pmat[cd], V); else pmat[cd] = V; }
-                else if (cd == CODE_FOLD) fold += V;
-                else e11 += V;
+    stage_table(P, table);
+    for (int r = blockIdx.y; r < n_rep; r += gridDim.y) {
+        __syncthreads();   // previous replica's readers are done with `beads`
+        stage_beads(P, r, beads);
+        __syncthreads();
+        const unsigned short* nbr = P.g.nbr1 + size_t(r) * P.n_bead * K;
+        const int* cnt = P.g.cnt1 + size_t(r) * P.n_bead;
+        const int* code = P.code + size_t(r) * P.n_bead * K;
+        const int* lower = P.lower + size_t(r) * P.n_bead;
+        float* pmat = P.pmat + size_t(r) * P.max_pairs * 36;
+        float e11 = 0.f;
+        for (int i0 = blockIdx.x * n_grp; i0 < P.n_bead; i0 += gridDim.x * n_grp) {
+            int i = i0 + grp;
+            float fold = 0.f;
+            if (i < P.n_bead) {
+                BeadRec bi = beads[i];
+                const bool multi = P.res_nrot[bi.res_rot >> 3] > 1;
+                const unsigned short* row = nbr + size_t(i) * K;
+                const int* crow = code + size_t(i) * K;
+                const int c = cnt[i], lo = lower[i];
+                // partners with a smaller index only matter when they have a single state (their energy folds into bead i)
+                if (multi)
+                    for (int k = lane; k < lo; k += RG)
+                        if (crow[k] == CODE_FOLD) fold += pair_term<false>(P, beads[row[k]], bi, table, nullptr, nullptr);
+                for (int k0 = lo + lane; k0 < c; k0 += RG * PF) {
+                    int js[PF], cds[PF];
+#pragma unroll
+                    for (int u = 0; u < PF; ++u) {
+                        int k = k0 + u * RG;
+                        js[u] = k < c ? (int)row[k] : -1;
+                        cds[u] = k < c ? crow[k] : CODE_SS;
+                    }
+#pragma unroll
+                    for (int u = 0; u < PF; ++u) {
+                        int cd = cds[u];
+                        if (js[u] < 0) continue;
+                        if (cd <= -2 && cd != CODE_SS) continue;   // (single, multi): handled from the partner's row
+                        if (cd == CODE_SS && !want_pot) continue;
+                        float V = pair_term<false>(P, bi, beads[js[u]], table, nullptr, nullptr);
+                        if (cd >= 0) { if (P.multi_bead_states) atomicAdd(&pmat[cd], V); else pmat[cd] = V; }
+                        else if (cd == CODE_FOLD) fold += V;
+                        else e11 += V;
+                    }
+                }
             }
+            fold = group_sum<RG>(fold);
+            if (i < P.n_bead && lane == 0) P.fold[size_t(r) * P.n_bead + i] = fold;
         }
-        fold = group_sum<RG>(fold);
-        if (i < P.n_bead && lane == 0) P.fold[size_t(r) * P.n_bead + i] = fold;
-    }
-    if (want_pot) {
-        e11 = warp_sum(e11);
-        if ((threadIdx.x & 31) == 0 && e11 != 0.f) atomicAdd(&P.e11[r], e11);
+        if (want_pot) {
+            e11 = warp_sum(e11);
+            if ((threadIdx.x & 31) == 0 && e11 != 0.f) atomicAdd(&P.e11[r], e11);
+        }
     }
 }
 
-__global__ void __launch_bounds__(EDGE_TPB) k_rot_deriv(RotamerDev P) {
+__global__ void __launch_bounds__(EDGE_TPB, 3) k_rot_deriv(RotamerDev P, int n_rep) {
     extern __shared__ float4 smem4[];
     BeadRec* beads = reinterpret_cast<BeadRec*>(smem4);
     float* table = reinterpret_cast<float*>(beads + P.n_bead);
-    const int r = blockIdx.y, K = P.g.K1;
-    stage_shared(P, r, beads, table);
-    const unsigned short* nbr = P.g.nbr1 + size_t(r) * P.n_bead * K;
-    const int* cnt = P.g.cnt1 + size_t(r) * P.n_bead;
-    const int* code = P.code + size_t(r) * P.n_bead * K;
-    const float* pmat = P.pmat + size_t(r) * P.max_pairs * 36;
-    const float* nm = P.node_marg + size_t(r) * P.n_res * MAXR;
+    const int K = P.g.K1;
     const int grp = threadIdx.x / RG, lane = threadIdx.x % RG, n_grp = EDGE_TPB / RG;
-    for (int i0 = blockIdx.x * n_grp; i0 < P.n_bead; i0 += gridDim.x * n_grp) {
-        int i = i0 + grp;
-        float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        float my_marg = 0.f;
-        if (i < P.n_bead) {
-            BeadRec bi = beads[i];
-            my_marg = nm[(bi.res_rot >> 3) * MAXR + (bi.res_rot & 7)];
-            const unsigned short* row = nbr + size_t(i) * K;
-            const int* crow = code + size_t(i) * K;
-            int c = cnt[i];
-            for (int k = lane; k < c; k += RG) {
-                int j = row[k], cd = crow[k];
-                float s = cd >= 0 ? pmat[cd] : (cd == CODE_FOLD ? my_marg : (cd == CODE_SS ? 1.f : nm[-2 - cd]));
-                // one evaluation with the operands in (lower index, higher index) order, as the reference's i1<i2 edge;
-                // selecting operands and results instead of branching keeps the warp converged
-                float d1[6], d2[6];
-                const bool first = i < j;
-                BeadRec bj = beads[j];
-                pair_term<true>(P, first ? bi : bj, first ? bj : bi, table, d1, d2);
+    stage_table(P, table);
+    for (int r = blockIdx.y; r < n_rep; r += gridDim.y) {
+        __syncthreads();
+        stage_beads(P, r, beads);
+        __syncthreads();
+        const unsigned short* nbr = P.g.nbr1 + size_t(r) * P.n_bead * K;
+        const int* cnt = P.g.cnt1 + size_t(r) * P.n_bead;
+        const int* code = P.code + size_t(r) * P.n_bead * K;
+        const float* pmat = P.pmat + size_t(r) * P.max_pairs * 36;
+        const float* nm = P.node_marg + size_t(r) * P.n_res * MAXR;
+        for (int i0 = blockIdx.x * n_grp; i0 < P.n_bead; i0 += gridDim.x * n_grp) {
+            int i = i0 + grp;
+            float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            float my_marg = 0.f;
+            float4 old_a = make_float4(0.f, 0.f, 0.f, 0.f), old_b = old_a;
+            float old_p[MAX_PROB_NODES] = {0.f, 0.f, 0.f, 0.f};
+            float* dst = nullptr;
+            int loc = 0;
+            if (i < P.n_bead) {
+                BeadRec bi = beads[i];
+                my_marg = nm[(bi.res_rot >> 3) * MAXR + (bi.res_rot & 7)];
+                if (lane == 0) {   // the read half of the read-modify-writes is issued before the row walk hides its latency
+                    dst = elem_sens_ptr(P.g.s1, r, i);
+                    old_a = reinterpret_cast<const float4*>(dst)[0];
+                    old_b = reinterpret_cast<const float4*>(dst)[1];
+                    loc = P.g.s1.loc[i];
+                    for (int p = 0; p < P.n_prob; ++p) old_p[p] = P.prob_sens[p][(size_t(r) * P.prob_n[p] + loc) * P.prob_wp[p]];
+                }
+                const unsigned short* row = nbr + size_t(i) * K;
+                const int* crow = code + size_t(i) * K;
+                const int c = cnt[i];
+                for (int k0 = lane; k0 < c; k0 += RG * PF) {
+                    int js[PF], cds[PF];
+                    float ss[PF];
 #pragma unroll
-                for (int q = 0; q < 6; ++q) acc[q] += s * (first ? d1[q] : d2[q]);
+                    for (int u = 0; u < PF; ++u) {
+                        int k = k0 + u * RG;
+                        js[u] = k < c ? (int)row[k] : -1;
+                        cds[u] = k < c ? crow[k] : CODE_SS;
+                    }
+#pragma unroll
+                    for (int u = 0; u < PF; ++u) {
+                        int cd = cds[u];
+                        ss[u] = js[u] < 0 ? 0.f : (cd >= 0 ? pmat[cd] : (cd == CODE_FOLD ? my_marg : (cd == CODE_SS ? 1.f : nm[-2 - cd])));
+                    }
+#pragma unroll
+                    for (int u = 0; u < PF; ++u) {
+                        if (js[u] < 0) continue;
+                        // one evaluation with the operands in (lower index, higher index) order, as the reference's i1<i2
+                        // edge; selecting operands and results instead of branching keeps the warp converged
+                        float d1[6], d2[6];
+                        const bool first = i < js[u];
+                        BeadRec bj = beads[js[u]];
+                        pair_term<true>(P, first ? bi : bj, first ? bj : bi, table, d1, d2);
+#pragma unroll
+                        for (int q = 0; q < 6; ++q) acc[q] += ss[u] * (first ? d1[q] : d2[q]);
+                    }
+                }
             }
-        }
 #pragma unroll
-        for (int q = 0; q < 6; ++q) acc[q] = group_sum<RG>(acc[q]);
-        if (i < P.n_bead && lane == 0) {
-            float* dst = elem_sens_ptr(P.g.s1, r, i);
-            float4 a = reinterpret_cast<float4*>(dst)[0], b = reinterpret_cast<float4*>(dst)[1];
-            a.x += acc[0]; a.y += acc[1]; a.z += acc[2]; a.w += acc[3]; b.x += acc[4]; b.y += acc[5];
-            reinterpret_cast<float4*>(dst)[0] = a;
-            reinterpret_cast<float4*>(dst)[1] = b;
-            int loc = P.g.s1.loc[i];
-            for (int p = 0; p < P.n_prob; ++p) P.prob_sens[p][(size_t(r) * P.prob_n[p] + loc) * P.prob_wp[p]] += my_marg;
+            for (int q = 0; q < 6; ++q) acc[q] = group_sum<RG>(acc[q]);
+            if (i < P.n_bead && lane == 0) {
+                old_a.x += acc[0]; old_a.y += acc[1]; old_a.z += acc[2]; old_a.w += acc[3]; old_b.x += acc[4]; old_b.y += acc[5];
+                reinterpret_cast<float4*>(dst)[0] = old_a;
+                reinterpret_cast<float4*>(dst)[1] = old_b;
+                for (int p = 0; p < P.n_prob; ++p) P.prob_sens[p][(size_t(r) * P.prob_n[p] + loc) * P.prob_wp[p]] = old_p[p] + my_marg;
+            }
         }
     }
 }
@@ -755,10 +805,12 @@ struct RotamerSidechain : PotentialNode {
         ig.build(s);
         RotamerDev P = dev();
         int want = mode == PotentialAndDerivMode;
+        // edge kernels: persistent CTAs (3 resident per SM by shared memory) striding over the replicas
+        int persist = std::min(engine->n_rep, 148 * 3);
         k_rot_prep<<<engine->n_rep, PREP_TPB, smem_prep, s>>>(P);
-        k_rot_energy<<<dim3(P.n_chunk, engine->n_rep), EDGE_TPB, smem_edge, s>>>(P, want);
+        k_rot_energy<<<dim3(P.n_chunk, persist), EDGE_TPB, smem_edge, s>>>(P, want, engine->n_rep);
         k_rot_bp<<<engine->n_rep, BP_TPB, smem_bp, s>>>(P, want);
-        k_rot_deriv<<<dim3(P.n_chunk, engine->n_rep), EDGE_TPB, smem_edge, s>>>(P);
+        k_rot_deriv<<<dim3(P.n_chunk, persist), EDGE_TPB, smem_edge, s>>>(P, engine->n_rep);
     }
     bool get_pairlist(int replica, std::vector<int>& i1, std::vector<int>& i2) override { return ig.pairlist(replica, i1, i2); }
     std::vector<float> get_param() const override { return ig.h_param; }
