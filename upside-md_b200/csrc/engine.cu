@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace ub {
@@ -132,6 +133,7 @@ Engine::Engine(int n_atom_, int n_rep_, int device_) : n_rep(n_rep_), n_atom(n_a
         throw std::string("no CUDA device available: this engine has no CPU fallback (") + cudaGetErrorString(e) + ")";
     UB_CUDA(cudaSetDevice(device));
     UB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    if (const char* e = getenv("UPSIDE_B200_NO_DAG")) use_dag = atoi(e) == 0;
     nodes.emplace_back();
     nodes[0].name = "pos";
     nodes[0].computation.reset(new Pos(n_atom));
@@ -145,6 +147,10 @@ Engine::~Engine() {
     for (auto& g : graph_eval) if (g) cudaGraphExecDestroy(g);
     if (graph_round) cudaGraphExecDestroy(graph_round);
     nodes.clear();
+    for (auto st : node_stream) cudaStreamDestroy(st);
+    for (auto e : ev_fwd) cudaEventDestroy(e);
+    for (auto e : ev_bwd) cudaEventDestroy(e);
+    if (ev_start) cudaEventDestroy(ev_start);
     if (stream) cudaStreamDestroy(stream);
 }
 
@@ -219,11 +225,66 @@ void Engine::enqueue_compute(cudaStream_t s, ComputeMode mode) {
     // forward in construction (topological) order, then backward in reverse order, is equivalent.
     UB_CUDA(cudaMemsetAsync(sens_arena.p, 0, sens_arena.n * sizeof(float), s));
     if (mode == PotentialAndDerivMode) UB_CUDA(cudaMemsetAsync(pot_arena.p, 0, pot_arena.n * sizeof(float), s));
-    for (auto& n : nodes) n.computation->compute_value(s, mode);
-    for (size_t i = nodes.size(); i-- > 0;)
-        if (!nodes[i].computation->potential_term) nodes[i].computation->propagate_deriv(s);
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    UB_CUDA(cudaStreamIsCapturing(s, &cap));
+    if (use_dag && cap == cudaStreamCaptureStatusActive) {
+        enqueue_compute_dag(s, mode);
+    } else {
+        for (auto& n : nodes) n.computation->compute_value(s, mode);
+        for (size_t i = nodes.size(); i-- > 0;)
+            if (!nodes[i].computation->potential_term) nodes[i].computation->propagate_deriv(s);
+    }
     if (mode == PotentialAndDerivMode && n_pot_nodes)
         k_sum_potentials<<<(n_rep + 127) / 128, 128, 0, s>>>(potential.p, pot_ptrs.p, n_pot_nodes, n_rep);
+}
+
+// The same work as the loop above, issued on one stream per node with event edges:
+//   forward  of node i : after the forward of its parents;
+//   backward of node i : after the backward (CoordNode) / forward (PotentialNode) of each child, which is what fills sens_i;
+//   a kernel set that adds into a parent's sens (backward of a CoordNode, forward of a PotentialNode) additionally waits for
+//   the previous writer of that buffer: the gather-form kernels update sens with plain read-modify-writes, so writers of
+//   one buffer stay serialised, in the same order as in the sequential schedule (bit-identical sums).
+void Engine::enqueue_compute_dag(cudaStream_t s, ComputeMode mode) {
+    const size_t N = nodes.size();
+    if (node_stream.size() != N) {
+        for (auto st : node_stream) cudaStreamDestroy(st);
+        for (auto e : ev_fwd) cudaEventDestroy(e);
+        for (auto e : ev_bwd) cudaEventDestroy(e);
+        node_stream.assign(N, nullptr); ev_fwd.assign(N, nullptr); ev_bwd.assign(N, nullptr);
+        for (size_t i = 0; i < N; ++i) {
+            UB_CUDA(cudaStreamCreateWithFlags(&node_stream[i], cudaStreamNonBlocking));
+            UB_CUDA(cudaEventCreateWithFlags(&ev_fwd[i], cudaEventDisableTiming));
+            UB_CUDA(cudaEventCreateWithFlags(&ev_bwd[i], cudaEventDisableTiming));
+        }
+        if (!ev_start) UB_CUDA(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
+    }
+    UB_CUDA(cudaEventRecord(ev_start, s));   // after the memsets
+    std::vector<cudaEvent_t> last_writer(N, nullptr);   // last kernel set that added into sens of node i
+    std::vector<cudaEvent_t> last_event(N, nullptr);    // last thing recorded on node i's stream (for the final join)
+    for (size_t i = 0; i < N; ++i) {
+        cudaStream_t st = node_stream[i];
+        auto& nd = nodes[i];
+        UB_CUDA(cudaStreamWaitEvent(st, ev_start, 0));
+        for (size_t p : nd.parents) if (p) UB_CUDA(cudaStreamWaitEvent(st, ev_fwd[p], 0));
+        const bool pot = nd.computation->potential_term;
+        if (pot) for (size_t p : nd.parents) if (last_writer[p]) UB_CUDA(cudaStreamWaitEvent(st, last_writer[p], 0));
+        nd.computation->compute_value(st, mode);
+        UB_CUDA(cudaEventRecord(ev_fwd[i], st));
+        last_event[i] = ev_fwd[i];
+        if (pot) for (size_t p : nd.parents) last_writer[p] = ev_fwd[i];
+    }
+    for (size_t i = N; i-- > 0;) {
+        auto& nd = nodes[i];
+        if (nd.computation->potential_term) continue;
+        cudaStream_t st = node_stream[i];
+        for (size_t c : nd.children) UB_CUDA(cudaStreamWaitEvent(st, nodes[c].computation->potential_term ? ev_fwd[c] : ev_bwd[c], 0));
+        for (size_t p : nd.parents) if (last_writer[p]) UB_CUDA(cudaStreamWaitEvent(st, last_writer[p], 0));
+        nd.computation->propagate_deriv(st);
+        UB_CUDA(cudaEventRecord(ev_bwd[i], st));
+        last_event[i] = ev_bwd[i];
+        for (size_t p : nd.parents) last_writer[p] = ev_bwd[i];
+    }
+    for (size_t i = 0; i < N; ++i) UB_CUDA(cudaStreamWaitEvent(s, last_event[i], 0));
 }
 
 void Engine::compute(ComputeMode mode) {
@@ -273,14 +334,20 @@ __global__ void k_unpack4to3(float* __restrict__ dst, const float* __restrict__ 
     dst[3 * i] = v.x; dst[3 * i + 1] = v.y; dst[3 * i + 2] = v.z;
 }
 
+// device staging area for (n,3) <-> (n,4) conversion of host buffers: allocated once, grown on demand (cudaMalloc/cudaFree per
+// call would serialise the device and dominate a per-step upload/download loop)
+float* Engine::io_staging(size_t n_float) {
+    if (io_stage.n < n_float) io_stage.alloc(n_float);
+    return io_stage.p;
+}
 static void upload3(Engine& e, float* dev4, const float* host3, int first_rep, int n) {
     if (n < 0) n = e.n_rep - first_rep;
     if (first_rep < 0 || first_rep + n > e.n_rep) throw std::string("replica range out of bounds");
     long cnt = long(n) * e.n_atom;
     if (!cnt) return;
-    DevBuf<float> tmp(size_t(cnt) * 3);
-    UB_CUDA(cudaMemcpyAsync(tmp.p, host3, size_t(cnt) * 3 * sizeof(float), cudaMemcpyHostToDevice, e.stream));
-    k_pack3to4<<<(unsigned)((cnt + 255) / 256), 256, 0, e.stream>>>(dev4 + size_t(first_rep) * e.n_atom * 4, tmp.p, cnt);
+    float* tmp = e.io_staging(size_t(cnt) * 3);
+    UB_CUDA(cudaMemcpyAsync(tmp, host3, size_t(cnt) * 3 * sizeof(float), cudaMemcpyHostToDevice, e.stream));
+    k_pack3to4<<<(unsigned)((cnt + 255) / 256), 256, 0, e.stream>>>(dev4 + size_t(first_rep) * e.n_atom * 4, tmp, cnt);
     UB_CUDA(cudaStreamSynchronize(e.stream));
 }
 static void download3(Engine& e, const float* dev4, float* host3, int first_rep, int n) {
@@ -288,9 +355,9 @@ static void download3(Engine& e, const float* dev4, float* host3, int first_rep,
     if (first_rep < 0 || first_rep + n > e.n_rep) throw std::string("replica range out of bounds");
     long cnt = long(n) * e.n_atom;
     if (!cnt) return;
-    DevBuf<float> tmp(size_t(cnt) * 3);
-    k_unpack4to3<<<(unsigned)((cnt + 255) / 256), 256, 0, e.stream>>>(tmp.p, dev4 + size_t(first_rep) * e.n_atom * 4, cnt);
-    UB_CUDA(cudaMemcpyAsync(host3, tmp.p, size_t(cnt) * 3 * sizeof(float), cudaMemcpyDeviceToHost, e.stream));
+    float* tmp = e.io_staging(size_t(cnt) * 3);
+    k_unpack4to3<<<(unsigned)((cnt + 255) / 256), 256, 0, e.stream>>>(tmp, dev4 + size_t(first_rep) * e.n_atom * 4, cnt);
+    UB_CUDA(cudaMemcpyAsync(host3, tmp, size_t(cnt) * 3 * sizeof(float), cudaMemcpyDeviceToHost, e.stream));
     UB_CUDA(cudaStreamSynchronize(e.stream));
 }
 void Engine::set_pos(const float* p, int first_rep, int n) { UB_CUDA(cudaSetDevice(device)); upload3(*this, pos->output, p, first_rep, n); }

@@ -170,6 +170,8 @@ struct Engine {
     DevBuf<float*> pot_ptrs;         // device table of per-node potential pointers
     int n_pot_nodes = 0;
     DevBuf<int> error_flag;          // device-side failure flag (pair-list overflow etc.), checked at sync points
+    DevBuf<float> io_stage;          // staging for host I/O in (n,3) layout
+    float* io_staging(size_t n_float);
 
     // MD state
     DevBuf<float> mom;               // [B][n_atom][4]
@@ -188,6 +190,13 @@ struct Engine {
     cudaGraphExec_t graph_eval[2] = {nullptr, nullptr};
     cudaGraphExec_t graph_round = nullptr;
     bool use_graphs = true;
+    // While a graph is being captured the evaluation is issued as the node DAG, not as a chain: every node records its
+    // kernels on its own stream, ordered after its inputs only, so independent branches of the force field (springs, Rama
+    // terms, environment coverage, H-bond geometry ...) become parallel branches of the CUDA graph and overlap on the GPU.
+    bool use_dag = true;
+    std::vector<cudaStream_t> node_stream;
+    std::vector<cudaEvent_t> ev_fwd, ev_bwd;
+    cudaEvent_t ev_start = nullptr;
 
     Engine(int n_atom, int n_rep, int device);
     ~Engine();
@@ -200,6 +209,7 @@ struct Engine {
 
     void allocate();                                // assign device buffers after all nodes are added
     void enqueue_compute(cudaStream_t s, ComputeMode mode);   // raw kernel sequence (used for capture)
+    void enqueue_compute_dag(cudaStream_t s, ComputeMode mode);
     void compute(ComputeMode mode);                 // one evaluation of all replicas (graph replay), asynchronous
     void sync_and_check();                          // cudaStreamSynchronize + device error flag -> throws
 

@@ -71,10 +71,11 @@ __global__ void k_pairlist(IGraphSide A, IGraphSide Bs, unsigned short* __restri
             idi = A.id[i];
         }
         int n = 0;
-        // row-major rows [i][k] for the exact tables, column-major [k][i] for the Verlet candidates (coalesced when one
-        // thread owns one row, as here and in k_refine)
-        unsigned short* row = colmajor ? nbr + size_t(r) * K * A.n + (active ? i : 0) : nbr + (size_t(r) * A.n + (active ? i : 0)) * K;
-        const size_t rstride = colmajor ? (size_t)A.n : 1;
+        // row-major rows [i][k] for the exact tables; the Verlet candidates are stored in slices of eight, [k/8][i][8]: the
+        // thread that owns row i (here and in k_refine) moves 16 bytes per access and neighbouring threads touch
+        // neighbouring 16-byte words
+        unsigned short* row = colmajor ? nbr + size_t(r) * K * A.n : nbr + (size_t(r) * A.n + (active ? i : 0)) * K;
+        const int ii = active ? i : 0;
         for (int j0 = 0; j0 < Bs.n; j0 += TILE) {
             int j = j0 + threadIdx.x;
             __syncthreads();
@@ -94,7 +95,7 @@ __global__ void k_pairlist(IGraphSide A, IGraphSide Bs, unsigned short* __restri
                 float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
                 bool hit = d2 < cutoff2 && acceptable_id_pair(excl, idi, __float_as_int(t.w)) && !(same_group && (j0 + jj) == i);
                 if (hit) {
-                    if (n < K) row[n * rstride] = (unsigned short)(j0 + jj);
+                    if (n < K) row[colmajor ? (size_t(n >> 3) * A.n + ii) * 8 + (n & 7) : size_t(n)] = (unsigned short)(j0 + jj);
                     ++n;
                 }
             }
@@ -102,6 +103,8 @@ __global__ void k_pairlist(IGraphSide A, IGraphSide Bs, unsigned short* __restri
         if (active) {
             if (n > K) { atomicExch(error_flag, 1); n = K; }
             cnt[size_t(r) * A.n + i] = n;
+            // pad the last slice with the sentinel index Bs.n (k_refine keeps a far-away position there)
+            if (colmajor) for (int k = n; k & 7; ++k) row[(size_t(k >> 3) * A.n + ii) * 8 + (k & 7)] = (unsigned short)Bs.n;
         }
         __syncthreads();
     }
@@ -148,30 +151,33 @@ static __global__ void k_cache_check(IGraphSide A, IGraphSide Bs, int two_groups
 // compaction keeps the ascending order); for an asymmetric graph the transposed table is refined in the same launch.
 struct RefineTable { const unsigned short* cand; const int* ccnt; int Kc; unsigned short* nbr; int* cnt; int K; };
 
-// one thread per candidate row (column-major candidates => coalesced), sequential compaction keeps the ascending order
-template <int G>
+// one thread per candidate row; a slice of eight candidates per 16-byte load, no bounds tests (padding entries index the
+// sentinel position, which is never in range); sequential compaction keeps the ascending order
 __device__ __forceinline__ void refine_rows(int r, int nA, const float4* posA, const float4* posB, RefineTable T, float cutoff2,
                                             int a_is_first, int* error_flag) {
     for (int i = threadIdx.x; i < nA; i += blockDim.x) {
         const float4 pi = posA[i];
         const int c = T.ccnt[size_t(r) * nA + i];
-        const unsigned short* ccol = T.cand + size_t(r) * T.Kc * nA + i;
+        const uint4* cs = reinterpret_cast<const uint4*>(T.cand + size_t(r) * T.Kc * nA) + i;
         unsigned short* row = T.nbr + (size_t(r) * nA + i) * T.K;
         int n = 0;
-        for (int k0 = 0; k0 < c; k0 += 8) {   // eight candidate loads in flight per step
-            int js[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) js[u] = k0 + u < c ? (int)ccol[size_t(k0 + u) * nA] : -1;
+        const int n_slice = (c + 7) >> 3;
+        uint4 v = n_slice ? cs[0] : make_uint4(0, 0, 0, 0);
+        for (int s = 0; s < n_slice; ++s) {
+            const uint4 cur = v;
+            if (s + 1 < n_slice) v = cs[size_t(s + 1) * nA];   // next slice in flight while this one is tested
+            const unsigned w[4] = {cur.x, cur.y, cur.z, cur.w};
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
-                if (js[u] < 0) continue;
-                float4 pj = posB[js[u]];
-                float dx = a_is_first ? pi.x - pj.x : pj.x - pi.x;
-                float dy = a_is_first ? pi.y - pj.y : pj.y - pi.y;
-                float dz = a_is_first ? pi.z - pj.z : pj.z - pi.z;
-                float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+                const int j = (u & 1) ? int(w[u >> 1] >> 16) : int(w[u >> 1] & 0xffffu);
+                const float4 pj = posB[j];
+                // group 1 minus group 2, as in the reference refine step; the squares make the order immaterial
+                const float dx = a_is_first ? pi.x - pj.x : pj.x - pi.x;
+                const float dy = a_is_first ? pi.y - pj.y : pj.y - pi.y;
+                const float dz = a_is_first ? pi.z - pj.z : pj.z - pi.z;
+                const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
                 if (d2 < cutoff2) {
-                    if (n < T.K) row[n] = (unsigned short)js[u];
+                    if (n < T.K) row[n] = (unsigned short)j;
                     ++n;
                 }
             }
@@ -185,20 +191,24 @@ template <int G>
 __global__ void k_refine(IGraphSide A, IGraphSide Bs, int two_groups, RefineTable T1, RefineTable T2, float cutoff2, int* error_flag) {
     extern __shared__ float4 sm_pos[];
     const int r = blockIdx.x;
-    float4* posA = sm_pos;
-    float4* posB = two_groups ? sm_pos + A.n : sm_pos;
+    float4* posA = sm_pos;                                  // [A.n + 1], last = sentinel
+    float4* posB = two_groups ? sm_pos + A.n + 1 : sm_pos;  // [Bs.n + 1]
+    const float4 far = make_float4(1e18f, 1e18f, 1e18f, 0.f);
     for (int i = threadIdx.x; i < A.n; i += blockDim.x) {
         const float* p = A.out + (size_t(r) * A.n_node + A.loc[i]) * A.wp;
         posA[i] = make_float4(p[0], p[1], p[2], 0.f);
     }
-    if (two_groups)
+    if (threadIdx.x == 0) posA[A.n] = far;
+    if (two_groups) {
         for (int i = threadIdx.x; i < Bs.n; i += blockDim.x) {
             const float* p = Bs.out + (size_t(r) * Bs.n_node + Bs.loc[i]) * Bs.wp;
             posB[i] = make_float4(p[0], p[1], p[2], 0.f);
         }
+        if (threadIdx.x == 0) posB[Bs.n] = far;
+    }
     __syncthreads();
-    refine_rows<G>(r, A.n, posA, posB, T1, cutoff2, 1, error_flag);
-    if (two_groups) refine_rows<G>(r, Bs.n, posB, posA, T2, cutoff2, 0, error_flag);
+    refine_rows(r, A.n, posA, posB, T1, cutoff2, 1, error_flag);
+    if (two_groups) refine_rows(r, Bs.n, posB, posA, T2, cutoff2, 0, error_flag);
 }
 
 // ---- row scheduling ---------------------------------------------------------------------------------------

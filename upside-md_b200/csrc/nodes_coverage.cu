@@ -6,13 +6,13 @@
 #include <algorithm>
 #include <cmath>
 
+#include "edgelist.cuh"
 #include "igraph.cuh"
 
 namespace ub {
 namespace {
 
 constexpr int CTPB = 256;
-constexpr int CG = 8;   // lanes per element row
 
 struct StagedGroup {
     float4* a;   // x,y,z,w0
@@ -20,134 +20,145 @@ struct StagedGroup {
     int* type;
 };
 
-// carve `n1`+`n2` staged elements and `n_tab` table floats out of dynamic shared memory and fill them
-__device__ __forceinline__ void stage_groups(const IGraphDev& g, int r, float4* smem, StagedGroup& S1, StagedGroup& S2,
-                                             float*& table, int n_tab) {
+// carve `n1`+`n2` staged elements and `n_tab` table floats out of dynamic shared memory; returns the first free byte
+__device__ __forceinline__ void* carve_groups(const IGraphDev& g, float4* smem, StagedGroup& S1, StagedGroup& S2, float*& table,
+                                              int n_tab) {
     S1.a = smem; S1.b = S1.a + g.s1.n;
     S2.a = S1.b + g.s1.n; S2.b = S2.a + g.s2.n;
-    S1.type = reinterpret_cast<int*>(S2.b + g.s2.n);
+    table = reinterpret_cast<float*>(S2.b + g.s2.n);
+    S1.type = reinterpret_cast<int*>(table + ((n_tab + 3) & ~3));
     S2.type = S1.type + g.s1.n;
-    table = reinterpret_cast<float*>(S2.type + g.s2.n);
+    return S1.type + ((g.s1.n + g.s2.n + 3) & ~3);
+}
+// parameter table and element types do not depend on the replica: staged once per (persistent) CTA
+__device__ __forceinline__ void stage_table(const IGraphDev& g, const StagedGroup& S1, const StagedGroup& S2, float* table, int n_tab) {
+    for (int i = threadIdx.x; i < n_tab; i += blockDim.x) table[i] = g.param[i];
+    for (int i = threadIdx.x; i < g.s1.n; i += blockDim.x) S1.type[i] = g.s1.type[i];
+    for (int i = threadIdx.x; i < g.s2.n; i += blockDim.x) S2.type[i] = g.s2.type[i];
+}
+// both barriers included: the previous replica's readers are done before the overwrite, the data is visible after
+__device__ __forceinline__ void stage_groups(const IGraphDev& g, int r, const StagedGroup& S1, const StagedGroup& S2) {
+    __syncthreads();
     for (int i = threadIdx.x; i < g.s1.n; i += blockDim.x) {
         const float* p = elem_ptr(g.s1, r, i);
         S1.a[i] = reinterpret_cast<const float4*>(p)[0];
         S1.b[i] = g.s1.wp >= 8 ? reinterpret_cast<const float4*>(p)[1] : make_float4(0.f, 0.f, 0.f, 0.f);
-        S1.type[i] = g.s1.type[i];
     }
     for (int i = threadIdx.x; i < g.s2.n; i += blockDim.x) {
         const float* p = elem_ptr(g.s2, r, i);
         S2.a[i] = reinterpret_cast<const float4*>(p)[0];
         S2.b[i] = g.s2.wp >= 8 ? reinterpret_cast<const float4*>(p)[1] : make_float4(0.f, 0.f, 0.f, 0.f);
-        S2.type[i] = g.s2.type[i];
     }
-    for (int i = threadIdx.x; i < n_tab; i += blockDim.x) table[i] = g.param[i];
     __syncthreads();
 }
 __device__ __forceinline__ void unpack8(const StagedGroup& S, int i, float* x) {
     float4 a = S.a[i], b = S.b[i];
     x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
 }
-inline size_t staged_bytes(int n1, int n2, int n_tab) { return size_t(n1 + n2) * (2 * sizeof(float4) + sizeof(int)) + sizeof(float) * n_tab; }
+inline size_t staged_bytes(int n1, int n2, int n_tab) {
+    return size_t(n1 + n2) * 2 * sizeof(float4) + sizeof(float) * ((n_tab + 3) & ~3) + sizeof(int) * size_t((n1 + n2 + 3) & ~3);
+}
+
+// shared-memory sizes and persistent grids (as many CTAs as stay resident, striding over the replicas)
+struct CoverageLaunch {
+    size_t smem_fwd = 0, smem_bwd = 0;
+    int grid_fwd = 1, grid_bwd = 1, n_rows_max = 0;
+    void init(Engine* e, const IGraphHost& ig, int nv_bwd, int n_sens, const void* kf, const void* kb, const char* what) {
+        if (ig.K1 > EL_CAP || ig.K2 > EL_CAP) throw std::string(what) + ": neighbour capacity exceeds the edge chunk size";
+        n_rows_max = std::max(ig.n1, ig.n2);
+        size_t staged = staged_bytes(ig.n1, ig.n2, ig.n_type1 * ig.n_type2 * ig.n_param);
+        smem_fwd = staged + edge_scratch_bytes(n_rows_max, 1);
+        smem_bwd = staged + edge_scratch_bytes(n_rows_max, nv_bwd) + sizeof(float) * n_sens;
+        int lim = 0, n_sm = 0, occ_f = 0, occ_b = 0;
+        UB_CUDA(cudaDeviceGetAttribute(&lim, cudaDevAttrMaxSharedMemoryPerBlockOptin, e->device));
+        UB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, e->device));
+        if (smem_bwd > (size_t)lim) throw std::string(what) + ": system too large for the shared-memory kernels";
+        UB_CUDA(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fwd));
+        UB_CUDA(cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bwd));
+        UB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, kf, CTPB, smem_fwd));
+        UB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, kb, CTPB, smem_bwd));
+        grid_fwd = std::max(1, std::min(e->n_rep, n_sm * std::max(1, occ_f)));
+        grid_bwd = std::max(1, std::min(e->n_rep, n_sm * std::max(1, occ_b)));
+    }
+};
 
 // ================================================================================================ HBondCoverage
 // forward: per bead (group 2) the coverage of every H/O site (group 1) in range
-__global__ void __launch_bounds__(CTPB) k_hbond_coverage(IGraphDev g, QuadSplineShape q, float* __restrict__ out) {
+__global__ void __launch_bounds__(CTPB) k_hbond_coverage(IGraphDev g, QuadSplineShape q, float* __restrict__ out, int n_rep, int n_rows_max) {
     extern __shared__ float4 smem4[];
-    const int r = blockIdx.x;
     StagedGroup S1, S2;
     float* table;
-    stage_groups(g, r, smem4, S1, S2, table, g.n_type1 * g.n_type2 * g.n_param);
-    const int lane = threadIdx.x % CG, n_grp = CTPB / CG;
-    for (int j0 = 0; j0 < g.s2.n; j0 += n_grp) {
-        int j = j0 + threadIdx.x / CG;
-        float acc = 0.f;
-        if (j < g.s2.n) {
-            float x2[8];
-            unpack8(S2, j, x2);
-            int t2 = S2.type[j];
-            const unsigned short* row = g.nbr2 + (size_t(r) * g.s2.n + j) * g.K2;
-            int cnt = g.cnt2[size_t(r) * g.s2.n + j];
-            for (int k = lane; k < cnt; k += CG) {
-                int i = row[k];
-                float x1[8], d1[7], d2[6];
-                unpack8(S1, i, x1);
-                acc += hbond_coverage_edge(table + (S1.type[i] * g.n_type2 + t2) * g.n_param, q, x1, x2, d1, d2);
-            }
-        }
-        acc = group_sum<CG>(acc);
-        if (j < g.s2.n && lane == 0) out[size_t(r) * g.s2.n + j] = acc;
+    const int n_tab = g.n_type1 * g.n_type2 * g.n_param;
+    EdgeScratch E = carve_edge_scratch(carve_groups(g, smem4, S1, S2, table, n_tab), n_rows_max, 1);
+    stage_table(g, S1, S2, table, n_tab);
+    for (int r = blockIdx.x; r < n_rep; r += gridDim.x) {
+        stage_groups(g, r, S1, S2);
+        const int* cnt = g.cnt2 + size_t(r) * g.s2.n;
+        scan_row_lengths(g.s2.n, [&](int j) { return cnt[j]; }, E.start, E.wtot);
+        for_each_edge<1>(g.s2.n, g.nbr2 + size_t(r) * g.s2.n * g.K2, g.K2, E,
+            [&](int j, int i, float* o) {
+                float x1[8], x2[8], d1[7], d2[6];
+                unpack8(S1, i, x1); unpack8(S2, j, x2);
+                o[0] = hbond_coverage_edge(table + (S1.type[i] * g.n_type2 + S2.type[j]) * g.n_param, q, x1, x2, d1, d2);
+            },
+            [&](int j, int, const float* s) { out[size_t(r) * g.s2.n + j] = s[0]; });
     }
 }
 // backward: bead side sens[j] * sum_i dV/d(bead j); site side sum_j sens[j] * dV/d(site i) (7 components, last = d/d hb)
-__global__ void __launch_bounds__(CTPB) k_hbond_coverage_deriv(IGraphDev g, QuadSplineShape q, const float* __restrict__ sens) {
+__global__ void __launch_bounds__(CTPB) k_hbond_coverage_deriv(IGraphDev g, QuadSplineShape q, const float* __restrict__ sens, int n_rep,
+                                                               int n_rows_max) {
     extern __shared__ float4 smem4[];
-    const int r = blockIdx.x;
     StagedGroup S1, S2;
     float* table;
-    stage_groups(g, r, smem4, S1, S2, table, g.n_type1 * g.n_type2 * g.n_param);
-    const int lane = threadIdx.x % CG, n_grp = CTPB / CG;
-    const float* sn = sens + size_t(r) * g.s2.n;
-    for (int j0 = 0; j0 < g.s2.n; j0 += n_grp) {
-        int j = j0 + threadIdx.x / CG;
-        float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        float sj = 0.f;
-        if (j < g.s2.n) {
-            sj = sn[j];
-            float x2[8];
-            unpack8(S2, j, x2);
-            int t2 = S2.type[j];
-            const unsigned short* row = g.nbr2 + (size_t(r) * g.s2.n + j) * g.K2;
-            int cnt = (sj != 0.f) ? g.cnt2[size_t(r) * g.s2.n + j] : 0;
-            for (int k = lane; k < cnt; k += CG) {
-                int i = row[k];
-                float x1[8], d1[7], d2[6];
-                unpack8(S1, i, x1);
-                hbond_coverage_edge(table + (S1.type[i] * g.n_type2 + t2) * g.n_param, q, x1, x2, d1, d2);
+    const int n_tab = g.n_type1 * g.n_type2 * g.n_param;
+    EdgeScratch E = carve_edge_scratch(carve_groups(g, smem4, S1, S2, table, n_tab), n_rows_max, 7);
+    float* sn = reinterpret_cast<float*>(E.wtot + 33);   // [n2] sens of this replica's beads
+    stage_table(g, S1, S2, table, n_tab);
+    for (int r = blockIdx.x; r < n_rep; r += gridDim.x) {
+        stage_groups(g, r, S1, S2);   // (leading barrier: previous replica's readers of sn are done)
+        for (int j = threadIdx.x; j < g.s2.n; j += blockDim.x) sn[j] = sens[size_t(r) * g.s2.n + j];
+        __syncthreads();
+        const int* cnt2 = g.cnt2 + size_t(r) * g.s2.n;
+        scan_row_lengths(g.s2.n, [&](int j) { return sn[j] != 0.f ? cnt2[j] : 0; }, E.start, E.wtot);
+        for_each_edge<6>(g.s2.n, g.nbr2 + size_t(r) * g.s2.n * g.K2, g.K2, E,
+            [&](int j, int i, float* o) {
+                float x1[8], x2[8], d1[7];
+                unpack8(S1, i, x1); unpack8(S2, j, x2);
+                hbond_coverage_edge(table + (S1.type[i] * g.n_type2 + S2.type[j]) * g.n_param, q, x1, x2, d1, o);
+            },
+            [&](int j, int c, const float* s) {
+                if (!c) return;
+                float* dst = elem_sens_ptr(g.s2, r, j);
+                const float sj = sn[j];
+                float4 a = reinterpret_cast<float4*>(dst)[0], b = reinterpret_cast<float4*>(dst)[1];
+                a.x += sj * s[0]; a.y += sj * s[1]; a.z += sj * s[2]; a.w += sj * s[3]; b.x += sj * s[4]; b.y += sj * s[5];
+                reinterpret_cast<float4*>(dst)[0] = a; reinterpret_cast<float4*>(dst)[1] = b;
+            });
+        const int* cnt1 = g.cnt1 + size_t(r) * g.s1.n;
+        scan_row_lengths(g.s1.n, [&](int i) { return cnt1[i]; }, E.start, E.wtot);
+        for_each_edge<7>(g.s1.n, g.nbr1 + size_t(r) * g.s1.n * g.K1, g.K1, E,
+            [&](int i, int j, float* o) {
+                float x1[8], x2[8], d2[6];
+                unpack8(S1, i, x1); unpack8(S2, j, x2);
+                hbond_coverage_edge(table + (S1.type[i] * g.n_type2 + S2.type[j]) * g.n_param, q, x1, x2, o, d2);
+                const float sj = sn[j];
 #pragma unroll
-                for (int c = 0; c < 6; ++c) acc[c] += d2[c];
-            }
-        }
-#pragma unroll
-        for (int c = 0; c < 6; ++c) acc[c] = group_sum<CG>(acc[c]);
-        if (j < g.s2.n && lane == 0 && sj != 0.f) {
-            float* dst = elem_sens_ptr(g.s2, r, j);
-#pragma unroll
-            for (int c = 0; c < 6; ++c) dst[c] += sj * acc[c];
-        }
-    }
-    for (int i0 = 0; i0 < g.s1.n; i0 += n_grp) {
-        int i = i0 + threadIdx.x / CG;
-        float acc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        if (i < g.s1.n) {
-            float x1[8];
-            unpack8(S1, i, x1);
-            int t1 = S1.type[i];
-            const unsigned short* row = g.nbr1 + (size_t(r) * g.s1.n + i) * g.K1;
-            int cnt = g.cnt1[size_t(r) * g.s1.n + i];
-            for (int k = lane; k < cnt; k += CG) {
-                int j = row[k];
-                float sj = sn[j];
-                float x2[8], d1[7], d2[6];
-                unpack8(S2, j, x2);
-                hbond_coverage_edge(table + (t1 * g.n_type2 + S2.type[j]) * g.n_param, q, x1, x2, d1, d2);
-#pragma unroll
-                for (int c = 0; c < 7; ++c) acc[c] += sj * d1[c];
-            }
-        }
-#pragma unroll
-        for (int c = 0; c < 7; ++c) acc[c] = group_sum<CG>(acc[c]);
-        if (i < g.s1.n && lane == 0) {
-            float* dst = elem_sens_ptr(g.s1, r, i);
-#pragma unroll
-            for (int c = 0; c < 7; ++c) dst[c] += acc[c];
-        }
+                for (int c = 0; c < 7; ++c) o[c] *= sj;
+            },
+            [&](int i, int c, const float* s) {
+                if (!c) return;
+                float* dst = elem_sens_ptr(g.s1, r, i);
+                float4 a = reinterpret_cast<float4*>(dst)[0], b = reinterpret_cast<float4*>(dst)[1];
+                a.x += s[0]; a.y += s[1]; a.z += s[2]; a.w += s[3]; b.x += s[4]; b.y += s[5]; b.z += s[6];
+                reinterpret_cast<float4*>(dst)[0] = a; reinterpret_cast<float4*>(dst)[1] = b;
+            });
     }
 }
 struct HBondCoverage : CoordNode {
     IGraphHost ig;
     int nka = 15, nk = 12;
     float knot_spacing = 0.5f;
-    size_t smem = 0;
+    CoverageLaunch launch;
     HBondCoverage(Engine&, const h5l::Node& g, CoordNode& hb, CoordNode& sc)
         : CoordNode((int)h5_dims(g, "index2", 1)[0], 1), ig(g, false, EXCL_SEQ2, 7, 6, &hb, &sc) {
         if (hb.wp != 8 || sc.wp != 8) throw std::string("hbond_coverage expects 8-float rows on both arguments");
@@ -161,22 +172,17 @@ struct HBondCoverage : CoordNode {
     }
     void finalize() override {
         ig.allocate(engine);
-        smem = staged_bytes(ig.n1, ig.n2, ig.n_type1 * ig.n_type2 * ig.n_param);
-        int lim = 0;
-        UB_CUDA(cudaDeviceGetAttribute(&lim, cudaDevAttrMaxSharedMemoryPerBlockOptin, engine->device));
-        if (smem > (size_t)lim) throw std::string("hbond_coverage: system too large for the shared-memory kernels");
-        UB_CUDA(cudaFuncSetAttribute(k_hbond_coverage, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        UB_CUDA(cudaFuncSetAttribute(k_hbond_coverage_deriv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        launch.init(engine, ig, 7, ig.n2, (const void*)k_hbond_coverage, (const void*)k_hbond_coverage_deriv, "hbond_coverage");
     }
     QuadSplineShape shape() const { QuadSplineShape q; q.nka = nka; q.nk = nk; q.inv_dx = 1.f / knot_spacing; q.inv_dtheta = (nka - 3) / 2.f; return q; }
     void compute_value(cudaStream_t s, ComputeMode) override {
         if (!n_elem) return;
         ig.build(s);
-        k_hbond_coverage<<<engine->n_rep, CTPB, smem, s>>>(ig.dev(), shape(), output);
+        k_hbond_coverage<<<launch.grid_fwd, CTPB, launch.smem_fwd, s>>>(ig.dev(), shape(), output, engine->n_rep, launch.n_rows_max);
     }
     void propagate_deriv(cudaStream_t s) override {
         if (!n_elem) return;
-        k_hbond_coverage_deriv<<<engine->n_rep, CTPB, smem, s>>>(ig.dev(), shape(), sens);
+        k_hbond_coverage_deriv<<<launch.grid_bwd, CTPB, launch.smem_bwd, s>>>(ig.dev(), shape(), sens, engine->n_rep, launch.n_rows_max);
     }
     bool get_pairlist(int replica, std::vector<int>& i1, std::vector<int>& i2) override { return ig.pairlist(replica, i1, i2); }
     std::vector<float> get_param() const override { return ig.h_param; }
@@ -189,101 +195,84 @@ struct HBondCoverage : CoordNode {
 RegisterNodeType<HBondCoverage, 2> coverage_node("hbond_coverage");
 
 // ================================================================================================ EnvironmentCoverage
-__global__ void __launch_bounds__(CTPB) k_env_coverage(IGraphDev g, float* __restrict__ out) {
+// forward: per CB (group 1) the weighted count of side-chain beads (group 2) in its cone
+__global__ void __launch_bounds__(CTPB) k_env_coverage(IGraphDev g, float* __restrict__ out, int n_rep, int n_rows_max) {
     extern __shared__ float4 smem4[];
-    const int r = blockIdx.x;
     StagedGroup S1, S2;
     float* table;
-    stage_groups(g, r, smem4, S1, S2, table, g.n_type1 * g.n_type2 * g.n_param);
-    const int lane = threadIdx.x % CG, n_grp = CTPB / CG;
-    for (int i0 = 0; i0 < g.s1.n; i0 += n_grp) {
-        int i = i0 + threadIdx.x / CG;
-        float acc = 0.f;
-        if (i < g.s1.n) {
-            float x1[8];
-            unpack8(S1, i, x1);
-            const float* p = table + S1.type[i] * g.n_type2 * g.n_param;
-            const unsigned short* row = g.nbr1 + (size_t(r) * g.s1.n + i) * g.K1;
-            int cnt = g.cnt1[size_t(r) * g.s1.n + i];
-            for (int k = lane; k < cnt; k += CG) {
-                int j = row[k];
-                float4 v = S2.a[j];
-                float x2[4] = {v.x, v.y, v.z, v.w}, d1[6], d2[4];
-                acc += environment_edge(p + S2.type[j] * g.n_param, x1, x2, d1, d2);
-            }
-        }
-        acc = group_sum<CG>(acc);
-        if (i < g.s1.n && lane == 0) out[size_t(r) * g.s1.n + i] = acc;
-    }
-}
-__global__ void __launch_bounds__(CTPB) k_env_coverage_deriv(IGraphDev g, const float* __restrict__ sens) {
-    extern __shared__ float4 smem4[];
-    const int r = blockIdx.x;
-    StagedGroup S1, S2;
-    float* table;
-    stage_groups(g, r, smem4, S1, S2, table, g.n_type1 * g.n_type2 * g.n_param);
-    const int lane = threadIdx.x % CG, n_grp = CTPB / CG;
-    const float* sn = sens + size_t(r) * g.s1.n;
-    for (int i0 = 0; i0 < g.s1.n; i0 += n_grp) {
-        int i = i0 + threadIdx.x / CG;
-        float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        float si = 0.f;
-        if (i < g.s1.n) {
-            si = sn[i];
-            float x1[8];
-            unpack8(S1, i, x1);
-            const float* p = table + S1.type[i] * g.n_type2 * g.n_param;
-            const unsigned short* row = g.nbr1 + (size_t(r) * g.s1.n + i) * g.K1;
-            int cnt = (si != 0.f) ? g.cnt1[size_t(r) * g.s1.n + i] : 0;
-            for (int k = lane; k < cnt; k += CG) {
-                int j = row[k];
-                float4 v = S2.a[j];
-                float x2[4] = {v.x, v.y, v.z, v.w}, d1[6], d2[4];
-                environment_edge(p + S2.type[j] * g.n_param, x1, x2, d1, d2);
-#pragma unroll
-                for (int c = 0; c < 6; ++c) acc[c] += d1[c];
-            }
-        }
-#pragma unroll
-        for (int c = 0; c < 6; ++c) acc[c] = group_sum<CG>(acc[c]);
-        if (i < g.s1.n && lane == 0 && si != 0.f) {
-            float* dst = elem_sens_ptr(g.s1, r, i);
-#pragma unroll
-            for (int c = 0; c < 6; ++c) dst[c] += si * acc[c];
-        }
-    }
-    for (int j0 = 0; j0 < g.s2.n; j0 += n_grp) {
-        int j = j0 + threadIdx.x / CG;
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
-        if (j < g.s2.n) {
-            float4 v = S2.a[j];
-            float x2[4] = {v.x, v.y, v.z, v.w};
-            int t2 = S2.type[j];
-            const unsigned short* row = g.nbr2 + (size_t(r) * g.s2.n + j) * g.K2;
-            int cnt = g.cnt2[size_t(r) * g.s2.n + j];
-            for (int k = lane; k < cnt; k += CG) {
-                int i = row[k];
-                float si = sn[i];
+    const int n_tab = g.n_type1 * g.n_type2 * g.n_param;
+    EdgeScratch E = carve_edge_scratch(carve_groups(g, smem4, S1, S2, table, n_tab), n_rows_max, 1);
+    stage_table(g, S1, S2, table, n_tab);
+    for (int r = blockIdx.x; r < n_rep; r += gridDim.x) {
+        stage_groups(g, r, S1, S2);
+        const int* cnt = g.cnt1 + size_t(r) * g.s1.n;
+        scan_row_lengths(g.s1.n, [&](int i) { return cnt[i]; }, E.start, E.wtot);
+        for_each_edge<1>(g.s1.n, g.nbr1 + size_t(r) * g.s1.n * g.K1, g.K1, E,
+            [&](int i, int j, float* o) {
                 float x1[8], d1[6], d2[4];
                 unpack8(S1, i, x1);
-                environment_edge(table + (S1.type[i] * g.n_type2 + t2) * g.n_param, x1, x2, d1, d2);
+                float4 v = S2.a[j];
+                float x2[4] = {v.x, v.y, v.z, v.w};
+                o[0] = environment_edge(table + (S1.type[i] * g.n_type2 + S2.type[j]) * g.n_param, x1, x2, d1, d2);
+            },
+            [&](int i, int, const float* s) { out[size_t(r) * g.s1.n + i] = s[0]; });
+    }
+}
+__global__ void __launch_bounds__(CTPB) k_env_coverage_deriv(IGraphDev g, const float* __restrict__ sens, int n_rep, int n_rows_max) {
+    extern __shared__ float4 smem4[];
+    StagedGroup S1, S2;
+    float* table;
+    const int n_tab = g.n_type1 * g.n_type2 * g.n_param;
+    EdgeScratch E = carve_edge_scratch(carve_groups(g, smem4, S1, S2, table, n_tab), n_rows_max, 6);
+    float* sn = reinterpret_cast<float*>(E.wtot + 33);   // [n1] sens of this replica's CB coverages
+    stage_table(g, S1, S2, table, n_tab);
+    for (int r = blockIdx.x; r < n_rep; r += gridDim.x) {
+        stage_groups(g, r, S1, S2);   // (leading barrier: previous replica's readers of sn are done)
+        for (int i = threadIdx.x; i < g.s1.n; i += blockDim.x) sn[i] = sens[size_t(r) * g.s1.n + i];
+        __syncthreads();
+        const int* cnt1 = g.cnt1 + size_t(r) * g.s1.n;
+        scan_row_lengths(g.s1.n, [&](int i) { return sn[i] != 0.f ? cnt1[i] : 0; }, E.start, E.wtot);
+        for_each_edge<6>(g.s1.n, g.nbr1 + size_t(r) * g.s1.n * g.K1, g.K1, E,
+            [&](int i, int j, float* o) {
+                float x1[8], d2[4];
+                unpack8(S1, i, x1);
+                float4 v = S2.a[j];
+                float x2[4] = {v.x, v.y, v.z, v.w};
+                environment_edge(table + (S1.type[i] * g.n_type2 + S2.type[j]) * g.n_param, x1, x2, o, d2);
+            },
+            [&](int i, int c, const float* s) {
+                if (!c) return;
+                float* dst = elem_sens_ptr(g.s1, r, i);
+                const float si = sn[i];
+                float4 a = reinterpret_cast<float4*>(dst)[0], b = reinterpret_cast<float4*>(dst)[1];
+                a.x += si * s[0]; a.y += si * s[1]; a.z += si * s[2]; a.w += si * s[3]; b.x += si * s[4]; b.y += si * s[5];
+                reinterpret_cast<float4*>(dst)[0] = a; reinterpret_cast<float4*>(dst)[1] = b;
+            });
+        const int* cnt2 = g.cnt2 + size_t(r) * g.s2.n;
+        scan_row_lengths(g.s2.n, [&](int j) { return cnt2[j]; }, E.start, E.wtot);
+        for_each_edge<4>(g.s2.n, g.nbr2 + size_t(r) * g.s2.n * g.K2, g.K2, E,
+            [&](int j, int i, float* o) {
+                float x1[8], d1[6];
+                unpack8(S1, i, x1);
+                float4 v = S2.a[j];
+                float x2[4] = {v.x, v.y, v.z, v.w};
+                environment_edge(table + (S1.type[i] * g.n_type2 + S2.type[j]) * g.n_param, x1, x2, d1, o);
+                const float si = sn[i];
 #pragma unroll
-                for (int c = 0; c < 4; ++c) acc[c] += si * d2[c];
-            }
-        }
-#pragma unroll
-        for (int c = 0; c < 4; ++c) acc[c] = group_sum<CG>(acc[c]);
-        if (j < g.s2.n && lane == 0) {
-            float4* dst = reinterpret_cast<float4*>(elem_sens_ptr(g.s2, r, j));
-            float4 o = *dst;
-            o.x += acc[0]; o.y += acc[1]; o.z += acc[2]; o.w += acc[3];
-            *dst = o;
-        }
+                for (int c = 0; c < 4; ++c) o[c] *= si;
+            },
+            [&](int j, int c, const float* s) {
+                if (!c) return;
+                float4* dst = reinterpret_cast<float4*>(elem_sens_ptr(g.s2, r, j));
+                float4 o = *dst;
+                o.x += s[0]; o.y += s[1]; o.z += s[2]; o.w += s[3];
+                *dst = o;
+            });
     }
 }
 struct EnvironmentCoverage : CoordNode {
     IGraphHost ig;
-    size_t smem = 0;
+    CoverageLaunch launch;
     EnvironmentCoverage(Engine&, const h5l::Node& g, CoordNode& cb, CoordNode& wsc)
         : CoordNode((int)h5_dims(g, "index1", 1)[0], 1), ig(g, false, EXCL_SEQ2, 6, 4, &cb, &wsc) {
         if (ig.n_param != 4) throw std::string("environment_coverage expects 4 interaction parameters");
@@ -294,21 +283,16 @@ struct EnvironmentCoverage : CoordNode {
     }
     void finalize() override {
         ig.allocate(engine);
-        smem = staged_bytes(ig.n1, ig.n2, ig.n_type1 * ig.n_type2 * ig.n_param);
-        int lim = 0;
-        UB_CUDA(cudaDeviceGetAttribute(&lim, cudaDevAttrMaxSharedMemoryPerBlockOptin, engine->device));
-        if (smem > (size_t)lim) throw std::string("environment_coverage: system too large for the shared-memory kernels");
-        UB_CUDA(cudaFuncSetAttribute(k_env_coverage, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        UB_CUDA(cudaFuncSetAttribute(k_env_coverage_deriv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        launch.init(engine, ig, 6, ig.n1, (const void*)k_env_coverage, (const void*)k_env_coverage_deriv, "environment_coverage");
     }
     void compute_value(cudaStream_t s, ComputeMode) override {
         if (!n_elem) return;
         ig.build(s);
-        k_env_coverage<<<engine->n_rep, CTPB, smem, s>>>(ig.dev(), output);
+        k_env_coverage<<<launch.grid_fwd, CTPB, launch.smem_fwd, s>>>(ig.dev(), output, engine->n_rep, launch.n_rows_max);
     }
     void propagate_deriv(cudaStream_t s) override {
         if (!n_elem) return;
-        k_env_coverage_deriv<<<engine->n_rep, CTPB, smem, s>>>(ig.dev(), sens);
+        k_env_coverage_deriv<<<launch.grid_bwd, CTPB, launch.smem_bwd, s>>>(ig.dev(), sens, engine->n_rep, launch.n_rows_max);
     }
     bool get_pairlist(int replica, std::vector<int>& i1, std::vector<int>& i2) override { return ig.pairlist(replica, i1, i2); }
     std::vector<float> get_param() const override { return ig.h_param; }

@@ -13,7 +13,9 @@ namespace ub {
 static int neighbor_capacity(float cutoff, int n_other) {
     double scale = 1.0;
     if (const char* s = getenv("UPSIDE_B200_NEIGHBOR_SCALE")) scale = std::max(0.05, atof(s));
-    double k = scale * (8. + 0.55 * double(cutoff) * cutoff * cutoff);
+    // 0.75 elements per cubic Angstrom of the cutoff sphere: side-chain beads come up to six per residue (one per rotamer
+    // state), so clashing starting structures pack far more of them around a site than a relaxed chain does
+    double k = scale * (16. + 0.75 * double(cutoff) * cutoff * cutoff);
     int K = (int)std::min<double>(n_other, std::ceil(k));
     return std::max(K, 1);
 }
@@ -64,8 +66,8 @@ void IGraphHost::allocate(Engine* e) {
     if (const char* s = getenv("UPSIDE_B200_NO_VERLET_CACHE")) use_cache = atoi(s) == 0;
     if (use_cache) {
         skin = 1.0f + 0.2f * cutoff;   // cache_buffer of the reference, interaction_graph.h:395-396
-        Kc1 = neighbor_capacity(cutoff + skin, n2);
-        Kc2 = symmetric ? Kc1 : neighbor_capacity(cutoff + skin, n1);
+        Kc1 = (neighbor_capacity(cutoff + skin, n2) + 7) & ~7;   // slices of eight (see k_pairlist)
+        Kc2 = symmetric ? Kc1 : (neighbor_capacity(cutoff + skin, n1) + 7) & ~7;
         cand1.alloc(size_t(e->n_rep) * n1 * Kc1);
         ccnt1.alloc(size_t(e->n_rep) * n1);
         cpos1.alloc(size_t(e->n_rep) * n1 * 4);
@@ -121,7 +123,7 @@ void IGraphHost::build(cudaStream_t s) {
                                                                            d.error_flag, rep_list.p, n_list.p, 1);
     RefineTable T1{cand1.p, ccnt1.p, Kc1, d.nbr1, d.cnt1, d.K1};
     RefineTable T2{cand2.p, ccnt2.p, Kc2, symmetric ? nullptr : d.nbr2, symmetric ? nullptr : d.cnt2, d.K2};
-    size_t smem = sizeof(float4) * size_t(symmetric ? n1 : n1 + n2);
+    size_t smem = sizeof(float4) * size_t(symmetric ? n1 + 1 : n1 + n2 + 2);
     k_refine<RGL><<<B, 256, smem, s>>>(d.s1, d.s2, symmetric ? 0 : 1, T1, T2, d.cutoff2, d.error_flag);
 }
 

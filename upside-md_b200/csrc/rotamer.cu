@@ -64,6 +64,9 @@ struct RotamerDev {
     int* istart;              // [B][n_res+1]
     float* node_marg;         // [B][n_res][6]
     int* stats;               // [B][4]: n_iter, n_pair, converged, -
+    int* slow_list;           // [B] replicas the fast BP kernel declined
+    int* n_slow;              // [1] (reset by k_rot_prep)
+    int n_rep;
     float* potential;
     int* error_flag;
 };
@@ -118,7 +121,12 @@ __global__ void __launch_bounds__(PREP_TPB) k_rot_prep(RotamerDev P) {
                 int j = row[k];
                 lo += j < i;
                 int other = rr[j];
-                if (me & other & 1) atomicOr(&bitmap[(me >> 4) * nW + (other >> 9)], 1u << ((other >> 4) & 31));
+                if (me & other & 1) {
+                    // both directions, so that the adjacency stays symmetric even if a row was truncated by a capacity
+                    // overflow (reported through error_flag): every index derived below relies on that symmetry
+                    atomicOr(&bitmap[(me >> 4) * nW + (other >> 9)], 1u << ((other >> 4) & 31));
+                    atomicOr(&bitmap[(other >> 4) * nW + (me >> 9)], 1u << ((me >> 4) & 31));
+                }
             }
         }
 #pragma unroll
@@ -155,8 +163,11 @@ __global__ void __launch_bounds__(PREP_TPB) k_rot_prep(RotamerDev P) {
     __syncthreads();
     const int n_pair = estart[nR];
     if (tid == 0) { P.stats[size_t(r) * 4 + 1] = n_pair; P.e11[r] = 0.f; }
-    if (n_pair > P.max_pairs) {   // uniform across the block
+    if (tid == 0 && r == 0) *P.n_slow = 0;
+    if (n_pair > P.max_pairs) {   // uniform across the block: report, and leave an empty (consistent) graph behind
         if (tid == 0) { atomicExch(P.error_flag, 2); P.stats[size_t(r) * 4 + 1] = 0; }
+        for (int A = tid; A <= nR; A += PREP_TPB) P.istart[size_t(r) * (nR + 1) + A] = 0;
+        for (int i = tid; i < P.n_bead * K; i += PREP_TPB) code[i] = CODE_SS;
         return;
     }
     unsigned short* pair_ab = P.pair_ab + size_t(r) * P.max_pairs * 2;
@@ -526,9 +537,20 @@ __device__ __forceinline__ float bp_nodes(const int* res_nrot, int n_res, const 
     return dev;
 }
 
-__global__ void __launch_bounds__(BP_TPB) k_rot_bp(RotamerDev P, int want_pot) {
+// General path: any state count <= 6, any pair count (spills to global memory).  With `use_list` the CTAs stride over the
+// replicas the fast kernel declined (slow_list); otherwise CTA r solves replica r.
+__device__ void bp_solve_generic(const RotamerDev& P, int want_pot, int r, float* smem);
+__global__ void __launch_bounds__(BP_TPB) k_rot_bp(RotamerDev P, int want_pot, int use_list) {
     extern __shared__ float smem[];
-    const int r = blockIdx.x, tid = threadIdx.x;
+    if (!use_list) { bp_solve_generic(P, want_pot, blockIdx.x, smem); return; }
+    const int n = *P.n_slow;
+    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+        __syncthreads();
+        bp_solve_generic(P, want_pot, P.slow_list[i], smem);
+    }
+}
+__device__ void bp_solve_generic(const RotamerDev& P, int want_pot, int r, float* smem) {
+    const int tid = threadIdx.x;
     const int nR = P.n_res, SP = P.smem_pairs;
     const int n_pair = P.stats[size_t(r) * 4 + 1];
     float* prob = smem;                         // [nR][6]
@@ -547,7 +569,7 @@ __global__ void __launch_bounds__(BP_TPB) k_rot_bp(RotamerDev P, int want_pot) {
     // replicas whose pair count exceeds the shared-memory budget run the same code on their global scratch; their
     // messages spill to the area allocated behind the node marginals
     float* Pm = in_smem ? sm_P : g_pmat;
-    float* msg = in_smem ? sm_msg : P.node_marg + size_t(gridDim.x) * nR * MAXR + size_t(r) * P.max_pairs * 12;
+    float* msg = in_smem ? sm_msg : P.node_marg + size_t(P.n_rep) * nR * MAXR + size_t(r) * P.max_pairs * 12;
     const Lay lp = in_smem ? Lay{1, SP} : Lay{36, 1};
     const Lay lm = in_smem ? Lay{1, SP} : Lay{12, 1};
     const unsigned short* pair_ab = P.pair_ab + size_t(r) * P.max_pairs * 2;
@@ -665,6 +687,348 @@ __global__ void __launch_bounds__(BP_TPB) k_rot_bp(RotamerDev P, int want_pot) {
     }
 }
 
+// ================================================================================================ belief propagation, fast path
+// k_rot_bp2: the solver of k_rot_bp re-laid for throughput.  Residue pairs are oriented (fewer states first) and sorted
+// by class (6x6 | 3x6 | 3x3; the reference keeps separate 33/36/66 edge holders, rotamer.cpp:527-539), so that
+//   * pair matrices occupy 36/18/9 floats instead of a padded 36 (three resident CTAs per SM instead of two),
+//   * a warp of the message phase runs ONE unrolled nA x nB body without padding work,
+// and the node update runs 8 lanes per residue (one per state) instead of one thread per residue, which cuts the serial
+// chain per sweep to one shared-memory round trip per four incident pairs.  The sweep-end barrier doubles as the
+// convergence vote (__syncthreads_or).  Replicas that do not fit the shared-memory budget (or configurations with state
+// counts other than 1/3/6) are appended to slow_list and solved by k_rot_bp.
+constexpr int BP2_TPB = 384;
+
+struct Bp2Lay {
+    int nRp;     // padded residue count of the component-major belief arrays (== 4 mod 32: conflict-free node update)
+    int SP;      // pair capacity (== 4 mod 32)
+    int Pcap;    // floats available for pair matrices
+};
+
+template <int NA, int NB>
+__device__ __forceinline__ void bp2_pair(const float* __restrict__ bel, int nRp, int F, int S, float* __restrict__ msg, int SP, int p,
+                                         const float* __restrict__ Pc, int nc, int q) {
+    float v1[NA], v2[NB], m1[NA], m2[NB];
+#pragma unroll
+    for (int a = 0; a < NA; ++a) { v1[a] = __fdividef(bel[a * nRp + F], 1e-10f + msg[a * SP + p]); m1[a] = 0.f; }
+#pragma unroll
+    for (int b = 0; b < NB; ++b) { v2[b] = __fdividef(bel[b * nRp + S], 1e-10f + msg[(6 + b) * SP + p]); m2[b] = 0.f; }
+#pragma unroll
+    for (int a = 0; a < NA; ++a)
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            float pr = Pc[(a * NB + b) * nc + q];
+            m1[a] = fmaf(pr, v2[b], m1[a]);   // apply_left : message to the first residue
+            m2[b] = fmaf(v1[a], pr, m2[b]);   // apply_right: message to the second residue
+        }
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int a = 0; a < NA; ++a) s1 += m1[a];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) s2 += m2[b];
+    float i1 = __fdividef(1.f, s1), i2 = __fdividef(1.f, s2);
+#pragma unroll
+    for (int a = 0; a < NA; ++a) msg[a * SP + p] = m1[a] * i1;
+#pragma unroll
+    for (int b = 0; b < NB; ++b) msg[(6 + b) * SP + p] = m2[b] * i2;
+}
+
+// pair marginal (rotamer.cpp:403-429) written back in the pair's original (A,B) orientation, plus its Bethe term (:431-451)
+template <int NA, int NB>
+__device__ __forceinline__ float bp2_pair_marginal(const float* __restrict__ bel, int nRp, int F, int S, const float* __restrict__ msg,
+                                                   int SP, int p, const float* __restrict__ Pc, int nc, int q, float* __restrict__ out,
+                                                   bool swapped, int want_pot) {
+    float bc1[NA], bc2[NB], b1[NA], b2[NB];
+#pragma unroll
+    for (int a = 0; a < NA; ++a) { b1[a] = bel[a * nRp + F]; bc1[a] = b1[a] / (1e-10f + msg[a * SP + p]); }
+#pragma unroll
+    for (int b = 0; b < NB; ++b) { b2[b] = bel[b * nRp + S]; bc2[b] = b2[b] / (1e-10f + msg[(6 + b) * SP + p]); }
+    float s = 0.f;
+#pragma unroll
+    for (int a = 0; a < NA; ++a)
+#pragma unroll
+        for (int b = 0; b < NB; ++b) s += Pc[(a * NB + b) * nc + q] * bc1[a] * bc2[b];
+    float is = 1.f / s, en = 0.f;
+#pragma unroll
+    for (int a = 0; a < NA; ++a)
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            float pr = Pc[(a * NB + b) * nc + q];
+            float mg = pr * bc1[a] * bc2[b] * is;
+            if (want_pot) en += mg * __logf((1e-10f + mg) / (1e-10f + pr * b1[a] * b2[b]));
+            out[swapped ? b * 6 + a : a * 6 + b] = mg;
+        }
+    return en;
+}
+
+// node update: belief = prob * prod(incoming messages), max-normalised and damped (rotamer.cpp:488-499,258-273).  One thread
+// per residue; four incident pairs per step so that the index loads and the 4*NA message loads of a step are independent
+// (one shared-memory round trip per four pairs).  inc2 holds word offsets of the messages' component-0 entries; entries
+// past the end of the list read the column of ones.
+template <int NA>
+__device__ __forceinline__ float bp2_node(int A, const float* __restrict__ prob, float* __restrict__ bel, int nRp, int t0, int t1,
+                                          const int* __restrict__ inc2, const float* __restrict__ msg, int SP, int dummy, float damping) {
+    float b[NA];
+#pragma unroll
+    for (int a = 0; a < NA; ++a) b[a] = prob[a * nRp + A];
+    for (int t = t0; t < t1; t += 4) {
+        int off[4];
+        float m[4][NA];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) off[u] = t + u < t1 ? inc2[t + u] : dummy;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int a = 0; a < NA; ++a) m[u][a] = msg[off[u] + a * SP];
+        float s = 0.f;
+#pragma unroll
+        for (int a = 0; a < NA; ++a) { b[a] *= (m[0][a] * m[1][a]) * (m[2][a] * m[3][a]); s += b[a]; }
+        // renormalise (pure rescaling, rotamer.cpp:492-493): a product of four L1-normalised messages cannot underflow
+        const float is = __fdividef(1.f, s);
+#pragma unroll
+        for (int a = 0; a < NA; ++a) b[a] *= is;
+    }
+    float mx = b[0];
+#pragma unroll
+    for (int a = 1; a < NA; ++a) mx = fmaxf(mx, b[a]);
+    const float imx = __fdividef(1.f, mx);
+    float dev = 0.f;
+#pragma unroll
+    for (int a = 0; a < NA; ++a) {
+        const float o = bel[a * nRp + A];
+        const float n = (damping != 0.f) ? (1.f - damping) * imx * b[a] + damping * o : imx * b[a];
+        dev = fmaxf(dev, n - o);
+        bel[a * nRp + A] = n;
+    }
+    return dev;
+}
+
+__global__ void __launch_bounds__(BP2_TPB, 3) k_rot_bp2(RotamerDev P, Bp2Lay L, int want_pot) {
+    extern __shared__ float smem[];
+    const int r = blockIdx.x, tid = threadIdx.x;
+    const int nR = P.n_res, nRp = L.nRp, SP = L.SP;
+    const int n_pair = P.stats[size_t(r) * 4 + 1];
+    float* prob = smem;                          // [6][nRp]
+    float* bel = prob + 6 * nRp;                 // [6][nRp]
+    float* offs = bel + 6 * nRp;                 // [nR]
+    float* red = offs + nR;                      // [32]
+    int* istart = reinterpret_cast<int*>(red + 32);     // [nR+1]
+    int* nrot = istart + nR + 1;                         // [nR]
+    unsigned long long* wscan = reinterpret_cast<unsigned long long*>(nrot + nR + ((nR + 1) & 1));   // [34], 8-byte aligned
+    float* msg = reinterpret_cast<float*>(wscan + 34);   // [12][SP]
+    float* Pm = msg + 12 * SP;                           // [Pcap]: 6x6 block [36][n66] | 3x6 block [18][n36] | 3x3 block [9][n33]
+    int* inc2 = reinterpret_cast<int*>(Pm + L.Pcap);     // [2*SP] word offset of component 0 of each incident message
+    unsigned short* pos = reinterpret_cast<unsigned short*>(inc2 + 2 * SP);   // [SP] slot e -> sorted position p
+    unsigned short* perm = pos + SP;                     // [SP] p -> e
+    unsigned short* fs = perm + SP;                      // [2*SP] first/second residue of p, bit 15 of fs[2p] = swapped
+    unsigned short* nlist = fs + 2 * SP;                 // [nR] multi-state residues: 6-state first, then by falling degree
+    __shared__ int n_multi_s;
+
+    const unsigned short* pair_ab = P.pair_ab + size_t(r) * P.max_pairs * 2;
+    const int* inc = P.inc + size_t(r) * 2 * P.max_pairs;
+    float* g_pmat = P.pmat + size_t(r) * P.max_pairs * 36;
+    float* node_marg = P.node_marg + size_t(r) * nR * MAXR;
+    int* st = P.stats + size_t(r) * 4;
+
+    if (tid == 0) n_multi_s = 0;
+    for (int i = tid; i < nR; i += BP2_TPB) nrot[i] = P.res_nrot[i];
+    for (int i = tid; i <= nR; i += BP2_TPB) istart[i] = P.istart[size_t(r) * (nR + 1) + i];
+    for (int i = tid; i < 6 * nRp; i += BP2_TPB) bel[i] = 0.f;
+    __syncthreads();
+
+    // ---- orient and sort the pairs by class: one packed scan (three 21-bit counters) -------------------------------------
+    int n66, n36, n33;
+    {
+        const int lane = tid & 31, w = tid >> 5;
+        const int per = (n_pair + BP2_TPB - 1) / BP2_TPB;
+        const int e0 = min(n_pair, tid * per), e1 = min(n_pair, e0 + per);
+        auto cls = [&](int e) {
+            int nA = nrot[pair_ab[2 * e]], nB = nrot[pair_ab[2 * e + 1]];
+            return (nA == 6 && nB == 6) ? 0 : ((nA == 3 && nB == 3) ? 2 : 1);
+        };
+        unsigned long long s = 0ull;
+        for (int e = e0; e < e1; ++e) s += 1ull << (21 * cls(e));
+        unsigned long long incl = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { unsigned long long v = __shfl_up_sync(UB_FULL_MASK, incl, o); if (lane >= o) incl += v; }
+        if (lane == 31) wscan[w] = incl;
+        __syncthreads();
+        if (w == 0) {
+            unsigned long long v = lane < BP2_TPB / 32 ? wscan[lane] : 0ull, iv = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { unsigned long long u = __shfl_up_sync(UB_FULL_MASK, iv, o); if (lane >= o) iv += u; }
+            wscan[lane] = iv - v;
+            if (lane == 31) wscan[32] = iv;
+        }
+        __syncthreads();
+        const unsigned long long tot = wscan[32];
+        n66 = int(tot & 0x1fffff); n36 = int((tot >> 21) & 0x1fffff); n33 = int((tot >> 42) & 0x1fffff);
+        const bool fits = n_pair <= SP - 1 && 36 * n66 + 18 * n36 + 9 * n33 <= L.Pcap;   // column SP-1 is the neutral message
+        if (!fits) {   // uniform: k_rot_bp solves this replica
+            if (tid == 0) P.slow_list[atomicAdd(P.n_slow, 1)] = r;
+            return;
+        }
+        unsigned long long run = wscan[w] + incl - s;
+        const int cbase[3] = {0, n66, n66 + n36};
+        for (int e = e0; e < e1; ++e) {
+            int c = cls(e);
+            int p = cbase[c] + int((run >> (21 * c)) & 0x1fffff);
+            run += 1ull << (21 * c);
+            int A = pair_ab[2 * e], B = pair_ab[2 * e + 1];
+            bool sw = nrot[A] > nrot[B];
+            pos[e] = (unsigned short)p;
+            perm[p] = (unsigned short)e;
+            fs[2 * p] = (unsigned short)((sw ? B : A) | (sw ? 0x8000 : 0));
+            fs[2 * p + 1] = (unsigned short)(sw ? A : B);
+        }
+    }
+    const float* P66 = Pm;
+    const float* P36 = Pm + 36 * n66;
+    const float* P33 = P36 + 18 * n36;
+
+    // ---- node energies -> probabilities (convert_energy_to_prob :239-256; single-state partners already folded) ----------
+    for (int i = tid; i < nR * MAXR; i += BP2_TPB) { int A = i / MAXR, a = i % MAXR; bel[a * nRp + A] = P.enode[size_t(r) * nR * MAXR + i]; }
+    __syncthreads();
+    for (int A = tid; A < nR; A += BP2_TPB) {   // energy offset = smallest 1-body energy
+        float m = bel[A];
+        for (int a = 1; a < nrot[A]; ++a) m = fminf(m, bel[a * nRp + A]);
+        offs[A] = m;
+    }
+    __syncthreads();
+    for (int i = tid; i < P.n_bead; i += BP2_TPB) {
+        float f = P.fold[size_t(r) * P.n_bead + i];
+        if (f != 0.f) atomicAdd(&bel[P.bead_rot[i] * nRp + P.bead_res[i]], f);
+    }
+    __syncthreads();
+    for (int i = tid; i < 6 * nR; i += BP2_TPB) {
+        int a = i / nR, A = i - a * nR;
+        float pr = a < nrot[A] ? __expf(offs[A] - bel[a * nRp + A]) : 0.f;
+        prob[a * nRp + A] = pr;
+    }
+    {   // pair energies -> probabilities: coalesced 16-byte reads of the replica's pair-major energy array
+        const float4* src = reinterpret_cast<const float4*>(g_pmat);
+        for (int i = tid; i < n_pair * 9; i += BP2_TPB) {
+            float4 v = src[i];
+            const int e = i / 9, k0 = (i - e * 9) * 4;
+            const int A = pair_ab[2 * e], B = pair_ab[2 * e + 1], nA = nrot[A], nB = nrot[B];
+            const int p = pos[e];
+            const bool sw = nA > nB;
+            const int nF = sw ? nB : nA, nS = sw ? nA : nB;
+            float* blk; int nc, q;
+            if (nF == 6) { blk = Pm; nc = n66; q = p; }
+            else if (nS == 6) { blk = Pm + 36 * n66; nc = n36; q = p - n66; }
+            else { blk = Pm + 36 * n66 + 18 * n36; nc = n33; q = p - n66 - n36; }
+            const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                int k = k0 + u, a = k / 6, b = k - a * 6;
+                if (a < nA && b < nB) {
+                    int f = sw ? b : a, s2 = sw ? a : b;
+                    blk[(f * nS + s2) * nc + q] = __expf(-vv[u]);
+                }
+            }
+        }
+    }
+    for (int t = tid; t < 2 * n_pair; t += BP2_TPB) {
+        int cd = inc[t], p = pos[cd >> 1];
+        inc2[t] = ((cd & 1) ^ (fs[2 * p] >> 15)) * 6 * SP + p;
+    }
+    for (int k = tid; k < 12; k += BP2_TPB) msg[k * SP + SP - 1] = 1.f;
+    // residues in the order the node update takes them: rank by (state count, degree) falling, ties by index, so that the
+    // threads of a warp run the same unrolled body for about the same number of steps
+    for (int A = tid; A < nR; A += BP2_TPB) {
+        const int nA = nrot[A];
+        if (nA < 2) continue;
+        const int key = (nA << 16) | (istart[A + 1] - istart[A]);
+        int rank = 0;
+        for (int C = 0; C < nR; ++C) {
+            const int nC = nrot[C];
+            const int kc = (nC << 16) | (istart[C + 1] - istart[C]);
+            rank += (nC >= 2) && (kc > key || (kc == key && C < A));
+        }
+        nlist[rank] = (unsigned short)A;
+        atomicAdd(&n_multi_s, 1);
+    }
+    for (int p = tid; p < n_pair; p += BP2_TPB) {
+        int nF = nrot[fs[2 * p] & 0x7fff], nS = nrot[fs[2 * p + 1]];
+        for (int a = 0; a < 6; ++a) { msg[a * SP + p] = a < nF ? 1.f : 0.f; msg[(6 + a) * SP + p] = a < nS ? 1.f : 0.f; }
+    }
+    __syncthreads();
+    for (int i = tid; i < 6 * nRp; i += BP2_TPB) bel[i] = prob[i];
+    __syncthreads();
+
+    // ---- sweeps -------------------------------------------------------------------------------------------------------------
+    auto messages = [&]() {
+        for (int p = tid; p < n_pair; p += BP2_TPB) {
+            const int F = fs[2 * p] & 0x7fff, S = fs[2 * p + 1];
+            if (p < n66) bp2_pair<6, 6>(bel, nRp, F, S, msg, SP, p, P66, n66, p);
+            else if (p < n66 + n36) bp2_pair<3, 6>(bel, nRp, F, S, msg, SP, p, P36, n36, p - n66);
+            else bp2_pair<3, 3>(bel, nRp, F, S, msg, SP, p, P33, n33, p - n66 - n36);
+        }
+    };
+    const int n_multi = n_multi_s;
+    const float damping = P.damping;
+    const int dummy = SP - 1;   // column SP-1 of the side-0 rows holds ones: the neutral message
+    auto nodes = [&]() -> float {
+        float dev = 0.f;
+        for (int i = tid; i < n_multi; i += BP2_TPB) {
+            const int A = nlist[i];
+            if (nrot[A] == 6) dev = fmaxf(dev, bp2_node<6>(A, prob, bel, nRp, istart[A], istart[A + 1], inc2, msg, SP, dummy, damping));
+            else dev = fmaxf(dev, bp2_node<3>(A, prob, bel, nRp, istart[A], istart[A + 1], inc2, msg, SP, dummy, damping));
+        }
+        return dev;
+    };
+    // initial sweep: first messages from (prob, unit messages); node beliefs restart from prob/max (rotamer.cpp:1034)
+    messages();
+    __syncthreads();
+    for (int A = tid; A < nR; A += BP2_TPB) {
+        float mx = prob[A];
+        for (int k = 1; k < MAXR; ++k) mx = fmaxf(mx, prob[k * nRp + A]);
+        float imx = 1.f / mx;
+        for (int k = 0; k < MAXR; ++k) bel[k * nRp + A] = prob[k * nRp + A] * imx;
+    }
+    __syncthreads();
+    int iter = 0, unconverged = 1;
+    for (; unconverged && iter < P.max_iter; iter += P.chunk) {
+        float dev = 0.f;
+        for (int j = 0; j < P.chunk; ++j) {
+            messages();
+            __syncthreads();
+            dev = nodes();
+            if (j + 1 < P.chunk) __syncthreads();
+        }
+        unconverged = __syncthreads_or(dev > P.tol);
+    }
+    if (tid == 0) { st[0] = iter; st[2] = !unconverged; }
+
+    // ---- marginals (and Bethe free energy) ----------------------------------------------------------------------------------
+    float en = 0.f;
+    for (int A = tid; A < nR; A += BP2_TPB) {
+        int nA = nrot[A];
+        float b[MAXR], s = 0.f;
+        for (int k = 0; k < MAXR; ++k) { b[k] = nA > 1 ? bel[k * nRp + A] : (k == 0 ? 1.f : 0.f); s += b[k]; }
+        float is = 1.f / s;
+        for (int k = 0; k < MAXR; ++k) { b[k] *= is; bel[k * nRp + A] = b[k]; node_marg[A * MAXR + k] = b[k]; }
+        if (want_pot) {
+            float e = offs[A];
+            for (int k = 0; k < nA; ++k) e += b[k] * __logf((1e-10f + b[k]) / (1e-10f + prob[k * nRp + A]));
+            en += e;
+        }
+    }
+    __syncthreads();
+    for (int p = tid; p < n_pair; p += BP2_TPB) {
+        const int F = fs[2 * p] & 0x7fff, S = fs[2 * p + 1];
+        const bool sw = fs[2 * p] >> 15;
+        float* out = g_pmat + size_t(perm[p]) * 36;
+        if (p < n66) en += bp2_pair_marginal<6, 6>(bel, nRp, F, S, msg, SP, p, P66, n66, p, out, sw, want_pot);
+        else if (p < n66 + n36) en += bp2_pair_marginal<3, 6>(bel, nRp, F, S, msg, SP, p, P36, n36, p - n66, out, sw, want_pot);
+        else en += bp2_pair_marginal<3, 3>(bel, nRp, F, S, msg, SP, p, P33, n33, p - n66 - n36, out, sw, want_pot);
+    }
+    if (want_pot) {
+        float tot = block_sum(en, red);
+        if (tid == 0) P.potential[r] = tot + P.e11[r];
+    }
+}
+
 struct RotamerSidechain : PotentialNode {
     std::vector<CoordNode*> prob_nodes;
     IGraphHost ig;
@@ -677,7 +1041,10 @@ struct RotamerSidechain : PotentialNode {
     DevBuf<unsigned short> pair_ab;
     float damping, tol;
     int max_iter, chunk;
-    size_t smem_prep = 0, smem_edge = 0, smem_bp = 0;
+    size_t smem_prep = 0, smem_edge = 0, smem_bp = 0, smem_bp2 = 0;
+    Bp2Lay lay2{0, 0, 0};
+    bool fast_bp = false;
+    DevBuf<int> slow_list, n_slow;
 
     RotamerSidechain(Engine&, const h5l::Node& g, const ArgList& args)
         : prob_nodes(args.begin() + 1, args.end()), ig(h5_child(g, "pair_interaction"), true, EXCL_ROTAMER, 6, 6, args[0], nullptr) {
@@ -767,6 +1134,9 @@ struct RotamerSidechain : PotentialNode {
         UB_CUDA(cudaFuncSetAttribute(k_rot_energy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_edge));
         UB_CUDA(cudaFuncSetAttribute(k_rot_deriv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_edge));
         UB_CUDA(cudaFuncSetAttribute(k_rot_bp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bp));
+        plan_fast_bp(device_smem);
+        slow_list.alloc(B);
+        n_slow.alloc(1);
         pmat.alloc(B * max_pairs * 36);
         pair_ab.alloc(B * max_pairs * 2);
         inc.alloc(B * 2 * max_pairs);
@@ -778,6 +1148,42 @@ struct RotamerSidechain : PotentialNode {
         stats.alloc(B * 4);
         code.alloc(B * size_t(ig.n1) * ig.K1);
         lower.alloc(B * ig.n1);
+    }
+    // Shared-memory plan of k_rot_bp2: the most resident CTAs per SM (at most 3) whose pair capacity still covers a typical
+    // replica (3.8 residue pairs per residue; measured 2.6-3.3 on coil-like chains) with 26 floats of
+    // pair matrix per pair (class mix of a uniform sequence: 21.8).  Larger replicas take the general kernel.
+    static size_t bp2_bytes(int nR, const Bp2Lay& L) {
+        size_t words = size_t(12) * L.nRp + nR + 32 + (2 * nR + 1) + ((nR + 1) & 1) + 2 * 34 + size_t(12) * L.SP + L.Pcap;
+        return (words + 2 * size_t(L.SP)) * 4 + (size_t(4) * L.SP + nR) * 2 + 16;
+    }
+    void plan_fast_bp(int device_smem) {
+        fast_bp = false;
+        for (int n : res_nrot) if (n != 1 && n != 3 && n != 6) return;   // the class-specialised kernel knows 3 and 6 states
+        if (getenv("UPSIDE_B200_NO_FAST_BP")) return;
+        int sm_total = 0;
+        UB_CUDA(cudaDeviceGetAttribute(&sm_total, cudaDevAttrMaxSharedMemoryPerMultiprocessor, engine->device));
+        auto pad4 = [](int v) { return ((v + 27) / 32) * 32 + 4; };   // smallest value >= v that is 4 mod 32
+        const int want_pairs = std::min<long>(max_pairs, std::max<long>(32, (long)std::ceil(3.8 * n_res)));
+        for (int occ = 3; occ >= 1; --occ) {
+            size_t budget = std::min<size_t>(device_smem, size_t(sm_total) / occ - 1024);
+            Bp2Lay L;
+            L.nRp = pad4(n_res);
+            L.SP = pad4(4); L.Pcap = 0;
+            size_t fixed = bp2_bytes(n_res, L);
+            if (fixed >= budget) continue;
+            int sp = (int)std::min<size_t>(max_pairs + 1, (budget - fixed) / (12 * 4 + 26 * 4 + 16));
+            sp = std::min(sp, 32767);
+            if (sp < want_pairs + 1 && occ > 1) continue;
+            if (sp < 8) continue;
+            L.SP = pad4(sp) > sp ? pad4(sp) - 32 : sp;   // largest value <= sp that is 4 mod 32
+            if (L.SP < 4) continue;
+            L.Pcap = 26 * L.SP;
+            lay2 = L;
+            smem_bp2 = bp2_bytes(n_res, L);
+            UB_CUDA(cudaFuncSetAttribute(k_rot_bp2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bp2));
+            fast_bp = true;
+            return;
+        }
     }
     RotamerDev dev() {
         RotamerDev P;
@@ -798,6 +1204,7 @@ struct RotamerSidechain : PotentialNode {
         P.code = code.p; P.lower = lower.p; P.enode = enode.p; P.fold = fold.p; P.e11 = e11.p;
         P.pmat = pmat.p; P.pair_ab = pair_ab.p; P.inc = inc.p; P.istart = istart.p; P.node_marg = node_marg.p; P.stats = stats.p;
         P.potential = potential; P.error_flag = engine->error_flag.p;
+        P.slow_list = slow_list.p; P.n_slow = n_slow.p; P.n_rep = engine->n_rep;
         return P;
     }
     void compute_value(cudaStream_t s, ComputeMode mode) override {
@@ -809,7 +1216,12 @@ struct RotamerSidechain : PotentialNode {
         int persist = std::min(engine->n_rep, 148 * 3);
         k_rot_prep<<<engine->n_rep, PREP_TPB, smem_prep, s>>>(P);
         k_rot_energy<<<dim3(P.n_chunk, persist), EDGE_TPB, smem_edge, s>>>(P, want, engine->n_rep);
-        k_rot_bp<<<engine->n_rep, BP_TPB, smem_bp, s>>>(P, want);
+        if (fast_bp) {
+            k_rot_bp2<<<engine->n_rep, BP2_TPB, smem_bp2, s>>>(P, lay2, want);
+            k_rot_bp<<<std::min(engine->n_rep, 148), BP_TPB, smem_bp, s>>>(P, want, 1);   // replicas the fast path declined
+        } else {
+            k_rot_bp<<<engine->n_rep, BP_TPB, smem_bp, s>>>(P, want, 0);
+        }
         k_rot_deriv<<<dim3(P.n_chunk, persist), EDGE_TPB, smem_edge, s>>>(P, engine->n_rep);
     }
     bool get_pairlist(int replica, std::vector<int>& i1, std::vector<int>& i2) override { return ig.pairlist(replica, i1, i2); }
