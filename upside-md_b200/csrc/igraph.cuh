@@ -154,31 +154,36 @@ struct RefineTable { const unsigned short* cand; const int* ccnt; int Kc; unsign
 // one thread per candidate row; a slice of eight candidates per 16-byte load, no bounds tests (padding entries index the
 // sentinel position, which is never in range); sequential compaction keeps the ascending order
 __device__ __forceinline__ void refine_rows(int r, int nA, const float4* posA, const float4* posB, RefineTable T, float cutoff2,
-                                            int a_is_first, int* error_flag) {
-    for (int i = threadIdx.x; i < nA; i += blockDim.x) {
+                                            int a_is_first, int* error_flag, int t0, int n_thread) {
+    for (int i = t0; i < nA; i += n_thread) {
         const float4 pi = posA[i];
         const int c = T.ccnt[size_t(r) * nA + i];
         const uint4* cs = reinterpret_cast<const uint4*>(T.cand + size_t(r) * T.Kc * nA) + i;
         unsigned short* row = T.nbr + (size_t(r) * nA + i) * T.K;
         int n = 0;
         const int n_slice = (c + 7) >> 3;
-        uint4 v = n_slice ? cs[0] : make_uint4(0, 0, 0, 0);
-        for (int s = 0; s < n_slice; ++s) {
-            const uint4 cur = v;
-            if (s + 1 < n_slice) v = cs[size_t(s + 1) * nA];   // next slice in flight while this one is tested
-            const unsigned w[4] = {cur.x, cur.y, cur.z, cur.w};
+        // slices are fetched four at a time (independent 16-byte loads: one memory round trip per 32 candidates)
+        for (int s0 = 0; s0 < n_slice; s0 += 4) {
+            uint4 v[4];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int j = (u & 1) ? int(w[u >> 1] >> 16) : int(w[u >> 1] & 0xffffu);
-                const float4 pj = posB[j];
-                // group 1 minus group 2, as in the reference refine step; the squares make the order immaterial
-                const float dx = a_is_first ? pi.x - pj.x : pj.x - pi.x;
-                const float dy = a_is_first ? pi.y - pj.y : pj.y - pi.y;
-                const float dz = a_is_first ? pi.z - pj.z : pj.z - pi.z;
-                const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-                if (d2 < cutoff2) {
-                    if (n < T.K) row[n] = (unsigned short)j;
-                    ++n;
+            for (int q = 0; q < 4; ++q) v[q] = s0 + q < n_slice ? cs[size_t(s0 + q) * nA] : make_uint4(0, 0, 0, 0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (s0 + q >= n_slice) break;
+                const unsigned w[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int j = (u & 1) ? int(w[u >> 1] >> 16) : int(w[u >> 1] & 0xffffu);
+                    const float4 pj = posB[j];
+                    // group 1 minus group 2, as in the reference refine step; the squares make the order immaterial
+                    const float dx = a_is_first ? pi.x - pj.x : pj.x - pi.x;
+                    const float dy = a_is_first ? pi.y - pj.y : pj.y - pi.y;
+                    const float dz = a_is_first ? pi.z - pj.z : pj.z - pi.z;
+                    const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+                    if (d2 < cutoff2) {
+                        if (n < T.K) row[n] = (unsigned short)j;
+                        ++n;
+                    }
                 }
             }
         }
@@ -207,8 +212,16 @@ __global__ void k_refine(IGraphSide A, IGraphSide Bs, int two_groups, RefineTabl
         if (threadIdx.x == 0) posB[Bs.n] = far;
     }
     __syncthreads();
-    refine_rows(r, A.n, posA, posB, T1, cutoff2, 1, error_flag);
-    if (two_groups) refine_rows(r, Bs.n, posB, posA, T2, cutoff2, 0, error_flag);
+    // one row per thread where the block is large enough; with two groups the first A.n threads (rounded up to whole
+    // warps) refine table 1 while the others refine the transposed table
+    const int T = blockDim.x;
+    if (!two_groups) { refine_rows(r, A.n, posA, posB, T1, cutoff2, 1, error_flag, threadIdx.x, T); return; }
+    const int split = min(T - 32, (A.n + 31) & ~31);
+    if (split <= 0) {
+        refine_rows(r, A.n, posA, posB, T1, cutoff2, 1, error_flag, threadIdx.x, T);
+        refine_rows(r, Bs.n, posB, posA, T2, cutoff2, 0, error_flag, threadIdx.x, T);
+    } else if ((int)threadIdx.x < split) refine_rows(r, A.n, posA, posB, T1, cutoff2, 1, error_flag, threadIdx.x, split);
+    else refine_rows(r, Bs.n, posB, posA, T2, cutoff2, 0, error_flag, threadIdx.x - split, T - split);
 }
 
 // ---- row scheduling ---------------------------------------------------------------------------------------

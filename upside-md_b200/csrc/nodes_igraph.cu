@@ -17,7 +17,7 @@ static int neighbor_capacity(float cutoff, int n_other) {
     // state), so clashing starting structures pack far more of them around a site than a relaxed chain does
     double k = scale * (16. + 0.75 * double(cutoff) * cutoff * cutoff);
     int K = (int)std::min<double>(n_other, std::ceil(k));
-    return std::max(K, 1);
+    return (std::max(K, 1) + 7) & ~7;   // multiple of eight: every ELL row starts on a 16-byte boundary
 }
 
 IGraphHost::IGraphHost(const h5l::Node& grp, bool symmetric_, int excl_, int n_dim1, int n_dim2, CoordNode* p1, CoordNode* p2)
@@ -65,9 +65,13 @@ void IGraphHost::allocate(Engine* e) {
     }
     if (const char* s = getenv("UPSIDE_B200_NO_VERLET_CACHE")) use_cache = atoi(s) == 0;
     if (use_cache) {
-        skin = 1.0f + 0.2f * cutoff;   // cache_buffer of the reference, interaction_graph.h:395-396
-        Kc1 = (neighbor_capacity(cutoff + skin, n2) + 7) & ~7;   // slices of eight (see k_pairlist)
-        Kc2 = symmetric ? Kc1 : (neighbor_capacity(cutoff + skin, n1) + 7) & ~7;
+        // The skin only trades rebuild frequency against candidates per refine; the exact list does not depend on it.  The
+        // reference uses 1 + 0.2*cutoff (cache_buffer, interaction_graph.h:395-396); here an all-pairs rebuild costs more
+        // relative to a refine than on the CPU, and 1.5x that skin measured 2% faster end to end (0.35x: 9% slower).
+        skin = 1.5f * (1.0f + 0.2f * cutoff);
+        if (const char* sk = getenv("UPSIDE_B200_SKIN_SCALE")) skin = std::max(0.1f, (float)atof(sk)) * (1.0f + 0.2f * cutoff);
+        Kc1 = neighbor_capacity(cutoff + skin, n2);   // multiple of eight: slices (see k_pairlist)
+        Kc2 = symmetric ? Kc1 : neighbor_capacity(cutoff + skin, n1);
         cand1.alloc(size_t(e->n_rep) * n1 * Kc1);
         ccnt1.alloc(size_t(e->n_rep) * n1);
         cpos1.alloc(size_t(e->n_rep) * n1 * 4);
@@ -124,7 +128,9 @@ void IGraphHost::build(cudaStream_t s) {
     RefineTable T1{cand1.p, ccnt1.p, Kc1, d.nbr1, d.cnt1, d.K1};
     RefineTable T2{cand2.p, ccnt2.p, Kc2, symmetric ? nullptr : d.nbr2, symmetric ? nullptr : d.cnt2, d.K2};
     size_t smem = sizeof(float4) * size_t(symmetric ? n1 + 1 : n1 + n2 + 2);
-    k_refine<RGL><<<B, 256, smem, s>>>(d.s1, d.s2, symmetric ? 0 : 1, T1, T2, d.cutoff2, d.error_flag);
+    const int rows = symmetric ? n1 : ((n1 + 31) & ~31) + n2;
+    const int tpb = std::min(256, std::max(64, (rows + 31) & ~31));   // smaller blocks keep more of them resident
+    k_refine<RGL><<<B, tpb, smem, s>>>(d.s1, d.s2, symmetric ? 0 : 1, T1, T2, d.cutoff2, d.error_flag);
 }
 
 bool IGraphHost::pairlist(int replica, std::vector<int>& i1, std::vector<int>& i2) {

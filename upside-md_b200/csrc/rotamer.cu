@@ -71,20 +71,6 @@ struct RotamerDev {
     int* error_flag;
 };
 
-// number of set bits of `row` (nW words) strictly between positions lo and hi
-__device__ __forceinline__ int rank_between(const unsigned* row, int nW, int lo, int hi) {
-    int cnt = 0;
-    const int w0 = (lo + 1) >> 5, wh = hi >> 5;
-    const int w1 = min(wh, nW - 1);
-    for (int w = w0; w <= w1; ++w) {
-        unsigned bits = row[w];
-        if (w == w0) bits &= ~0u << ((lo + 1) & 31);
-        if (w == wh) bits &= (hi & 31) ? (~0u >> (32 - (hi & 31))) : 0u;
-        cnt += __popc(bits);
-    }
-    return cnt;
-}
-
 // ================================================================================================ prep
 __global__ void __launch_bounds__(PREP_TPB) k_rot_prep(RotamerDev P) {
     extern __shared__ unsigned smem_u[];
@@ -93,7 +79,9 @@ __global__ void __launch_bounds__(PREP_TPB) k_rot_prep(RotamerDev P) {
     unsigned* bitmap = smem_u;                                   // [nR][nW] symmetric residue adjacency (multi-state only)
     int* estart = reinterpret_cast<int*>(bitmap + nR * nW);      // [nR+1] first slot of pairs (A,B>A)
     int* istart = estart + nR + 1;                               // [nR+1]
-    float* en = reinterpret_cast<float*>(istart + nR + 1);       // [nR*6]
+    int* deg = istart + nR + 1;                                  // [nR]
+    int* ebase = deg + nR;                                       // [nR] slot base: estart - (neighbours below)
+    float* en = reinterpret_cast<float*>(ebase + nR);            // [nR*6]
     const unsigned short* nbr = P.g.nbr1 + size_t(r) * P.n_bead * K;
     const int* cnt = P.g.cnt1 + size_t(r) * P.n_bead;
     int* code = P.code + size_t(r) * P.n_bead * K;
@@ -102,6 +90,7 @@ __global__ void __launch_bounds__(PREP_TPB) k_rot_prep(RotamerDev P) {
     for (int i = tid; i < nR * MAXR; i += PREP_TPB) en[i] = 0.f;
     __syncthreads();
     int* rr = reinterpret_cast<int*>(en + nR * MAXR);   // [n_bead] res << 4 | rot << 1 | multi-state
+    unsigned short* wpre = reinterpret_cast<unsigned short*>(rr + P.n_bead);   // [nR][nW] set bits in the words before w
     for (int i = tid; i < P.n_bead; i += PREP_TPB) {
         float e = 0.f;
         int loc = P.g.s1.loc[i];
@@ -134,16 +123,27 @@ __global__ void __launch_bounds__(PREP_TPB) k_rot_prep(RotamerDev P) {
         if (i < P.n_bead && lane == 0) P.lower[size_t(r) * P.n_bead + i] = lo;
     }
     __syncthreads();
-    if (tid < 32) {   // exclusive scans of upper degree (pair slots) and full degree (incidence lists), one warp
-        int per = (nR + 31) / 32, a0 = tid * per, a1 = min(nR, a0 + per);
-        int su = 0, sf = 0;
-        for (int A = a0; A < a1; ++A) {
-            const unsigned* row = bitmap + A * nW;
-            int deg = 0;
-            for (int w = 0; w < nW; ++w) deg += __popc(row[w]);
-            su += rank_between(row, nW, A, nR);
-            sf += deg;
+    // Per residue: running popcounts of its adjacency row (wpre), degree, and the number of neighbours below itself.  With
+    // them the slot of pair (A,B>A) is ebase[A] + R_A(B), R_A(B) = wpre[A][B>>5] + popc(row_A[B>>5] below bit B): two
+    // independent shared-memory loads instead of a loop over the row.
+    for (int A = tid; A < nR; A += PREP_TPB) {
+        const unsigned* row = bitmap + A * nW;
+        int run = 0, below = 0;
+        for (int w = 0; w < nW; ++w) {
+            unsigned bits = row[w];
+            wpre[A * nW + w] = (unsigned short)run;
+            if (w == (A >> 5)) below = run + __popc(bits & ((1u << (A & 31)) - 1u));
+            run += __popc(bits);
         }
+        deg[A] = run;
+        ebase[A] = -below;            // completed after the scan
+        estart[A] = run - below;      // upper degree, scanned in place below
+    }
+    __syncthreads();
+    if (tid < 32) {   // exclusive scans of upper degree (pair slots) and full degree (incidence lists), one warp
+        int per = (nR + 31) / 32, a0 = min(nR, tid * per), a1 = min(nR, a0 + per);
+        int su = 0, sf = 0;
+        for (int A = a0; A < a1; ++A) { su += estart[A]; sf += deg[A]; }
         int pu = su, pf = sf;
         for (int o = 1; o < 32; o <<= 1) {
             int tu = __shfl_up_sync(UB_FULL_MASK, pu, o), tf = __shfl_up_sync(UB_FULL_MASK, pf, o);
@@ -151,16 +151,16 @@ __global__ void __launch_bounds__(PREP_TPB) k_rot_prep(RotamerDev P) {
         }
         int eu = pu - su, ef = pf - sf;
         for (int A = a0; A < a1; ++A) {
-            const unsigned* row = bitmap + A * nW;
-            int deg = 0;
-            for (int w = 0; w < nW; ++w) deg += __popc(row[w]);
-            estart[A] = eu; istart[A] = ef;
-            eu += rank_between(row, nW, A, nR);
-            ef += deg;
+            int up = estart[A];
+            estart[A] = eu; istart[A] = ef; ebase[A] += eu;
+            eu += up; ef += deg[A];
         }
         if (tid == 31) { estart[nR] = pu; istart[nR] = pf; }
     }
     __syncthreads();
+    auto slot_of = [&](int A, int B) {   // A < B, adjacent
+        return ebase[A] + (int)wpre[A * nW + (B >> 5)] + __popc(bitmap[A * nW + (B >> 5)] & ((1u << (B & 31)) - 1u));
+    };
     const int n_pair = estart[nR];
     if (tid == 0) { P.stats[size_t(r) * 4 + 1] = n_pair; P.e11[r] = 0.f; }
     if (tid == 0 && r == 0) *P.n_slow = 0;
@@ -187,14 +187,16 @@ __global__ void __launch_bounds__(PREP_TPB) k_rot_prep(RotamerDev P) {
                     pair_ab[2 * e + 1] = (unsigned short)C;
                     inc[t++] = 2 * e;
                 } else {
-                    inc[t++] = 2 * (estart[C] + rank_between(bitmap + C * nW, nW, C, A)) + 1;
+                    inc[t++] = 2 * slot_of(C, A) + 1;
                 }
             }
         }
     }
     for (int i = tid; i < nR * MAXR; i += PREP_TPB) P.enode[size_t(r) * nR * MAXR + i] = en[i];
-    float* pmat = P.pmat + size_t(r) * P.max_pairs * 36;
-    for (int i = tid; i < n_pair * 36; i += PREP_TPB) pmat[i] = 0.f;
+    {   // pair energies start from zero: 16-byte stores
+        float4* pm4 = reinterpret_cast<float4*>(P.pmat + size_t(r) * P.max_pairs * 36);
+        for (int i = tid; i < n_pair * 9; i += PREP_TPB) pm4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     // per-entry codes
     for (int i0 = 0; i0 < P.n_bead; i0 += n_grp) {
         int i = i0 + grp;
@@ -207,10 +209,8 @@ __global__ void __launch_bounds__(PREP_TPB) k_rot_prep(RotamerDev P) {
             int other = rr[row[k]], Bq = other >> 4, rb = (other >> 1) & 7;
             bool mB = other & 1;
             int cd;
-            if (mA && mB) {
-                if (A < Bq) cd = (estart[A] + rank_between(bitmap + A * nW, nW, A, Bq)) * 36 + ra * 6 + rb;
-                else cd = (estart[Bq] + rank_between(bitmap + Bq * nW, nW, Bq, A)) * 36 + rb * 6 + ra;
-            } else if (mA) cd = CODE_FOLD;
+            if (mA && mB) cd = A < Bq ? slot_of(A, Bq) * 36 + ra * 6 + rb : slot_of(Bq, A) * 36 + rb * 6 + ra;
+            else if (mA) cd = CODE_FOLD;
             else if (mB) cd = -2 - (Bq * MAXR + rb);
             else cd = CODE_SS;
             code[size_t(i) * K + k] = cd;
@@ -1126,7 +1126,8 @@ struct RotamerSidechain : PotentialNode {
         size_t budget = std::min<size_t>(device_smem, 110 * 1024);
         smem_pairs = budget > fixed_bp ? (int)std::min<size_t>(max_pairs, (budget - fixed_bp) / per_pair) : 0;
         smem_bp = fixed_bp + size_t(smem_pairs) * per_pair + 16;
-        smem_prep = sizeof(unsigned) * size_t(n_res) * n_words + sizeof(int) * 2 * (n_res + 1) + sizeof(float) * n_res * MAXR + sizeof(int) * ig.n1;
+        smem_prep = sizeof(unsigned) * size_t(n_res) * n_words + sizeof(int) * (4 * n_res + 2) + sizeof(float) * n_res * MAXR + sizeof(int) * ig.n1 +
+                    sizeof(unsigned short) * size_t(n_res) * n_words + 16;
         smem_edge = sizeof(BeadRec) * size_t(ig.n1) + sizeof(float) * table.n + sizeof(int) * (ig.n1 + 256);
         if (smem_prep > (size_t)device_smem || smem_edge > (size_t)device_smem || fixed_bp > (size_t)device_smem)
             throw std::string("rotamer node: system too large for the shared-memory kernels");
