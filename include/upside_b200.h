@@ -60,6 +60,39 @@ int ub_get_pairlist(UbEngine* e, const char* node, int replica, int max_edge, in
 int ub_md_init(UbEngine* e, uint32_t base_seed, const float* temperature, float dt, float thermostat_timescale,
                int thermostat_interval);
 int ub_md_set_temperature(UbEngine* e, const float* temperature);
+/* as ub_md_init with an explicit RNG key per replica: a replica of a sharded or regrouped set keeps the seed of its global
+ * index (reference: sys->random_seed = base_random_seed + ns, src/main.cpp:459) */
+int ub_md_init_seeds(UbEngine* e, const uint32_t* seeds, const float* temperature, float dt, float thermostat_timescale,
+                     int thermostat_interval);
+
+/* coordinates of a range of replicas, (n_replica,n_atom,3); exchange of coordinates between replica pairs
+ * (pairs = a0,b0,a1,b1,...), the coord_swap of ReplicaExchange::attempt_swaps (src/main.cpp:240-243) */
+int ub_set_pos_range(UbEngine* e, const float* pos, int first_replica, int n_replica);
+int ub_get_pos_range(UbEngine* e, float* pos, int first_replica, int n_replica);
+int ub_swap_pos(UbEngine* e, int n_pair, const int* pairs);
+
+/* Replica exchange, host side (src/main.cpp:120-275): swap-set parsing/validation, the Metropolis pass and its
+ * counter-based random stream (src/random.h:19-66, stream REPLICA_EXCHANGE_RANDOM_STREAM).  No device work: every rank
+ * of a sharded ladder calls this with the all-gathered energies and reaches the same decisions.
+ *   ub_replex_begin   once per attempt_swaps call (seed, round): restarts the draw counter
+ *   ub_replex_decide  one swap set: old/new_lboltz[i] = -beta_i*E_i before/after the trial exchange; accept[k] = 1 if
+ *                     pair k stays exchanged (a rejected pair must be swapped back by the caller)
+ *   ub_replex_decide_same_hamiltonian  temperature ladder over ONE Hamiltonian: trial energies are a permutation of the
+ *                     current ones, no second evaluation */
+typedef struct UbReplex UbReplex;
+UbReplex* ub_replex_create(int n_system, int n_set, const char* const* swap_sets);
+void ub_replex_destroy(UbReplex* h);
+int ub_replex_n_sets(const UbReplex* h);
+int ub_replex_set_size(const UbReplex* h, int set);
+int ub_replex_pairs(const UbReplex* h, int set, int* pairs /* 2*set_size */);
+int ub_replex_begin(UbReplex* h, uint32_t seed, uint64_t round);
+int ub_replex_decide(UbReplex* h, int set, const float* old_lboltz, const float* new_lboltz, int* accept);
+int ub_replex_decide_same_hamiltonian(UbReplex* h, int set, const float* beta, const float* energy, int* accept);
+int ub_replex_replica_indices(const UbReplex* h, int* out /* n_system */);
+int ub_replex_counts(const UbReplex* h, int set, uint64_t* n_attempt, uint64_t* n_success);
+/* known-answer access to the host generator: n_draw successive uniform_open_closed().x values (+ raw bits of the first) */
+int ub_host_rng_uniform(uint32_t seed, uint32_t stream, uint32_t atom, uint64_t timestep, int n_draw, float* out,
+                        uint32_t* bits_first /* 4 or NULL */);
 int ub_md_run(UbEngine* e, long n_round);      /* asynchronous; ub_sync waits and reports device-side failures */
 int ub_sync(UbEngine* e);
 int ub_recenter(UbEngine* e, int xy_only);     /* src/deriv_engine.cpp:37-48 */

@@ -101,3 +101,39 @@ def compact_sigmoid(x, sharpness):
     val = np.where(y < -1, 1., np.where(y > 1, 0., 0.25 * (y + 2) * (y - 1) * (y - 1)))
     der = np.where(np.abs(y) > 1, 0., sharpness * 0.75 * (y * y - 1))
     return val.astype('f4'), der.astype('f4')
+
+
+# ---- replica exchange (src/main.cpp:227-275) ---------------------------------------------------------------------
+def attempt_swaps(seed, round_num, swap_sets, temperature, energy_of_slot, slots, stats=None):
+    """One ReplicaExchange::attempt_swaps.  `slots[i]` = configuration currently held by system i (any hashable id),
+    `energy_of_slot(i, conf)` = potential of configuration `conf` evaluated in system slot i (the reference evaluates the
+    energy twice per swap set because the slots may carry different Hamiltonians).  Returns the new slots list; `stats`
+    (dict (set,pair) -> [n_success, n_attempt]) is updated if given.  fp32 arithmetic as in the reference."""
+    f32 = np.float32
+    slots = list(slots)
+    n = len(slots)
+    beta = [f32(1.) / f32(t) for t in temperature]
+    draw = 0
+    for si, pairs in enumerate(swap_sets):
+        old = [f32(-beta[i] * f32(energy_of_slot(i, slots[i]))) for i in range(n)]
+        for a, b in pairs:
+            slots[a], slots[b] = slots[b], slots[a]
+        new = [f32(-beta[i] * f32(energy_of_slot(i, slots[i]))) for i in range(n)]
+        for pi, (a, b) in enumerate(pairs):
+            diff = f32(f32(new[a] + new[b]) - f32(old[a] + old[b]))
+            reject = False
+            if diff < 0:   # the random number is only drawn for uphill exchanges (short-circuit &&, main.cpp:268)
+                u = u01(random_bits(seed, 1, 0, round_num, draw)[0])
+                draw += 1
+                reject = f32(np.exp(diff, dtype=f32)) < u
+            if reject:
+                slots[a], slots[b] = slots[b], slots[a]
+            if stats is not None:
+                st = stats.setdefault((si, pi), [0, 0])
+                st[1] += 1
+                st[0] += 0 if reject else 1
+    return slots
+
+
+def parse_swap_sets(strings):
+    return [[tuple(int(x) for x in p.split('-')) for p in s.split(',')] for s in strings]

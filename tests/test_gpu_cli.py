@@ -1,0 +1,91 @@
+"""GPU tests of the `upside` command line (upside_main of libupside_b200.so) and of replica exchange on the batched engine.
+Golden data: tests/golden/cli_replex.npz = the reference binary (unmodified src/main.cpp, oracle/_ref/upside_ref) run with
+the same flags on the same inputs (tools/make_golden_cli.py)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import parity
+from parity import ue
+from upside_md_b200 import h5lite
+from upside_md_b200 import replica_exchange as rx
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(parity.ROOT, 'tests', 'golden')
+sys.path.insert(0, os.path.join(parity.ROOT, 'tools'))
+
+
+def _write_inputs(tmp_path, start):
+    import make_golden_cli
+    return make_golden_cli.write_inputs(str(tmp_path), start)
+
+
+def test_cli_replica_exchange_matches_reference_binary(tmp_path):
+    g = np.load(os.path.join(GOLD, 'cli_replex.npz'))
+    paths = _write_inputs(tmp_path, g['start'])
+    ue.in_process_upside([str(a) for a in g['args']] + paths, verbose=False)
+    for i, p in enumerate(paths):
+        o = h5lite.load(p)['output']
+        assert o['pos'].data.shape == g['pos_%d' % i].shape                      # same datasets, same shapes
+        np.testing.assert_allclose(o['time'].data, g['time_%d' % i], rtol=1e-6)
+        np.testing.assert_allclose(o['temperature'].data, g['temperature_%d' % i], rtol=1e-6)
+        # identical exchange history: same decisions (same random stream, energies equal to ~1e-6), same bookkeeping
+        assert (o['replica_index'].data == g['replica_index_%d' % i]).all(), i
+        assert (o['replica_swap_partner'].data == g['replica_swap_partner_%d' % i]).all()
+        assert (o['replica_cumulative_swaps'].data == g['replica_cumulative_swaps_%d' % i]).all()
+        # trajectories: 10 rounds = 30 timesteps of deterministic-noise Langevin dynamics (+ exchanges)
+        assert np.abs(o['pos'].data[:4] - g['pos_%d' % i][:4]).max() < 2e-3
+        assert np.abs(o['pos'].data - g['pos_%d' % i]).max() < 3e-2
+        np.testing.assert_allclose(o['potential'].data[:4], g['potential_%d' % i][:4], rtol=2e-4, atol=2e-3)
+        np.testing.assert_allclose(o['kinetic'].data[:4], g['kinetic_%d' % i][:4], rtol=2e-3)
+        assert 'invocation' in o.attrs
+
+
+def test_cli_errors_and_flags(tmp_path):
+    g = np.load(os.path.join(GOLD, 'cli_replex.npz'))
+    paths = _write_inputs(tmp_path, g['start'][:2])
+    with pytest.raises(RuntimeError):     # missing required --frame-interval
+        ue.in_process_upside(['--duration', '0.1'] + paths, verbose=False)
+    with pytest.raises(RuntimeError):     # 3 temperatures for 2 systems
+        ue.in_process_upside(['--duration', '0.1', '--frame-interval', '0.05', '--temperature', '0.7,0.8,0.9'] + paths, verbose=False)
+    with pytest.raises(RuntimeError):     # overlapping swap set
+        ue.in_process_upside(['--duration', '0.1', '--frame-interval', '0.05', '--replica-interval', '0.05', '--swap-set', '0-1,1-0'] + paths, verbose=False)
+    with pytest.raises(RuntimeError):     # unknown flag
+        ue.in_process_upside(['--duration', '0.1', '--frame-interval', '0.05', '--no-such-flag'] + paths, verbose=False)
+    # annealing + thermostat interval + no recentering run through and log the annealed temperature
+    ue.in_process_upside(['--duration', '0.2', '--frame-interval', '0.054', '--temperature', '0.9', '--anneal-factor', '0.5',
+                          '--thermostat-interval', '0.054', '--disable-recentering', '--seed', '3'] + paths, verbose=False)
+    o = h5lite.load(paths[0])['output']
+    T = o['temperature'].data.ravel()
+    assert T[0] == pytest.approx(0.9, rel=1e-6) and T[-1] < T[0] and np.isfinite(o['pos'].data).all()
+
+
+def test_sharded_ladder_on_the_engine_single_rank():
+    """ShardedLadder driving a real BatchEngine: exchanges permute coordinates between replicas and nothing else"""
+    cfg = parity.CONFIGS[1]
+    g = np.load(os.path.join(GOLD, 'config1.npz'))
+    n = 6
+    pos = np.array([g['pos'][i % 3] for i in range(n)], dtype='f4')
+    pos += (np.arange(n, dtype='f4') * 1e-3)[:, None, None]          # make the six configurations distinguishable
+    T = np.geomspace(0.7, 1.0, n).astype('f4')
+    be = ue.BatchEngine(cfg, n)
+    be.set_pos(pos)
+    be.md_init_seeds(T, 100 + np.arange(n))
+    lad = rx.ShardedLadder(rx.batch_engine_adapter(be), T, ['0-1,2-3,4-5', '1-2,3-4'], seed=5)
+    e0 = be.evaluate(want_deriv=False)
+    acc = lad.attempt_swaps(3)
+    p1 = be.get_pos()
+    perm = list(range(n))
+    for s in acc:
+        for a, b in s:
+            perm[a], perm[b] = perm[b], perm[a]
+    assert sum(len(s) for s in acc) > 0
+    for i in range(n):
+        assert (p1[i] == pos[perm[i]]).all()
+    e1 = be.evaluate(want_deriv=False)
+    assert np.allclose(e1, e0[perm], rtol=1e-6)
+    lad.run(4, 2)
+    assert np.isfinite(be.get_pos()).all()
+    be.close()

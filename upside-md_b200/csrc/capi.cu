@@ -6,6 +6,7 @@
 #include "../../include/engine_c_library.h"
 #include "../../include/upside_b200.h"
 #include "engine.h"
+#include "replica_exchange.h"
 #include "spline_fit.h"
 
 namespace ub {
@@ -199,6 +200,18 @@ int ub_get_pairlist(UbEngine* e, const char* node, int replica, int max_edge, in
 int ub_md_init(UbEngine* e, uint32_t base_seed, const float* temperature, float dt, float timescale, int interval) {
     UB_TRY e->eng->md_init(base_seed, temperature, dt, timescale, interval); return 0; UB_CATCH
 }
+int ub_md_init_seeds(UbEngine* e, const uint32_t* seeds, const float* temperature, float dt, float timescale, int interval) {
+    UB_TRY e->eng->md_init_seeds(seeds, temperature, dt, timescale, interval); return 0; UB_CATCH
+}
+int ub_set_pos_range(UbEngine* e, const float* pos, int first_replica, int n_replica) {
+    UB_TRY e->eng->set_pos(pos, first_replica, n_replica); return 0; UB_CATCH
+}
+int ub_get_pos_range(UbEngine* e, float* pos, int first_replica, int n_replica) {
+    UB_TRY e->eng->sync_and_check(); e->eng->get_pos(pos, first_replica, n_replica); return 0; UB_CATCH
+}
+int ub_swap_pos(UbEngine* e, int n_pair, const int* pairs) {
+    UB_TRY e->eng->sync_and_check(); e->eng->swap_pos(std::vector<int>(pairs, pairs + 2 * n_pair)); return 0; UB_CATCH
+}
 int ub_md_set_temperature(UbEngine* e, const float* temperature) { UB_TRY e->eng->set_temperature(temperature); return 0; UB_CATCH }
 int ub_md_run(UbEngine* e, long n_round) { UB_TRY e->eng->md_run(n_round); return 0; UB_CATCH }
 int ub_sync(UbEngine* e) { UB_TRY e->eng->sync_and_check(); return 0; UB_CATCH }
@@ -236,6 +249,64 @@ int ub_launches_per_eval(UbEngine* e) {
 }
 int ub_rng_probe(uint32_t seed, uint32_t stream, uint32_t atom, uint64_t t, uint32_t* bits4, float* normal3_u01) {
     UB_TRY ub::rng_probe(seed, stream, atom, t, bits4, normal3_u01); return 0; UB_CATCH
+}
+
+// ---- replica exchange: host-side plan (no device work; usable without a GPU) ------------------------------------------
+struct UbReplex {
+    ub::ReplicaExchangePlan plan;
+    ub::HostRandomGenerator rng;
+    UbReplex(int n, const std::vector<std::string>& sets) : plan(n, sets), rng(0u, ub::REPLICA_EXCHANGE_RANDOM_STREAM, 0u, 0ull) {}
+};
+UbReplex* ub_replex_create(int n_system, int n_set, const char* const* swap_sets) {
+    try {
+        std::vector<std::string> sets(swap_sets, swap_sets + n_set);
+        return new UbReplex(n_system, sets);
+    } catch (const std::string& e) { fail(e); }
+    catch (const std::exception& e) { fail(e.what()); }
+    catch (...) { fail("unknown error"); }
+    return nullptr;
+}
+void ub_replex_destroy(UbReplex* h) { delete h; }
+int ub_replex_n_sets(const UbReplex* h) { return (int)h->plan.swap_sets.size(); }
+int ub_replex_set_size(const UbReplex* h, int set) { return set >= 0 && set < (int)h->plan.swap_sets.size() ? (int)h->plan.swap_sets[set].size() : -1; }
+int ub_replex_pairs(const UbReplex* h, int set, int* pairs) {
+    UB_TRY
+    const auto& ss = h->plan.swap_sets.at(set);
+    for (size_t i = 0; i < ss.size(); ++i) { pairs[2 * i] = ss[i].sys1; pairs[2 * i + 1] = ss[i].sys2; }
+    return 0;
+    UB_CATCH
+}
+int ub_replex_begin(UbReplex* h, uint32_t seed, uint64_t round) {
+    h->rng = ub::HostRandomGenerator(seed, ub::REPLICA_EXCHANGE_RANDOM_STREAM, 0u, round);
+    return 0;
+}
+int ub_replex_decide(UbReplex* h, int set, const float* old_lboltz, const float* new_lboltz, int* accept) {
+    UB_TRY h->plan.decide(set, old_lboltz, new_lboltz, h->rng, accept); return 0; UB_CATCH
+}
+int ub_replex_decide_same_hamiltonian(UbReplex* h, int set, const float* beta, const float* energy, int* accept) {
+    UB_TRY h->plan.decide_same_hamiltonian(set, beta, energy, h->rng, accept); return 0; UB_CATCH
+}
+int ub_replex_replica_indices(const UbReplex* h, int* out) {
+    for (int i = 0; i < h->plan.n_system; ++i) out[i] = h->plan.replica_indices[i];
+    return 0;
+}
+int ub_replex_counts(const UbReplex* h, int set, uint64_t* n_attempt, uint64_t* n_success) {
+    UB_TRY
+    const auto& ss = h->plan.swap_sets.at(set);
+    for (size_t i = 0; i < ss.size(); ++i) { n_attempt[i] = ss[i].n_attempt; n_success[i] = ss[i].n_success; }
+    return 0;
+    UB_CATCH
+}
+int ub_host_rng_uniform(uint32_t seed, uint32_t stream, uint32_t atom, uint64_t timestep, int n_draw, float* out, uint32_t* bits_first) {
+    ub::HostRandomGenerator g(seed, stream, atom, timestep);
+    for (int i = 0; i < n_draw; ++i) {
+        if (i == 0 && bits_first) {
+            ub::HostRandomGenerator g2 = g;
+            g2.random_bits(bits_first);
+        }
+        out[i] = g.uniform_open_closed_x();
+    }
+    return 0;
 }
 
 // ================================================================================ reference single-replica ABI

@@ -491,12 +491,17 @@ void Engine::set_temperature(const float* T) {
 }
 
 void Engine::md_init(uint32_t base_seed, const float* T, float dt_, float timescale, int interval) {
+    std::vector<uint32_t> seeds(n_rep);
+    for (int r = 0; r < n_rep; ++r) seeds[r] = base_seed + (uint32_t)r;   // main.cpp:459
+    md_init_seeds(seeds.data(), T, dt_, timescale, interval);
+}
+
+void Engine::md_init_seeds(const uint32_t* seeds, const float* T, float dt_, float timescale, int interval) {
     UB_CUDA(cudaSetDevice(device));
     dt = dt_;
     thermostat_timescale = timescale;
     thermostat_interval = std::max(1, interval);
-    h_seed.resize(n_rep);
-    for (int r = 0; r < n_rep; ++r) h_seed[r] = base_seed + (uint32_t)r;   // main.cpp:459
+    h_seed.assign(seeds, seeds + n_rep);
     seed.upload(h_seed);
     d_invocation.alloc(1);
     n_thermostat_invocations = 0;
@@ -570,6 +575,21 @@ __global__ void k_recenter(float* __restrict__ pos, int n_atom, int xy_only) {
         v.x -= ctr[0]; v.y -= ctr[1]; v.z -= ctr[2];
         p[i] = v;
     }
+}
+// exchange the coordinates of replica pairs (replica exchange swaps engine.pos only: main.cpp:240-243)
+__global__ void k_swap_pos(float* __restrict__ pos, const int* __restrict__ pairs, int n_atom) {
+    float4* a = reinterpret_cast<float4*>(pos) + size_t(pairs[2 * blockIdx.x]) * n_atom;
+    float4* b = reinterpret_cast<float4*>(pos) + size_t(pairs[2 * blockIdx.x + 1]) * n_atom;
+    for (int i = threadIdx.x; i < n_atom; i += blockDim.x) { float4 t = a[i]; a[i] = b[i]; b[i] = t; }
+}
+void Engine::swap_pos(const std::vector<int>& pairs) {
+    UB_CUDA(cudaSetDevice(device));
+    if (pairs.empty()) return;
+    for (int v : pairs) if (v < 0 || v >= n_rep) throw std::string("replica index out of range in swap");
+    DevBuf<int> d;
+    d.upload(pairs);
+    k_swap_pos<<<(unsigned)(pairs.size() / 2), 128, 0, stream>>>(pos->output, d.p, n_atom);
+    UB_CUDA(cudaStreamSynchronize(stream));
 }
 void Engine::recenter(bool xy_only) {
     UB_CUDA(cudaSetDevice(device));

@@ -223,11 +223,14 @@ struct Engine {
 
     // MD (reference main.cpp:515-523,657-663; deriv_engine.cpp:11-35,172-192; thermostat.cpp:9-18)
     void md_init(uint32_t base_seed, const float* temperature, float dt, float timescale, int thermostat_interval);
+    // explicit RNG key per replica (replica r of a sharded or regrouped set keeps the seed of its global index)
+    void md_init_seeds(const uint32_t* seeds, const float* temperature, float dt, float timescale, int thermostat_interval);
     void set_temperature(const float* temperature);
     void enqueue_thermostat(cudaStream_t s);
     void enqueue_integration_cycle(cudaStream_t s);
     void md_run(long n_round);
     void recenter(bool xy_only);
+    void swap_pos(const std::vector<int>& pairs);   // pairs = (a0,b0,a1,b1,...): exchange coordinates of replicas a_k and b_k
     std::vector<float> kinetic_energy();
 };
 

@@ -77,6 +77,23 @@ def lib():
     L.ub_launches_per_eval.argtypes = [ct.c_void_p]
     L.ub_rng_probe.argtypes = [ct.c_uint32, ct.c_uint32, ct.c_uint32, ct.c_uint64, ct.POINTER(ct.c_uint32), _fp]
     L.upside_main.argtypes = [ct.c_int, ct.POINTER(ct.c_char_p), ct.c_int]
+    L.ub_md_init_seeds.argtypes = [ct.c_void_p, ct.POINTER(ct.c_uint32), _fp, ct.c_float, ct.c_float, ct.c_int]
+    L.ub_set_pos_range.argtypes = [ct.c_void_p, _fp, ct.c_int, ct.c_int]
+    L.ub_get_pos_range.argtypes = [ct.c_void_p, _fp, ct.c_int, ct.c_int]
+    L.ub_swap_pos.argtypes = [ct.c_void_p, ct.c_int, _ip]
+    L.ub_replex_create.restype = ct.c_void_p
+    L.ub_replex_create.argtypes = [ct.c_int, ct.c_int, ct.POINTER(ct.c_char_p)]
+    L.ub_replex_destroy.restype = None
+    L.ub_replex_destroy.argtypes = [ct.c_void_p]
+    L.ub_replex_n_sets.argtypes = [ct.c_void_p]
+    L.ub_replex_set_size.argtypes = [ct.c_void_p, ct.c_int]
+    L.ub_replex_pairs.argtypes = [ct.c_void_p, ct.c_int, _ip]
+    L.ub_replex_begin.argtypes = [ct.c_void_p, ct.c_uint32, ct.c_uint64]
+    L.ub_replex_decide.argtypes = [ct.c_void_p, ct.c_int, _fp, _fp, _ip]
+    L.ub_replex_decide_same_hamiltonian.argtypes = [ct.c_void_p, ct.c_int, _fp, _fp, _ip]
+    L.ub_replex_replica_indices.argtypes = [ct.c_void_p, _ip]
+    L.ub_replex_counts.argtypes = [ct.c_void_p, ct.c_int, ct.POINTER(ct.c_uint64), ct.POINTER(ct.c_uint64)]
+    L.ub_host_rng_uniform.argtypes = [ct.c_uint32, ct.c_uint32, ct.c_uint32, ct.c_uint64, ct.c_int, _fp, ct.POINTER(ct.c_uint32)]
     _lib = L
     return L
 
@@ -294,6 +311,29 @@ class BatchEngine(object):
         T = np.ascontiguousarray(np.broadcast_to(np.asarray(temperature, dtype='f4'), (self.n_replica,)))
         if self.L.ub_md_init(self.e, int(seed), _f(T), dt, timescale, int(thermostat_interval)): raise _err('md_init')
 
+    def md_init_seeds(self, temperature, seeds, dt=0.009, timescale=5.0, thermostat_interval=1):
+        """as md_init with one RNG key per replica (seed of system ns in the reference = base_seed + ns, main.cpp:459)"""
+        T = np.ascontiguousarray(np.broadcast_to(np.asarray(temperature, dtype='f4'), (self.n_replica,)))
+        sd = np.ascontiguousarray(np.asarray(seeds, dtype=np.uint32))
+        assert sd.shape == (self.n_replica,)
+        if self.L.ub_md_init_seeds(self.e, sd.ctypes.data_as(ct.POINTER(ct.c_uint32)), _f(T), dt, timescale, int(thermostat_interval)):
+            raise _err('md_init_seeds')
+
+    def get_pos_range(self, first, n):
+        a = np.zeros((n, self.n_atom, 3), dtype='f4')
+        if self.L.ub_get_pos_range(self.e, _f(a), int(first), int(n)): raise _err('get_pos_range')
+        return a
+
+    def set_pos_range(self, pos, first):
+        a = np.require(pos, dtype='f4', requirements='C')
+        assert a.shape[1:] == (self.n_atom, 3)
+        if self.L.ub_set_pos_range(self.e, _f(a), int(first), int(a.shape[0])): raise _err('set_pos_range')
+
+    def swap_pos(self, pairs):
+        """exchange the coordinates of replica pairs [(a0,b0),(a1,b1),...]"""
+        p = np.require(np.asarray(pairs, dtype='i4').reshape(-1, 2), requirements='C')
+        if self.L.ub_swap_pos(self.e, int(p.shape[0]), p.ctypes.data_as(_ip)): raise _err('swap_pos')
+
     def set_temperature(self, temperature):
         T = np.ascontiguousarray(np.broadcast_to(np.asarray(temperature, dtype='f4'), (self.n_replica,)))
         if self.L.ub_md_set_temperature(self.e, _f(T)): raise _err('md_set_temperature')
@@ -326,6 +366,15 @@ def rng_probe(seed, stream, atom, timestep):
     f = np.zeros(4, dtype='f4')
     if lib().ub_rng_probe(seed, stream, atom, timestep, bits, _f(f)): raise _err('rng_probe')
     return np.array(list(bits), dtype=np.uint32), f[:3].copy(), float(f[3])
+
+
+def host_rng_uniform(seed, stream, atom, timestep, n_draw):
+    """n_draw successive RandomGenerator(seed, stream, atom, timestep).uniform_open_closed().x on the HOST generator,
+    and the raw Threefry bits of the first draw"""
+    out = np.zeros(n_draw, dtype='f4')
+    bits = (ct.c_uint32 * 4)()
+    lib().ub_host_rng_uniform(seed, stream, atom, timestep, n_draw, _f(out), bits)
+    return out, np.array(list(bits), dtype=np.uint32)
 
 
 def in_process_upside(args, verbose=True):
