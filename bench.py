@@ -178,7 +178,7 @@ def gpu_arm(args):
     roof = None
     launches = eng.launches_per_eval()
     if rank == 0:
-        roof = rotamer_roofline(eng, stream, torch)
+        roof = kernel_rooflines(eng, stream, torch)
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
         cpu = cpu_reference_arm(args.steps, 3, max_seconds=20.0)
@@ -200,9 +200,12 @@ def gpu_arm(args):
         dist.destroy_process_group()
 
 
-def rotamer_roofline(eng, stream, torch):
-    """time PotentialAndDeriv-free evaluations and attribute the algorithmic flops of SURVEY.md §8(d)"""
+def kernel_rooflines(eng, stream, torch):
+    """Roofline of the dominant kernel group, measured live: ub_profile_eval times one evaluation kernel group by kernel
+    group with CUDA events on the engine's stream (after warm-up, mean of 3); the algorithmic flops of SURVEY.md
+    section 8(d) are attributed group by group from live counts (edges, BP sweeps, residue-pair classes)."""
     peaks, how = measured_peaks()
+    fp32_peak = 148 * 128 * 2 * peaks.get('sm_max_mhz', 1965.0) * 1e6 / 1e12
     n = 5
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with torch.cuda.stream(stream):
@@ -211,6 +214,14 @@ def rotamer_roofline(eng, stream, torch):
         ev1.record(stream)
     eng.sync()
     ms_eval = ev0.elapsed_time(ev1) / (3 * n)
+    acc = {}
+    order = []
+    for rep in range(3):
+        for label, ms in eng.profile_eval():
+            if label not in acc:
+                acc[label] = 0.0
+                order.append(label)
+            acc[label] += ms / 3
     # live counts from a sample of replicas
     sample = range(0, eng.n_replica, max(1, eng.n_replica // 16))
     eng.evaluate(want_deriv=False)
@@ -220,14 +231,43 @@ def rotamer_roofline(eng, stream, torch):
     e_hb = np.mean([len(eng.pairlist('protein_hbond', r)) for r in sample])
     st = np.array([eng.get_value_by_name('rotamer', 'solve_stats', r) for r in sample])
     sweeps, pairs = st[:, 0].mean() + 1, st[:, 1].mean()
-    flops = e_rot * 324 + e_cov * 324 + e_hb * 314 + e_env * 110 + sweeps * pairs * 200 + 2000 * N_RES
-    fp32_peak = 148 * 128 * 2 * peaks.get('sm_max_mhz', 1965.0) * 1e6 / 1e12
-    achieved = flops * eng.n_replica / (ms_eval * 1e-3) / 1e12
-    return dict(bound='fp32', achieved=achieved, peak=fp32_peak, unit='TFLOP/s', frac=achieved / fp32_peak, traffic=None,
-                kernel='whole force evaluation (all kernels)', ms_per_force_eval=ms_eval,
-                algorithmic_flops_per_replica_eval=flops,
-                counts=dict(rotamer_edges=e_rot, coverage_edges=e_cov, env_edges=e_env, hbond_edges=e_hb, bp_sweeps=sweeps, bp_pairs=pairs),
-                peak_source='derived 148 SM x 128 lanes x 2 x sm_max_mhz (%s clocks); no FP32 entry in MEASURED_PEAKS.json' % how)
+    n66, n36 = st[:, 3].mean(), st[:, 4].mean()
+    n33 = pairs - n66 - n36
+    nrot = np.array([1, 1, 3, 3, 3, 3, 3, 3, 3, 3, 6, 6, 6, 6, 6, 6, 6, 6, 6, 6]).mean()   # per residue type, SURVEY section 8
+    f_bp = sweeps * (275 * n66 + 190 * n36 + 110 * n33 + N_RES * (4 * nrot + 5))
+    groups = {   # algorithmic flops per replica and evaluation, and the profile labels that do the work
+        'rotamer pair term (k_rot_energy + k_rot_deriv)': (e_rot * 324, ['rotamer/energy', 'rotamer/deriv']),
+        'rotamer belief propagation (k_rot_bp2)': (f_bp, ['rotamer/bp']),
+        'hbond_coverage x2 (fwd + bwd)': (e_cov * 324, ['hbond_coverage:fwd', 'hbond_coverage_hydrophobe:fwd', 'hbond_coverage:bwd',
+                                                         'hbond_coverage_hydrophobe:bwd']),
+        'environment_coverage (fwd + bwd)': (e_env * 110, ['environment_coverage:fwd', 'environment_coverage:bwd']),
+        'protein_hbond (fwd + bwd)': (e_hb * 314, ['protein_hbond:fwd', 'protein_hbond:bwd']),
+    }
+    table = []
+    for name, (flops, labels) in groups.items():
+        ms = sum(acc.get(l, 0.0) for l in labels)
+        ach = flops * eng.n_replica / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
+        table.append(dict(kernel=name, ms=ms, algorithmic_flops_per_replica=flops, achieved_tflops=ach, frac=ach / fp32_peak))
+    pl_ms = acc.get('(pairlist)', 0.0) + acc.get('rotamer/pairlist', 0.0)
+    table.append(dict(kernel='pair lists (k_cache_check + k_pairlist + k_refine, all graphs)', ms=pl_ms))
+    table.append(dict(kernel='rotamer prep (k_rot_prep)', ms=acc.get('rotamer/prep', 0.0)))
+    top = max(table[:5], key=lambda t: t['ms'])
+    flops_total = e_rot * 324 + e_cov * 324 + e_hb * 314 + e_env * 110 + f_bp + 2000 * N_RES
+    traffic = None
+    tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(top['kernel'])
+    return dict(bound='fp32', achieved=top['achieved_tflops'], peak=fp32_peak, unit='TFLOP/s', frac=top['frac'], traffic=traffic,
+                kernel=top['kernel'], ms_per_launch=top['ms'], algorithmic_flops_per_replica=top['algorithmic_flops_per_replica'],
+                whole_evaluation=dict(ms=ms_eval, algorithmic_flops_per_replica=flops_total,
+                                      achieved_tflops=flops_total * eng.n_replica / (ms_eval * 1e-3) / 1e12,
+                                      frac=flops_total * eng.n_replica / (ms_eval * 1e-3) / 1e12 / fp32_peak,
+                                      sum_of_serial_kernel_ms=sum(acc.values())),
+                kernels=table,
+                counts=dict(rotamer_edges=e_rot, coverage_edges=e_cov, env_edges=e_env, hbond_edges=e_hb, bp_sweeps=sweeps, bp_pairs=pairs,
+                            bp_pairs_6x6=n66, bp_pairs_3x6=n36),
+                peak_source='FP32 FMA pipe: 148 SM x 128 lanes x 2 x sm_max_mhz (%s clocks); MEASURED_PEAKS.json has no FP32 entry, '
+                            'the path has no dense contraction and moves ~1.4 TB/s of HBM (profiles/)' % how)
 
 
 def reference_arm(args):

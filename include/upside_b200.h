@@ -103,6 +103,11 @@ void* ub_stream(UbEngine* e);
 /* number of kernels the engine launches per evaluation / per MD round (for the bench's gpu_launches claim) */
 int ub_launches_per_eval(UbEngine* e);
 
+/* One DerivMode evaluation timed kernel group by kernel group with CUDA events on the engine's stream (linear order, no
+ * graph): label i (NUL-terminated, label_len bytes each) took ms[i].  Labels are "<node>:fwd", "<node>:bwd" and finer
+ * marks inside multi-kernel nodes ("rotamer/pairlist", "rotamer/prep", "rotamer/energy", "rotamer/bp", "rotamer/deriv"). */
+int ub_profile_eval(UbEngine* e, int max_entry, char* labels, int label_len, float* ms, int* n_entry);
+
 /* known-answer access to the device RNG (src/random.h:19-66): threefry bits, normal3 and u01(word0) */
 int ub_rng_probe(uint32_t seed, uint32_t stream, uint32_t atom, uint64_t timestep, uint32_t* bits4, float* normal3_u01);
 

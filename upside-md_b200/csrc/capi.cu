@@ -247,6 +247,19 @@ int ub_launches_per_eval(UbEngine* e) {
         return k;
     } catch (...) { return -1; }
 }
+int ub_profile_eval(UbEngine* e, int max_entry, char* labels, int label_len, float* ms, int* n_entry) {
+    UB_TRY
+    auto v = e->eng->profile_eval(ub::DerivMode);
+    e->eng->sync_and_check();
+    *n_entry = (int)v.size();
+    for (int i = 0; i < (int)v.size() && i < max_entry; ++i) {
+        strncpy(labels + size_t(i) * label_len, v[i].first.c_str(), label_len);
+        labels[size_t(i) * label_len + label_len - 1] = 0;
+        ms[i] = v[i].second;
+    }
+    return 0;
+    UB_CATCH
+}
 int ub_rng_probe(uint32_t seed, uint32_t stream, uint32_t atom, uint64_t t, uint32_t* bits4, float* normal3_u01) {
     UB_TRY ub::rng_probe(seed, stream, atom, t, bits4, normal3_u01); return 0; UB_CATCH
 }

@@ -230,9 +230,9 @@ void Engine::enqueue_compute(cudaStream_t s, ComputeMode mode) {
     if (use_dag && cap == cudaStreamCaptureStatusActive) {
         enqueue_compute_dag(s, mode);
     } else {
-        for (auto& n : nodes) n.computation->compute_value(s, mode);
+        for (auto& n : nodes) { n.computation->compute_value(s, mode); mark(s, n.name + ":fwd"); }
         for (size_t i = nodes.size(); i-- > 0;)
-            if (!nodes[i].computation->potential_term) nodes[i].computation->propagate_deriv(s);
+            if (!nodes[i].computation->potential_term) { nodes[i].computation->propagate_deriv(s); mark(s, nodes[i].name + ":bwd"); }
     }
     if (mode == PotentialAndDerivMode && n_pot_nodes)
         k_sum_potentials<<<(n_rep + 127) / 128, 128, 0, s>>>(potential.p, pot_ptrs.p, n_pot_nodes, n_rep);
@@ -303,6 +303,26 @@ void Engine::compute(ComputeMode mode) {
         UB_CUDA(cudaGraphDestroy(g));
     }
     UB_CUDA(cudaGraphLaunch(graph_eval[mode], stream));
+}
+
+std::vector<std::pair<std::string, float>> Engine::profile_eval(ComputeMode mode) {
+    UB_CUDA(cudaSetDevice(device));
+    UB_CUDA(cudaStreamSynchronize(stream));
+    profiling = true;
+    marks.clear();
+    mark(stream, "start");
+    enqueue_compute(stream, mode);   // not capturing: linear order, one mark after every kernel group
+    UB_CUDA(cudaStreamSynchronize(stream));
+    profiling = false;
+    std::vector<std::pair<std::string, float>> out;
+    for (size_t i = 1; i < marks.size(); ++i) {
+        float ms = 0.f;
+        UB_CUDA(cudaEventElapsedTime(&ms, marks[i - 1].second, marks[i].second));
+        out.emplace_back(marks[i].first, ms);
+    }
+    for (auto& m : marks) cudaEventDestroy(m.second);
+    marks.clear();
+    return out;
 }
 
 void Engine::sync_and_check() {

@@ -198,6 +198,20 @@ struct Engine {
     std::vector<cudaEvent_t> ev_fwd, ev_bwd;
     cudaEvent_t ev_start = nullptr;
 
+    // Live timing of one evaluation kernel group by kernel group (CUDA events on the engine's stream, linear order, no graph):
+    // while `profiling` is set, mark(s, label) records an event; the engine marks every node's forward / backward, nodes
+    // with several kernels add finer marks (e.g. "rotamer/bp").  profile_eval returns (label, milliseconds) pairs.
+    bool profiling = false;
+    std::vector<std::pair<std::string, cudaEvent_t>> marks;
+    void mark(cudaStream_t s, const std::string& label) {
+        if (!profiling) return;
+        cudaEvent_t e;
+        UB_CUDA(cudaEventCreate(&e));
+        UB_CUDA(cudaEventRecord(e, s));
+        marks.emplace_back(label, e);
+    }
+    std::vector<std::pair<std::string, float>> profile_eval(ComputeMode mode);
+
     Engine(int n_atom, int n_rep, int device);
     ~Engine();
     Engine(const Engine&) = delete;

@@ -131,6 +131,7 @@ void IGraphHost::build(cudaStream_t s) {
     const int rows = symmetric ? n1 : ((n1 + 31) & ~31) + n2;
     const int tpb = std::min(256, std::max(64, (rows + 31) & ~31));   // smaller blocks keep more of them resident
     k_refine<RGL><<<B, tpb, smem, s>>>(d.s1, d.s2, symmetric ? 0 : 1, T1, T2, d.cutoff2, d.error_flag);
+    engine->mark(s, "(pairlist)");
 }
 
 bool IGraphHost::pairlist(int replica, std::vector<int>& i1, std::vector<int>& i2) {

@@ -998,7 +998,7 @@ __global__ void __launch_bounds__(BP2_TPB, 3) k_rot_bp2(RotamerDev P, Bp2Lay L, 
         }
         unconverged = __syncthreads_or(dev > P.tol);
     }
-    if (tid == 0) { st[0] = iter; st[2] = !unconverged; }
+    if (tid == 0) { st[0] = iter; st[2] = !unconverged; st[3] = n66 | (n36 << 16); }   // st[3]: class counts for the flop audit
 
     // ---- marginals (and Bethe free energy) ----------------------------------------------------------------------------------
     float en = 0.f;
@@ -1215,15 +1215,20 @@ struct RotamerSidechain : PotentialNode {
         int want = mode == PotentialAndDerivMode;
         // edge kernels: persistent CTAs (3 resident per SM by shared memory) striding over the replicas
         int persist = std::min(engine->n_rep, 148 * 3);
+        engine->mark(s, "rotamer/pairlist");
         k_rot_prep<<<engine->n_rep, PREP_TPB, smem_prep, s>>>(P);
+        engine->mark(s, "rotamer/prep");
         k_rot_energy<<<dim3(P.n_chunk, persist), EDGE_TPB, smem_edge, s>>>(P, want, engine->n_rep);
+        engine->mark(s, "rotamer/energy");
         if (fast_bp) {
             k_rot_bp2<<<engine->n_rep, BP2_TPB, smem_bp2, s>>>(P, lay2, want);
             k_rot_bp<<<std::min(engine->n_rep, 148), BP_TPB, smem_bp, s>>>(P, want, 1);   // replicas the fast path declined
         } else {
             k_rot_bp<<<engine->n_rep, BP_TPB, smem_bp, s>>>(P, want, 0);
         }
+        engine->mark(s, "rotamer/bp");
         k_rot_deriv<<<dim3(P.n_chunk, persist), EDGE_TPB, smem_edge, s>>>(P, engine->n_rep);
+        engine->mark(s, "rotamer/deriv");
     }
     bool get_pairlist(int replica, std::vector<int>& i1, std::vector<int>& i2) override { return ig.pairlist(replica, i1, i2); }
     std::vector<float> get_param() const override { return ig.h_param; }
@@ -1241,10 +1246,10 @@ struct RotamerSidechain : PotentialNode {
             for (int b = 0; b < ig.n1; ++b) out[b] = nmg[bead_res[b] * MAXR + bead_rot[b]];
             return out;
         }
-        if (nm == "solve_stats") {     // B200 extension: (n_iter, n residue pairs, converged)
+        if (nm == "solve_stats") {     // B200 extension: (n_iter, n residue pairs, converged, n 6x6 pairs, n 3x6 pairs)
             std::vector<int> st(4);
             UB_CUDA(cudaMemcpy(st.data(), stats.p + size_t(replica) * 4, 4 * sizeof(int), cudaMemcpyDeviceToHost));
-            return {float(st[0]), float(st[1]), float(st[2])};
+            return {float(st[0]), float(st[1]), float(st[2]), float(st[3] & 0xffff), float((st[3] >> 16) & 0xffff)};
         }
         throw std::string("Value ") + log_name + " not implemented";
     }

@@ -75,6 +75,7 @@ def lib():
     L.ub_stream.restype = ct.c_void_p
     L.ub_stream.argtypes = [ct.c_void_p]
     L.ub_launches_per_eval.argtypes = [ct.c_void_p]
+    L.ub_profile_eval.argtypes = [ct.c_void_p, ct.c_int, ct.c_char_p, ct.c_int, _fp, _ip]
     L.ub_rng_probe.argtypes = [ct.c_uint32, ct.c_uint32, ct.c_uint32, ct.c_uint64, ct.POINTER(ct.c_uint32), _fp]
     L.upside_main.argtypes = [ct.c_int, ct.POINTER(ct.c_char_p), ct.c_int]
     L.ub_md_init_seeds.argtypes = [ct.c_void_p, ct.POINTER(ct.c_uint32), _fp, ct.c_float, ct.c_float, ct.c_int]
@@ -356,6 +357,16 @@ class BatchEngine(object):
 
     def stream(self):
         return self.L.ub_stream(self.e)
+
+    def profile_eval(self):
+        """[(label, milliseconds)] of one DerivMode evaluation, kernel group by kernel group (CUDA events, engine stream)"""
+        cap, ll = 256, 64
+        buf = ct.create_string_buffer(cap * ll)
+        ms = np.zeros(cap, dtype='f4')
+        n = ct.c_int()
+        if self.L.ub_profile_eval(self.e, cap, buf, ll, _f(ms), ct.byref(n)): raise _err('profile_eval')
+        raw = buf.raw
+        return [(raw[i * ll:(i + 1) * ll].split(b'\0')[0].decode(), float(ms[i])) for i in range(min(n.value, cap))]
 
     def launches_per_eval(self):
         return self.L.ub_launches_per_eval(self.e)
