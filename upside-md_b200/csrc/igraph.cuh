@@ -278,10 +278,37 @@ __device__ __forceinline__ float quadspline_edge(const float* __restrict__ p, co
     f3 u = inv_dist * displace;
     float cos1 = dot(rvec1, u), cos2 = -dot(rvec2, u);
     float a1v, a1d, a2v, a2d, wv, wd, nv, nd;
-    deboor_vd(p, q.nka, (cos1 + 1.f) * q.inv_dtheta + 1.f, a1v, a1d);
-    deboor_vd(p + q.nka, q.nka, (cos2 + 1.f) * q.inv_dtheta + 1.f, a2v, a2d);
-    clamped_deboor_vd(p + 2 * q.nka, q.nk, dist_coord, wv, wd);
-    clamped_deboor_vd(p + 2 * q.nka + q.nk, q.nk, dist_coord, nv, nd);
+    float w[4], d[4];
+    {
+        float x = (cos1 + 1.f) * q.inv_dtheta + 1.f;
+        int b = max(1, min((int)x, q.nka - 3));
+        bspline_weights(x - (float)b, w, d);
+        bspline_apply(w, d, p[b - 1], p[b], p[b + 1], p[b + 2], a1v, a1d);
+        const float* p2 = p + q.nka;
+        x = (cos2 + 1.f) * q.inv_dtheta + 1.f;
+        b = max(1, min((int)x, q.nka - 3));
+        bspline_weights(x - (float)b, w, d);
+        bspline_apply(w, d, p2[b - 1], p2[b], p2[b + 1], p2[b + 2], a2v, a2d);
+    }
+    {   // the wide and narrow radial profiles share the knot interval and hence the weights (clamping: spline.h:275-310)
+        const float* wide = p + 2 * q.nka;
+        const float* narrow = wide + q.nk;
+        const int nk = q.nk;
+        if (dist_coord < 1.f) {
+            wv = (1.f / 6.f) * wide[0] + (2.f / 3.f) * wide[1] + (1.f / 6.f) * wide[2];
+            nv = (1.f / 6.f) * narrow[0] + (2.f / 3.f) * narrow[1] + (1.f / 6.f) * narrow[2];
+            wd = nd = 0.f;
+        } else if (dist_coord >= (float)(nk - 2)) {
+            wv = (1.f / 6.f) * wide[nk - 3] + (2.f / 3.f) * wide[nk - 2] + (1.f / 6.f) * wide[nk - 1];
+            nv = (1.f / 6.f) * narrow[nk - 3] + (2.f / 3.f) * narrow[nk - 2] + (1.f / 6.f) * narrow[nk - 1];
+            wd = nd = 0.f;
+        } else {
+            int b = (int)dist_coord;
+            bspline_weights(dist_coord - (float)b, w, d);
+            bspline_apply(w, d, wide[b - 1], wide[b], wide[b + 1], wide[b + 2], wv, wd);
+            bspline_apply(w, d, narrow[b - 1], narrow[b], narrow[b + 1], narrow[b + 2], nv, nd);
+        }
+    }
     float angular_weight = a1v * a2v;
     float radial_deriv = q.inv_dx * (wd + angular_weight * nd);
     float ang_d1 = q.inv_dtheta * a1d * a2v * nv;

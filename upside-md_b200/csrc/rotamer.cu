@@ -226,13 +226,19 @@ __device__ __forceinline__ int sym_row(int t1, int t2, int nT, bool& swap) {
     return a * nT - (a * (a - 1)) / 2 + (b - a);
 }
 
-// the B-spline table is staged once per CTA (CTAs are persistent over replicas), beads once per replica
-__device__ __forceinline__ void stage_table(const RotamerDev& P, float* table) {
+// the B-spline table is staged once per CTA (CTAs are persistent over replicas), beads once per replica.  `rowoff` maps an
+// ordered type pair to (float offset of its row) | swap bit, so the per-pair table lookup is one shared-memory load.
+__device__ __forceinline__ void stage_table(const RotamerDev& P, float* table, int* rowoff) {
     const int n4 = ((P.n_type * (P.n_type + 1) / 2) * P.g.n_param) / 4;   // n_param is even and rows come in pairs: multiple of 4
     const float4* src = reinterpret_cast<const float4*>(P.table);
     float4* dst = reinterpret_cast<float4*>(table);
     for (int i = threadIdx.x; i < n4; i += blockDim.x) dst[i] = src[i];
     for (int i = n4 * 4 + threadIdx.x; i < (P.n_type * (P.n_type + 1) / 2) * P.g.n_param; i += blockDim.x) table[i] = P.table[i];
+    for (int i = threadIdx.x; i < P.n_type * P.n_type; i += blockDim.x) {
+        bool swap;
+        int row = sym_row(i / P.n_type, i % P.n_type, P.n_type, swap);
+        rowoff[i] = (row * P.g.n_param) << 1 | (swap ? 1 : 0);
+    }
 }
 __device__ __forceinline__ void stage_beads(const RotamerDev& P, int r, BeadRec* beads) {
     for (int i = threadIdx.x; i < P.n_bead; i += blockDim.x) {
@@ -240,22 +246,27 @@ __device__ __forceinline__ void stage_beads(const RotamerDev& P, int r, BeadRec*
         float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
         BeadRec br;
         br.x = a.x; br.y = a.y; br.z = a.z; br.dx = a.w; br.dy = b.x; br.dz = b.y;
-        br.type = P.g.s1.type[i];
+        const int t = P.g.s1.type[i];
+        br.type = (t * P.n_type) << 8 | t;     // rowoff index of (b1,b2) = (b1.type >> 8) + (b2.type & 0xff)
         br.res_rot = (P.bead_res[i] << 3) | P.bead_rot[i];
         beads[i] = br;
     }
 }
 
-// quadspline on shared-memory operands, (lo,hi) ordering as the reference's i1<i2 edge
-template <bool DERIV>
-__device__ __forceinline__ float pair_term(const RotamerDev& P, const BeadRec& b1, const BeadRec& b2, const float* table,
-                                           float* d1, float* d2) {
-    bool swap;
-    const float* row = table + sym_row(b1.type, b2.type, P.n_type, swap) * P.g.n_param;
-    const float* ang1 = row + (swap ? P.q.nka : 0);
-    const float* ang2 = row + (swap ? 0 : P.q.nka);
-    const float* wide = row + 2 * P.q.nka;
-    const float* narrow = wide + P.q.nk;
+// quadspline on shared-memory operands, (lo,hi) ordering as the reference's i1<i2 edge.  NKA/NK > 0: knot counts known at
+// compile time (ff_1: 15 angular, 16 radial), all sub-table offsets become immediates; 0: read from P.q.
+struct PairTab { const float* table; const int* rowoff; };
+template <bool DERIV, int NKA, int NK>
+__device__ __forceinline__ float pair_term(const RotamerDev& P, const PairTab& T, const BeadRec& b1, const BeadRec& b2, float* d1,
+                                           float* d2) {
+    const int nka = NKA ? NKA : P.q.nka, nk = NK ? NK : P.q.nk;
+    const int ro = T.rowoff[(b1.type >> 8) + (b2.type & 0xff)];
+    const bool swap = ro & 1;
+    const float* row = T.table + (ro >> 1);
+    const float* ang1 = row + (swap ? nka : 0);
+    const float* ang2 = row + (swap ? 0 : nka);
+    const float* wide = row + 2 * nka;
+    const float* narrow = wide + nk;
     f3 displace = mk3(b2.x - b1.x, b2.y - b1.y, b2.z - b1.z);
     f3 rvec1 = mk3(b1.dx, b1.dy, b1.dz), rvec2 = mk3(b2.dx, b2.dy, b2.dz);
     float dist2 = mag2(displace);
@@ -264,17 +275,19 @@ __device__ __forceinline__ float pair_term(const RotamerDev& P, const BeadRec& b
     f3 u = inv_dist * displace;
     float cos1 = dot(rvec1, u), cos2 = -dot(rvec2, u);
     float a1v, a1d, a2v, a2d, wv, wd, nv, nd;
+    float w[4], d[4];
     {
         float x = (cos1 + 1.f) * P.q.inv_dtheta + 1.f;
-        int b = max(1, min((int)x, P.q.nka - 3));
-        deboor_core(ang1[b - 1], ang1[b], ang1[b + 1], ang1[b + 2], x - (float)b, a1v, a1d);
+        int b = max(1, min((int)x, nka - 3));
+        bspline_weights(x - (float)b, w, d);
+        bspline_apply(w, d, ang1[b - 1], ang1[b], ang1[b + 1], ang1[b + 2], a1v, a1d);
         x = (cos2 + 1.f) * P.q.inv_dtheta + 1.f;
-        b = max(1, min((int)x, P.q.nka - 3));
-        deboor_core(ang2[b - 1], ang2[b], ang2[b + 1], ang2[b + 2], x - (float)b, a2v, a2d);
+        b = max(1, min((int)x, nka - 3));
+        bspline_weights(x - (float)b, w, d);
+        bspline_apply(w, d, ang2[b - 1], ang2[b], ang2[b + 1], ang2[b + 2], a2v, a2d);
     }
-    {   // both radial splines share the knot interval (clamped rule of spline.h:275-310)
+    {   // both radial splines share the knot interval and hence the weights (clamped rule of spline.h:275-310)
         float x = dist_coord;
-        int nk = P.q.nk;
         if (x < 1.f) {
             wv = (1.f / 6.f) * wide[0] + (2.f / 3.f) * wide[1] + (1.f / 6.f) * wide[2];
             nv = (1.f / 6.f) * narrow[0] + (2.f / 3.f) * narrow[1] + (1.f / 6.f) * narrow[2];
@@ -285,9 +298,9 @@ __device__ __forceinline__ float pair_term(const RotamerDev& P, const BeadRec& b
             wd = nd = 0.f;
         } else {
             int b = (int)x;
-            float y = x - (float)b;
-            deboor_core(wide[b - 1], wide[b], wide[b + 1], wide[b + 2], y, wv, wd);
-            deboor_core(narrow[b - 1], narrow[b], narrow[b + 1], narrow[b + 2], y, nv, nd);
+            bspline_weights(x - (float)b, w, d);
+            bspline_apply(w, d, wide[b - 1], wide[b], wide[b + 1], wide[b + 2], wv, wd);
+            bspline_apply(w, d, narrow[b - 1], narrow[b], narrow[b + 1], narrow[b + 2], nv, nd);
         }
     }
     float angular_weight = a1v * a2v;
@@ -306,13 +319,16 @@ __device__ __forceinline__ float pair_term(const RotamerDev& P, const BeadRec& b
 
 constexpr int PF = 4;   // row entries prefetched per lane: the index/code/marginal loads of a batch are independent
 
+template <int NKA, int NK>
 __global__ void __launch_bounds__(EDGE_TPB, 3) k_rot_energy(RotamerDev P, int want_pot, int n_rep) {
     extern __shared__ float4 smem4[];
     BeadRec* beads = reinterpret_cast<BeadRec*>(smem4);
     float* table = reinterpret_cast<float*>(beads + P.n_bead);
+    int* rowoff = reinterpret_cast<int*>(table + (((P.n_type * (P.n_type + 1) / 2) * P.g.n_param + 3) & ~3));
+    const PairTab T{table, rowoff};
     const int K = P.g.K1;
     const int grp = threadIdx.x / RG, lane = threadIdx.x % RG, n_grp = EDGE_TPB / RG;
-    stage_table(P, table);
+    stage_table(P, table, rowoff);
     for (int r = blockIdx.y; r < n_rep; r += gridDim.y) {
         __syncthreads();   // previous replica's readers are done with `beads`
         stage_beads(P, r, beads);
@@ -335,7 +351,7 @@ __global__ void __launch_bounds__(EDGE_TPB, 3) k_rot_energy(RotamerDev P, int wa
                 // partners with a smaller index only matter when they have a single state (their energy folds into bead i)
                 if (multi)
                     for (int k = lane; k < lo; k += RG)
-                        if (crow[k] == CODE_FOLD) fold += pair_term<false>(P, beads[row[k]], bi, table, nullptr, nullptr);
+                        if (crow[k] == CODE_FOLD) fold += pair_term<false, NKA, NK>(P, T, beads[row[k]], bi, nullptr, nullptr);
                 for (int k0 = lo + lane; k0 < c; k0 += RG * PF) {
                     int js[PF], cds[PF];
 #pragma unroll
@@ -350,7 +366,7 @@ __global__ void __launch_bounds__(EDGE_TPB, 3) k_rot_energy(RotamerDev P, int wa
                         if (js[u] < 0) continue;
                         if (cd <= -2 && cd != CODE_SS) continue;   // (single, multi): handled from the partner's row
                         if (cd == CODE_SS && !want_pot) continue;
-                        float V = pair_term<false>(P, bi, beads[js[u]], table, nullptr, nullptr);
+                        float V = pair_term<false, NKA, NK>(P, T, bi, beads[js[u]], nullptr, nullptr);
                         if (cd >= 0) { if (P.multi_bead_states) atomicAdd(&pmat[cd], V); else pmat[cd] = V; }
                         else if (cd == CODE_FOLD) fold += V;
                         else e11 += V;
@@ -367,13 +383,16 @@ __global__ void __launch_bounds__(EDGE_TPB, 3) k_rot_energy(RotamerDev P, int wa
     }
 }
 
+template <int NKA, int NK>
 __global__ void __launch_bounds__(EDGE_TPB, 3) k_rot_deriv(RotamerDev P, int n_rep) {
     extern __shared__ float4 smem4[];
     BeadRec* beads = reinterpret_cast<BeadRec*>(smem4);
     float* table = reinterpret_cast<float*>(beads + P.n_bead);
+    int* rowoff = reinterpret_cast<int*>(table + (((P.n_type * (P.n_type + 1) / 2) * P.g.n_param + 3) & ~3));
+    const PairTab T{table, rowoff};
     const int K = P.g.K1;
     const int grp = threadIdx.x / RG, lane = threadIdx.x % RG, n_grp = EDGE_TPB / RG;
-    stage_table(P, table);
+    stage_table(P, table, rowoff);
     for (int r = blockIdx.y; r < n_rep; r += gridDim.y) {
         __syncthreads();
         stage_beads(P, r, beads);
@@ -426,7 +445,7 @@ __global__ void __launch_bounds__(EDGE_TPB, 3) k_rot_deriv(RotamerDev P, int n_r
                         float d1[6], d2[6];
                         const bool first = i < js[u];
                         BeadRec bj = beads[js[u]];
-                        pair_term<true>(P, first ? bi : bj, first ? bj : bi, table, d1, d2);
+                        pair_term<true, NKA, NK>(P, T, first ? bi : bj, first ? bj : bi, d1, d2);
 #pragma unroll
                         for (int q = 0; q < 6; ++q) acc[q] += ss[u] * (first ? d1[q] : d2[q]);
                     }
@@ -1128,12 +1147,15 @@ struct RotamerSidechain : PotentialNode {
         smem_bp = fixed_bp + size_t(smem_pairs) * per_pair + 16;
         smem_prep = sizeof(unsigned) * size_t(n_res) * n_words + sizeof(int) * (4 * n_res + 2) + sizeof(float) * n_res * MAXR + sizeof(int) * ig.n1 +
                     sizeof(unsigned short) * size_t(n_res) * n_words + 16;
-        smem_edge = sizeof(BeadRec) * size_t(ig.n1) + sizeof(float) * table.n + sizeof(int) * (ig.n1 + 256);
+        smem_edge = sizeof(BeadRec) * size_t(ig.n1) + sizeof(float) * (table.n + 4) + sizeof(int) * size_t(ig.n_type1) * ig.n_type1 + 64;
+        if (ig.n_type1 > 255) throw std::string("rotamer node: more than 255 bead types");
         if (smem_prep > (size_t)device_smem || smem_edge > (size_t)device_smem || fixed_bp > (size_t)device_smem)
             throw std::string("rotamer node: system too large for the shared-memory kernels");
         UB_CUDA(cudaFuncSetAttribute(k_rot_prep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_prep));
-        UB_CUDA(cudaFuncSetAttribute(k_rot_energy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_edge));
-        UB_CUDA(cudaFuncSetAttribute(k_rot_deriv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_edge));
+        UB_CUDA(cudaFuncSetAttribute(k_rot_energy<15, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_edge));
+        UB_CUDA(cudaFuncSetAttribute(k_rot_deriv<15, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_edge));
+        UB_CUDA(cudaFuncSetAttribute(k_rot_energy<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_edge));
+        UB_CUDA(cudaFuncSetAttribute(k_rot_deriv<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_edge));
         UB_CUDA(cudaFuncSetAttribute(k_rot_bp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bp));
         plan_fast_bp(device_smem);
         slow_list.alloc(B);
@@ -1218,7 +1240,9 @@ struct RotamerSidechain : PotentialNode {
         engine->mark(s, "rotamer/pairlist");
         k_rot_prep<<<engine->n_rep, PREP_TPB, smem_prep, s>>>(P);
         engine->mark(s, "rotamer/prep");
-        k_rot_energy<<<dim3(P.n_chunk, persist), EDGE_TPB, smem_edge, s>>>(P, want, engine->n_rep);
+        const bool ff1_knots = nka == 15 && nk == 16;   // the PARAM_7A_CUTOFF build of the reference (bead_interaction.h:12-27)
+        if (ff1_knots) k_rot_energy<15, 16><<<dim3(P.n_chunk, persist), EDGE_TPB, smem_edge, s>>>(P, want, engine->n_rep);
+        else k_rot_energy<0, 0><<<dim3(P.n_chunk, persist), EDGE_TPB, smem_edge, s>>>(P, want, engine->n_rep);
         engine->mark(s, "rotamer/energy");
         if (fast_bp) {
             k_rot_bp2<<<engine->n_rep, BP2_TPB, smem_bp2, s>>>(P, lay2, want);
@@ -1227,7 +1251,8 @@ struct RotamerSidechain : PotentialNode {
             k_rot_bp<<<engine->n_rep, BP_TPB, smem_bp, s>>>(P, want, 0);
         }
         engine->mark(s, "rotamer/bp");
-        k_rot_deriv<<<dim3(P.n_chunk, persist), EDGE_TPB, smem_edge, s>>>(P, engine->n_rep);
+        if (ff1_knots) k_rot_deriv<15, 16><<<dim3(P.n_chunk, persist), EDGE_TPB, smem_edge, s>>>(P, engine->n_rep);
+        else k_rot_deriv<0, 0><<<dim3(P.n_chunk, persist), EDGE_TPB, smem_edge, s>>>(P, engine->n_rep);
         engine->mark(s, "rotamer/deriv");
     }
     bool get_pairlist(int replica, std::vector<int>& i1, std::vector<int>& i2) override { return ig.pairlist(replica, i1, i2); }
