@@ -194,7 +194,7 @@ def gpu_arm(args):
                     e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=bytes_io, d2h_bytes_per_step=bytes_io, steps=e2e_steps),
                     gpu_launches=int((launches * 3 + 3 + 2) * args.steps), roofline=roof,
                     cpu_baseline=({k: cpu[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')} if cpu else None))
-        print(json.dumps(line, default=float))
+        emit(line)
     eng.close()
     if world > 1:
         dist.destroy_process_group()
@@ -276,7 +276,7 @@ def reference_arm(args):
         return
     cpu = cpu_reference_arm(args.steps, args.warmup, max_seconds=90.0)
     if cpu is None:
-        print(json.dumps(dict(impl='reference', unavailable='oracle/_ref not built (run __graft_entry__.build() where /root/reference exists)')))
+        emit(dict(impl='reference', unavailable='oracle/_ref not built (run __graft_entry__.build() where /root/reference exists)'))
         return
     line = dict(impl='reference', metric=METRIC, value=cpu['value'], unit=UNIT, n_gpus=args.gpus, steps=cpu['rounds'], warmup=args.warmup,
                 ms_per_step=cpu['seconds'] * 1e3 / cpu['rounds'], higher_is_better=True, scaling='weak', vs_baseline=None,
@@ -285,10 +285,22 @@ def reference_arm(args):
                 us_per_force_eval=cpu['us_per_force_eval'],
                 cpu_baseline={k: cpu[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')},
                 e2e=dict(value=cpu['value'], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
-    print(json.dumps(line, default=float))
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """the one JSON line goes to the real stdout; everything else a library prints (NCCL's version banner) went to stderr"""
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (json.dumps(line, default=float) + '\n').encode())
 
 
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=30)

@@ -19,6 +19,7 @@
 #include <cmath>
 
 #include "igraph.cuh"
+#include "edgelist.cuh"
 
 namespace ub {
 namespace {
@@ -29,10 +30,13 @@ constexpr int EDGE_TPB = 256;
 constexpr int BP_TPB = 384;
 constexpr int RG = 8;              // lanes per bead row
 constexpr int MAX_PROB_NODES = 4;
-constexpr int CODE_FOLD = -1;      // (multi-state bead, single-state partner)
 constexpr int CODE_SS = INT_MIN;   // (single, single)
-// code >= 0: index into the replica's pair-matrix array (slot*36 + a*6 + b); code <= -2: (single bead, multi partner),
-// -2-code = partner's node index res*6+rot
+// Entry codes.  code >= 0: index into the replica's pair-matrix array (slot*36 + a*6 + b).  Otherwise, unless CODE_SS,
+// t = -2-code names a node state (t>>1 = res*6+rot) whose marginal weights the entry in the backward pass: bit 0 set
+// ("fold") = (multi-state bead, single-state partner), the node is the bead's own and the pair energy folds into its
+// 1-body energy; bit 0 clear = (single-state bead, multi-state partner), the node is the partner's.
+__host__ __device__ constexpr int code_node(int node, bool fold) { return -2 - (2 * node + (fold ? 1 : 0)); }
+__device__ __forceinline__ bool code_is_fold(int cd) { return cd < 0 && cd != CODE_SS && ((-2 - cd) & 1); }
 
 struct BeadRec {   // 32 bytes, staged in shared memory by the edge kernels
     float x, y, z, dx, dy, dz;
@@ -51,14 +55,20 @@ struct RotamerDev {
     float* prob_sens[MAX_PROB_NODES];
     int prob_wp[MAX_PROB_NODES], prob_n[MAX_PROB_NODES];
     float damping, tol;
-    int max_iter, chunk, max_pairs, smem_pairs, multi_bead_states, n_chunk;
-    // per-replica scratch in global memory
-    int* code;                // [B][n_bead][K1]
-    int* lower;               // [B][n_bead]  number of partners with a smaller bead index
+    int max_iter, chunk, max_pairs, smem_pairs, multi_bead_states, cap_e;
+    // per-replica scratch in global memory.  The bead pair list of a replica is kept as CSR rows (one row per bead, both
+    // directions of every pair, partners ascending): entry e of row i = rowstart[i] + k.
+    int* rowstart;            // [B][n_bead+1]
+    unsigned short* dj;       // [B][cap_e]  partner bead
+    int* code;                // [B][cap_e]  where the pair energy goes / which marginal weights its derivative
+    float* ss;                // [B][cap_e]  that marginal (written by the BP kernels)
+    unsigned short* lower;    // [B][n_bead] partners with a smaller bead index | bit 15: some of them fold into this bead
+    unsigned short* order_e;  // [B][n_bead] rows by falling number of entries the energy kernel evaluates
+    unsigned short* order_d;  // [B][n_bead] rows by falling length
     float* enode;             // [B][n_res][6]  1-body energy per (residue, state)
     float* fold;              // [B][n_bead]    energy of single-state partners
     float* e11;               // [B]
-    float* pmat;              // [B][max_pairs][36]  pair energy -> marginal
+    float* pmat;              // [B][max_pairs][36]  pair energy (-> marginal on the general BP path)
     unsigned short* pair_ab;  // [B][max_pairs][2]
     int* inc;                 // [B][2*max_pairs]
     int* istart;              // [B][n_res+1]
@@ -71,27 +81,54 @@ struct RotamerDev {
     int* error_flag;
 };
 
+// rows by falling key (clipped to 255) into order[0..n): counting sort, see sort_rows_desc (igraph.cuh)
+template <typename KeyF>
+__device__ __forceinline__ void sort_rows_desc_u16(int n, KeyF key, unsigned short* order, int* hist) {
+    for (int b = threadIdx.x; b < 256; b += blockDim.x) hist[b] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&hist[min(max(key(i), 0), 255)], 1);
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        int lane = threadIdx.x, sum = 0, v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { v[u] = hist[255 - (lane * 8 + u)]; sum += v[u]; }
+        int incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(UB_FULL_MASK, incl, o); if (lane >= o) incl += t; }
+        int run = incl - sum;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { hist[255 - (lane * 8 + u)] = run; run += v[u]; }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) order[atomicAdd(&hist[min(max(key(i), 0), 255)], 1)] = (unsigned short)i;
+    __syncthreads();
+}
+
 // ================================================================================================ prep
 __global__ void __launch_bounds__(PREP_TPB) k_rot_prep(RotamerDev P) {
     extern __shared__ unsigned smem_u[];
     const int r = blockIdx.x, tid = threadIdx.x;
-    const int nR = P.n_res, nW = P.n_words, K = P.g.K1;
+    const int nR = P.n_res, nW = P.n_words, K = P.g.K1, nb = P.n_bead;
     unsigned* bitmap = smem_u;                                   // [nR][nW] symmetric residue adjacency (multi-state only)
     int* estart = reinterpret_cast<int*>(bitmap + nR * nW);      // [nR+1] first slot of pairs (A,B>A)
     int* istart = estart + nR + 1;                               // [nR+1]
     int* deg = istart + nR + 1;                                  // [nR]
     int* ebase = deg + nR;                                       // [nR] slot base: estart - (neighbours below)
     float* en = reinterpret_cast<float*>(ebase + nR);            // [nR*6]
-    const unsigned short* nbr = P.g.nbr1 + size_t(r) * P.n_bead * K;
-    const int* cnt = P.g.cnt1 + size_t(r) * P.n_bead;
-    int* code = P.code + size_t(r) * P.n_bead * K;
+    int* rr = reinterpret_cast<int*>(en + nR * MAXR);            // [n_bead] res << 4 | rot << 1 | multi-state
+    int* rs = rr + nb;                                           // [n_bead+1] CSR row starts
+    int* wtot = rs + nb + 1;                                     // [33]
+    int* hist = wtot + 33;                                       // [256]
+    unsigned short* wpre = reinterpret_cast<unsigned short*>(hist + 256);   // [nR][nW] set bits in the words before w
+    unsigned short* lo_s = wpre + nR * nW;                       // [n_bead]
+    unsigned short* ce_s = lo_s + nb;                            // [n_bead] entries the energy kernel evaluates
+    const unsigned short* nbr = P.g.nbr1 + size_t(r) * nb * K;
+    const int* cnt = P.g.cnt1 + size_t(r) * nb;
 
     for (int i = tid; i < nR * nW; i += PREP_TPB) bitmap[i] = 0u;
     for (int i = tid; i < nR * MAXR; i += PREP_TPB) en[i] = 0.f;
     __syncthreads();
-    int* rr = reinterpret_cast<int*>(en + nR * MAXR);   // [n_bead] res << 4 | rot << 1 | multi-state
-    unsigned short* wpre = reinterpret_cast<unsigned short*>(rr + P.n_bead);   // [nR][nW] set bits in the words before w
-    for (int i = tid; i < P.n_bead; i += PREP_TPB) {
+    for (int i = tid; i < nb; i += PREP_TPB) {
         float e = 0.f;
         int loc = P.g.s1.loc[i];
         for (int p = 0; p < P.n_prob; ++p) e += P.prob_out[p][(size_t(r) * P.prob_n[p] + loc) * P.prob_wp[p]];
@@ -101,15 +138,13 @@ __global__ void __launch_bounds__(PREP_TPB) k_rot_prep(RotamerDev P) {
     }
     __syncthreads();
     const int grp = tid / RG, lane = tid % RG, n_grp = PREP_TPB / RG;
-    for (int i0 = 0; i0 < P.n_bead; i0 += n_grp) {   // RG lanes per bead row: adjacency bits and the count of lower partners
-        int i = i0 + grp, lo = 0;
-        if (i < P.n_bead) {
+    for (int i0 = 0; i0 < nb; i0 += n_grp) {   // RG lanes per bead row: adjacency bits
+        int i = i0 + grp;
+        if (i < nb) {
             const unsigned short* row = nbr + size_t(i) * K;
             int c = cnt[i], me = rr[i];
             for (int k = lane; k < c; k += RG) {
-                int j = row[k];
-                lo += j < i;
-                int other = rr[j];
+                int other = rr[row[k]];
                 if (me & other & 1) {
                     // both directions, so that the adjacency stays symmetric even if a row was truncated by a capacity
                     // overflow (reported through error_flag): every index derived below relies on that symmetry
@@ -118,11 +153,8 @@ __global__ void __launch_bounds__(PREP_TPB) k_rot_prep(RotamerDev P) {
                 }
             }
         }
-#pragma unroll
-        for (int o = RG / 2; o > 0; o >>= 1) lo += __shfl_xor_sync(UB_FULL_MASK, lo, o);
-        if (i < P.n_bead && lane == 0) P.lower[size_t(r) * P.n_bead + i] = lo;
     }
-    __syncthreads();
+    scan_row_lengths(nb, [&](int i) { return cnt[i]; }, rs, wtot);   // (ends with a barrier: the bitmap is complete too)
     // Per residue: running popcounts of its adjacency row (wpre), degree, and the number of neighbours below itself.  With
     // them the slot of pair (A,B>A) is ebase[A] + R_A(B), R_A(B) = wpre[A][B>>5] + popc(row_A[B>>5] below bit B): two
     // independent shared-memory loads instead of a loop over the row.
@@ -164,15 +196,20 @@ __global__ void __launch_bounds__(PREP_TPB) k_rot_prep(RotamerDev P) {
     const int n_pair = estart[nR];
     if (tid == 0) { P.stats[size_t(r) * 4 + 1] = n_pair; P.e11[r] = 0.f; }
     if (tid == 0 && r == 0) *P.n_slow = 0;
-    if (n_pair > P.max_pairs) {   // uniform across the block: report, and leave an empty (consistent) graph behind
-        if (tid == 0) { atomicExch(P.error_flag, 2); P.stats[size_t(r) * 4 + 1] = 0; }
+    int* rowstart = P.rowstart + size_t(r) * (nb + 1);
+    if (n_pair > P.max_pairs || rs[nb] > P.cap_e) {   // uniform across the block: report, and leave an empty graph behind
+        if (tid == 0) { atomicExch(P.error_flag, n_pair > P.max_pairs ? 2 : 3); P.stats[size_t(r) * 4 + 1] = 0; }
         for (int A = tid; A <= nR; A += PREP_TPB) P.istart[size_t(r) * (nR + 1) + A] = 0;
-        for (int i = tid; i < P.n_bead * K; i += PREP_TPB) code[i] = CODE_SS;
+        for (int i = tid; i <= nb; i += PREP_TPB) rowstart[i] = 0;
+        for (int i = tid; i < nb; i += PREP_TPB) {
+            P.lower[size_t(r) * nb + i] = 0; P.order_e[size_t(r) * nb + i] = P.order_d[size_t(r) * nb + i] = (unsigned short)i;
+        }
         return;
     }
     unsigned short* pair_ab = P.pair_ab + size_t(r) * P.max_pairs * 2;
     int* inc = P.inc + size_t(r) * 2 * P.max_pairs;
     for (int A = tid; A <= nR; A += PREP_TPB) P.istart[size_t(r) * (nR + 1) + A] = istart[A];
+    for (int i = tid; i <= nb; i += PREP_TPB) rowstart[i] = rs[i];
     for (int A = tid; A < nR; A += PREP_TPB) {
         const unsigned* row = bitmap + A * nW;
         int t = istart[A], up = 0;
@@ -197,25 +234,45 @@ __global__ void __launch_bounds__(PREP_TPB) k_rot_prep(RotamerDev P) {
         float4* pm4 = reinterpret_cast<float4*>(P.pmat + size_t(r) * P.max_pairs * 36);
         for (int i = tid; i < n_pair * 9; i += PREP_TPB) pm4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    // per-entry codes
-    for (int i0 = 0; i0 < P.n_bead; i0 += n_grp) {
+    // CSR rows: partner + code per entry; per row the number of lower partners and of entries the energy kernel evaluates
+    unsigned short* dj = P.dj + size_t(r) * P.cap_e;
+    int* code = P.code + size_t(r) * P.cap_e;
+    for (int i0 = 0; i0 < nb; i0 += n_grp) {
         int i = i0 + grp;
-        if (i >= P.n_bead) continue;
-        int me = rr[i], A = me >> 4, ra = (me >> 1) & 7;
-        bool mA = me & 1;
-        const unsigned short* row = nbr + size_t(i) * K;
-        int c = cnt[i];
-        for (int k = lane; k < c; k += RG) {
-            int other = rr[row[k]], Bq = other >> 4, rb = (other >> 1) & 7;
-            bool mB = other & 1;
-            int cd;
-            if (mA && mB) cd = A < Bq ? slot_of(A, Bq) * 36 + ra * 6 + rb : slot_of(Bq, A) * 36 + rb * 6 + ra;
-            else if (mA) cd = CODE_FOLD;
-            else if (mB) cd = -2 - (Bq * MAXR + rb);
-            else cd = CODE_SS;
-            code[size_t(i) * K + k] = cd;
+        int lo = 0, nfl = 0, nev = 0;
+        if (i < nb) {
+            int me = rr[i], A = me >> 4, ra = (me >> 1) & 7;
+            bool mA = me & 1;
+            const unsigned short* row = nbr + size_t(i) * K;
+            const int c = cnt[i], base = rs[i];
+            for (int k = lane; k < c; k += RG) {
+                const int j = row[k];
+                int other = rr[j], Bq = other >> 4, rb = (other >> 1) & 7;
+                bool mB = other & 1;
+                int cd;
+                if (mA && mB) cd = A < Bq ? slot_of(A, Bq) * 36 + ra * 6 + rb : slot_of(Bq, A) * 36 + rb * 6 + ra;
+                else if (mA) cd = code_node(A * MAXR + ra, true);
+                else if (mB) cd = code_node(Bq * MAXR + rb, false);
+                else cd = CODE_SS;
+                dj[base + k] = (unsigned short)j;
+                code[base + k] = cd;
+                const bool below = j < i;
+                lo += below;
+                nfl += below && mA && !mB;
+                nev += below ? (mA && !mB) : (mA || !mB);   // upper entries of a single-state bead with a multi-state partner are skipped
+            }
         }
+#pragma unroll
+        for (int o = RG / 2; o > 0; o >>= 1) {
+            lo += __shfl_xor_sync(UB_FULL_MASK, lo, o); nfl += __shfl_xor_sync(UB_FULL_MASK, nfl, o); nev += __shfl_xor_sync(UB_FULL_MASK, nev, o);
+        }
+        if (i < nb && lane == 0) { lo_s[i] = (unsigned short)(lo | (nfl ? 0x8000 : 0)); ce_s[i] = (unsigned short)nev; }
     }
+    __syncthreads();
+    for (int i = tid; i < nb; i += PREP_TPB) P.lower[size_t(r) * nb + i] = lo_s[i];
+    // thread-per-row consumers take the rows in order of falling length, so that the threads of a warp finish together
+    sort_rows_desc_u16(nb, [&](int i) { return (int)ce_s[i]; }, P.order_e + size_t(r) * nb, hist);
+    sort_rows_desc_u16(nb, [&](int i) { return rs[i + 1] - rs[i]; }, P.order_d + size_t(r) * nb, hist);
 }
 
 // ================================================================================================ edge kernels
@@ -317,8 +374,12 @@ __device__ __forceinline__ float pair_term(const RotamerDev& P, const PairTab& T
     return wv + angular_weight * nv;
 }
 
-constexpr int PF = 4;   // row entries prefetched per lane: the index/code/marginal loads of a batch are independent
+constexpr int PF = 4;   // row entries fetched per step: the index/code/weight loads of a step are independent
 
+// Edge kernels: ONE THREAD PER CSR ROW, rows taken in order of falling length (order_e / order_d from k_rot_prep) so that
+// the threads of a warp walk rows of about the same length; a thread keeps its row's sums in registers, so nothing is
+// reduced across lanes and every sum has a fixed order.  CTAs are persistent over replicas (blockIdx.y strides); with a
+// small batch the rows of a replica are split over gridDim.x CTAs.
 template <int NKA, int NK>
 __global__ void __launch_bounds__(EDGE_TPB, 3) k_rot_energy(RotamerDev P, int want_pot, int n_rep) {
     extern __shared__ float4 smem4[];
@@ -326,55 +387,50 @@ __global__ void __launch_bounds__(EDGE_TPB, 3) k_rot_energy(RotamerDev P, int wa
     float* table = reinterpret_cast<float*>(beads + P.n_bead);
     int* rowoff = reinterpret_cast<int*>(table + (((P.n_type * (P.n_type + 1) / 2) * P.g.n_param + 3) & ~3));
     const PairTab T{table, rowoff};
-    const int K = P.g.K1;
-    const int grp = threadIdx.x / RG, lane = threadIdx.x % RG, n_grp = EDGE_TPB / RG;
+    const int nb = P.n_bead;
     stage_table(P, table, rowoff);
     for (int r = blockIdx.y; r < n_rep; r += gridDim.y) {
         __syncthreads();   // previous replica's readers are done with `beads`
         stage_beads(P, r, beads);
         __syncthreads();
-        const unsigned short* nbr = P.g.nbr1 + size_t(r) * P.n_bead * K;
-        const int* cnt = P.g.cnt1 + size_t(r) * P.n_bead;
-        const int* code = P.code + size_t(r) * P.n_bead * K;
-        const int* lower = P.lower + size_t(r) * P.n_bead;
+        const int* rowstart = P.rowstart + size_t(r) * (nb + 1);
+        const unsigned short* dj = P.dj + size_t(r) * P.cap_e;
+        const int* code = P.code + size_t(r) * P.cap_e;
+        const unsigned short* order = P.order_e + size_t(r) * nb;
+        const unsigned short* lower = P.lower + size_t(r) * nb;
         float* pmat = P.pmat + size_t(r) * P.max_pairs * 36;
         float e11 = 0.f;
-        for (int i0 = blockIdx.x * n_grp; i0 < P.n_bead; i0 += gridDim.x * n_grp) {
-            int i = i0 + grp;
+        for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nb; t += gridDim.x * blockDim.x) {
+            const int i = order[t];
+            const BeadRec bi = beads[i];
+            const int base = rowstart[i], c = rowstart[i + 1] - base;
+            const int lw = lower[i], lo = lw & 0x7fff;
             float fold = 0.f;
-            if (i < P.n_bead) {
-                BeadRec bi = beads[i];
-                const bool multi = P.res_nrot[bi.res_rot >> 3] > 1;
-                const unsigned short* row = nbr + size_t(i) * K;
-                const int* crow = code + size_t(i) * K;
-                const int c = cnt[i], lo = lower[i];
-                // partners with a smaller index only matter when they have a single state (their energy folds into bead i)
-                if (multi)
-                    for (int k = lane; k < lo; k += RG)
-                        if (crow[k] == CODE_FOLD) fold += pair_term<false, NKA, NK>(P, T, beads[row[k]], bi, nullptr, nullptr);
-                for (int k0 = lo + lane; k0 < c; k0 += RG * PF) {
-                    int js[PF], cds[PF];
+            // partners with a smaller index only matter when they have a single state (their energy folds into bead i)
+            if (lw & 0x8000)
+                for (int k = 0; k < lo; ++k)
+                    if (code_is_fold(code[base + k])) fold += pair_term<false, NKA, NK>(P, T, beads[dj[base + k]], bi, nullptr, nullptr);
+            for (int k0 = lo; k0 < c; k0 += PF) {
+                int js[PF], cds[PF];
 #pragma unroll
-                    for (int u = 0; u < PF; ++u) {
-                        int k = k0 + u * RG;
-                        js[u] = k < c ? (int)row[k] : -1;
-                        cds[u] = k < c ? crow[k] : CODE_SS;
-                    }
+                for (int u = 0; u < PF; ++u) {
+                    const int k = k0 + u;
+                    js[u] = k < c ? (int)dj[base + k] : -1;
+                    cds[u] = k < c ? code[base + k] : CODE_SS;
+                }
 #pragma unroll
-                    for (int u = 0; u < PF; ++u) {
-                        int cd = cds[u];
-                        if (js[u] < 0) continue;
-                        if (cd <= -2 && cd != CODE_SS) continue;   // (single, multi): handled from the partner's row
-                        if (cd == CODE_SS && !want_pot) continue;
-                        float V = pair_term<false, NKA, NK>(P, T, bi, beads[js[u]], nullptr, nullptr);
-                        if (cd >= 0) { if (P.multi_bead_states) atomicAdd(&pmat[cd], V); else pmat[cd] = V; }
-                        else if (cd == CODE_FOLD) fold += V;
-                        else e11 += V;
-                    }
+                for (int u = 0; u < PF; ++u) {
+                    const int cd = cds[u];
+                    if (js[u] < 0) continue;
+                    if (cd == CODE_SS) { if (!want_pot) continue; }
+                    else if (cd < 0 && !code_is_fold(cd)) continue;   // (single, multi): handled from the partner's row
+                    const float V = pair_term<false, NKA, NK>(P, T, bi, beads[js[u]], nullptr, nullptr);
+                    if (cd >= 0) { if (P.multi_bead_states) atomicAdd(&pmat[cd], V); else pmat[cd] = V; }
+                    else if (cd == CODE_SS) e11 += V;
+                    else fold += V;
                 }
             }
-            fold = group_sum<RG>(fold);
-            if (i < P.n_bead && lane == 0) P.fold[size_t(r) * P.n_bead + i] = fold;
+            P.fold[size_t(r) * nb + i] = fold;
         }
         if (want_pot) {
             e11 = warp_sum(e11);
@@ -390,76 +446,70 @@ __global__ void __launch_bounds__(EDGE_TPB, 3) k_rot_deriv(RotamerDev P, int n_r
     float* table = reinterpret_cast<float*>(beads + P.n_bead);
     int* rowoff = reinterpret_cast<int*>(table + (((P.n_type * (P.n_type + 1) / 2) * P.g.n_param + 3) & ~3));
     const PairTab T{table, rowoff};
-    const int K = P.g.K1;
-    const int grp = threadIdx.x / RG, lane = threadIdx.x % RG, n_grp = EDGE_TPB / RG;
+    const int nb = P.n_bead;
     stage_table(P, table, rowoff);
     for (int r = blockIdx.y; r < n_rep; r += gridDim.y) {
         __syncthreads();
         stage_beads(P, r, beads);
         __syncthreads();
-        const unsigned short* nbr = P.g.nbr1 + size_t(r) * P.n_bead * K;
-        const int* cnt = P.g.cnt1 + size_t(r) * P.n_bead;
-        const int* code = P.code + size_t(r) * P.n_bead * K;
-        const float* pmat = P.pmat + size_t(r) * P.max_pairs * 36;
+        const int* rowstart = P.rowstart + size_t(r) * (nb + 1);
+        const unsigned short* dj = P.dj + size_t(r) * P.cap_e;
+        const float* ssr = P.ss + size_t(r) * P.cap_e;
+        const unsigned short* order = P.order_d + size_t(r) * nb;
         const float* nm = P.node_marg + size_t(r) * P.n_res * MAXR;
-        for (int i0 = blockIdx.x * n_grp; i0 < P.n_bead; i0 += gridDim.x * n_grp) {
-            int i = i0 + grp;
-            float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            float my_marg = 0.f;
-            float4 old_a = make_float4(0.f, 0.f, 0.f, 0.f), old_b = old_a;
+        for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nb; t += gridDim.x * blockDim.x) {
+            const int i = order[t];
+            const BeadRec bi = beads[i];
+            const int base = rowstart[i], c = rowstart[i + 1] - base;
+            // the read half of the read-modify-writes is issued before the row walk hides its latency
+            float* dst = elem_sens_ptr(P.g.s1, r, i);
+            float4 old_a = reinterpret_cast<const float4*>(dst)[0], old_b = reinterpret_cast<const float4*>(dst)[1];
+            const int loc = P.g.s1.loc[i];
             float old_p[MAX_PROB_NODES] = {0.f, 0.f, 0.f, 0.f};
-            float* dst = nullptr;
-            int loc = 0;
-            if (i < P.n_bead) {
-                BeadRec bi = beads[i];
-                my_marg = nm[(bi.res_rot >> 3) * MAXR + (bi.res_rot & 7)];
-                if (lane == 0) {   // the read half of the read-modify-writes is issued before the row walk hides its latency
-                    dst = elem_sens_ptr(P.g.s1, r, i);
-                    old_a = reinterpret_cast<const float4*>(dst)[0];
-                    old_b = reinterpret_cast<const float4*>(dst)[1];
-                    loc = P.g.s1.loc[i];
-                    for (int p = 0; p < P.n_prob; ++p) old_p[p] = P.prob_sens[p][(size_t(r) * P.prob_n[p] + loc) * P.prob_wp[p]];
+            for (int p = 0; p < P.n_prob; ++p) old_p[p] = P.prob_sens[p][(size_t(r) * P.prob_n[p] + loc) * P.prob_wp[p]];
+            const float my_marg = nm[(bi.res_rot >> 3) * MAXR + (bi.res_rot & 7)];
+            float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            for (int k0 = 0; k0 < c; k0 += PF) {
+                int js[PF];
+                float ss[PF];
+#pragma unroll
+                for (int u = 0; u < PF; ++u) {
+                    const int k = k0 + u;
+                    js[u] = k < c ? (int)dj[base + k] : -1;
+                    ss[u] = k < c ? ssr[base + k] : 0.f;
                 }
-                const unsigned short* row = nbr + size_t(i) * K;
-                const int* crow = code + size_t(i) * K;
-                const int c = cnt[i];
-                for (int k0 = lane; k0 < c; k0 += RG * PF) {
-                    int js[PF], cds[PF];
-                    float ss[PF];
 #pragma unroll
-                    for (int u = 0; u < PF; ++u) {
-                        int k = k0 + u * RG;
-                        js[u] = k < c ? (int)row[k] : -1;
-                        cds[u] = k < c ? crow[k] : CODE_SS;
-                    }
+                for (int u = 0; u < PF; ++u) {
+                    if (js[u] < 0) continue;
+                    // one evaluation with the operands in (lower index, higher index) order, as the reference's i1<i2
+                    // edge; selecting operands and results instead of branching keeps the warp converged
+                    float d1[6], d2[6];
+                    const bool first = i < js[u];
+                    const BeadRec bj = beads[js[u]];
+                    pair_term<true, NKA, NK>(P, T, first ? bi : bj, first ? bj : bi, d1, d2);
 #pragma unroll
-                    for (int u = 0; u < PF; ++u) {
-                        int cd = cds[u];
-                        ss[u] = js[u] < 0 ? 0.f : (cd >= 0 ? pmat[cd] : (cd == CODE_FOLD ? my_marg : (cd == CODE_SS ? 1.f : nm[-2 - cd])));
-                    }
-#pragma unroll
-                    for (int u = 0; u < PF; ++u) {
-                        if (js[u] < 0) continue;
-                        // one evaluation with the operands in (lower index, higher index) order, as the reference's i1<i2
-                        // edge; selecting operands and results instead of branching keeps the warp converged
-                        float d1[6], d2[6];
-                        const bool first = i < js[u];
-                        BeadRec bj = beads[js[u]];
-                        pair_term<true, NKA, NK>(P, T, first ? bi : bj, first ? bj : bi, d1, d2);
-#pragma unroll
-                        for (int q = 0; q < 6; ++q) acc[q] += ss[u] * (first ? d1[q] : d2[q]);
-                    }
+                    for (int q = 0; q < 6; ++q) acc[q] += ss[u] * (first ? d1[q] : d2[q]);
                 }
             }
-#pragma unroll
-            for (int q = 0; q < 6; ++q) acc[q] = group_sum<RG>(acc[q]);
-            if (i < P.n_bead && lane == 0) {
-                old_a.x += acc[0]; old_a.y += acc[1]; old_a.z += acc[2]; old_a.w += acc[3]; old_b.x += acc[4]; old_b.y += acc[5];
-                reinterpret_cast<float4*>(dst)[0] = old_a;
-                reinterpret_cast<float4*>(dst)[1] = old_b;
-                for (int p = 0; p < P.n_prob; ++p) P.prob_sens[p][(size_t(r) * P.prob_n[p] + loc) * P.prob_wp[p]] = old_p[p] + my_marg;
-            }
+            old_a.x += acc[0]; old_a.y += acc[1]; old_a.z += acc[2]; old_a.w += acc[3]; old_b.x += acc[4]; old_b.y += acc[5];
+            reinterpret_cast<float4*>(dst)[0] = old_a;
+            reinterpret_cast<float4*>(dst)[1] = old_b;
+            for (int p = 0; p < P.n_prob; ++p) P.prob_sens[p][(size_t(r) * P.prob_n[p] + loc) * P.prob_wp[p]] = old_p[p] + my_marg;
         }
+    }
+}
+
+// weight of every CSR entry in the backward pass (propagate_derivatives, rotamer.cpp:956-985): the pair marginal for two
+// multi-state residues, a node marginal when one of them has a single state, 1 for two single-state residues.
+// pair_marg(code) and node_marg(node) read the marginals wherever the calling BP kernel holds them.
+template <typename PairF, typename NodeF>
+__device__ __forceinline__ void emit_entry_weights(const RotamerDev& P, int r, int n_thread, PairF pair_marg, NodeF node_marg) {
+    const int n_ent = P.rowstart[size_t(r) * (P.n_bead + 1) + P.n_bead];
+    const int* code = P.code + size_t(r) * P.cap_e;
+    float* ss = P.ss + size_t(r) * P.cap_e;
+    for (int e = threadIdx.x; e < n_ent; e += n_thread) {
+        const int cd = code[e];
+        ss[e] = cd >= 0 ? pair_marg(cd) : (cd == CODE_SS ? 1.f : node_marg((-2 - cd) >> 1));
     }
 }
 
@@ -700,6 +750,8 @@ __device__ void bp_solve_generic(const RotamerDev& P, int want_pot, int r, float
                 out[a * 6 + b] = mg;
             }
     }
+    __syncthreads();   // this CTA's global writes of the pair marginals are visible to all its threads
+    emit_entry_weights(P, r, BP_TPB, [&](int cd) { return g_pmat[cd]; }, [&](int node) { return bel[node]; });
     if (want_pot) {
         float tot = block_sum(en, red);
         if (tid == 0) P.potential[r] = tot + P.e11[r];
@@ -751,11 +803,11 @@ __device__ __forceinline__ void bp2_pair(const float* __restrict__ bel, int nRp,
     for (int b = 0; b < NB; ++b) msg[(6 + b) * SP + p] = m2[b] * i2;
 }
 
-// pair marginal (rotamer.cpp:403-429) written back in the pair's original (A,B) orientation, plus its Bethe term (:431-451)
+// pair marginal (rotamer.cpp:403-429), in place of the pair's probability matrix in shared memory, plus its Bethe term
+// (:431-451)
 template <int NA, int NB>
 __device__ __forceinline__ float bp2_pair_marginal(const float* __restrict__ bel, int nRp, int F, int S, const float* __restrict__ msg,
-                                                   int SP, int p, const float* __restrict__ Pc, int nc, int q, float* __restrict__ out,
-                                                   bool swapped, int want_pot) {
+                                                   int SP, int p, float* __restrict__ Pc, int nc, int q, int want_pot) {
     float bc1[NA], bc2[NB], b1[NA], b2[NB];
 #pragma unroll
     for (int a = 0; a < NA; ++a) { b1[a] = bel[a * nRp + F]; bc1[a] = b1[a] / (1e-10f + msg[a * SP + p]); }
@@ -774,7 +826,7 @@ __device__ __forceinline__ float bp2_pair_marginal(const float* __restrict__ bel
             float pr = Pc[(a * NB + b) * nc + q];
             float mg = pr * bc1[a] * bc2[b] * is;
             if (want_pot) en += mg * __logf((1e-10f + mg) / (1e-10f + pr * b1[a] * b2[b]));
-            out[swapped ? b * 6 + a : a * 6 + b] = mg;
+            Pc[(a * NB + b) * nc + q] = mg;
         }
     return en;
 }
@@ -900,9 +952,9 @@ __global__ void __launch_bounds__(BP2_TPB, 3) k_rot_bp2(RotamerDev P, Bp2Lay L, 
             fs[2 * p + 1] = (unsigned short)(sw ? A : B);
         }
     }
-    const float* P66 = Pm;
-    const float* P36 = Pm + 36 * n66;
-    const float* P33 = P36 + 18 * n36;
+    float* P66 = Pm;
+    float* P36 = Pm + 36 * n66;
+    float* P33 = P36 + 18 * n36;
 
     // ---- node energies -> probabilities (convert_energy_to_prob :239-256; single-state partners already folded) ----------
     for (int i = tid; i < nR * MAXR; i += BP2_TPB) { int A = i / MAXR, a = i % MAXR; bel[a * nRp + A] = P.enode[size_t(r) * nR * MAXR + i]; }
@@ -1036,12 +1088,23 @@ __global__ void __launch_bounds__(BP2_TPB, 3) k_rot_bp2(RotamerDev P, Bp2Lay L, 
     __syncthreads();
     for (int p = tid; p < n_pair; p += BP2_TPB) {
         const int F = fs[2 * p] & 0x7fff, S = fs[2 * p + 1];
-        const bool sw = fs[2 * p] >> 15;
-        float* out = g_pmat + size_t(perm[p]) * 36;
-        if (p < n66) en += bp2_pair_marginal<6, 6>(bel, nRp, F, S, msg, SP, p, P66, n66, p, out, sw, want_pot);
-        else if (p < n66 + n36) en += bp2_pair_marginal<3, 6>(bel, nRp, F, S, msg, SP, p, P36, n36, p - n66, out, sw, want_pot);
-        else en += bp2_pair_marginal<3, 3>(bel, nRp, F, S, msg, SP, p, P33, n33, p - n66 - n36, out, sw, want_pot);
+        if (p < n66) en += bp2_pair_marginal<6, 6>(bel, nRp, F, S, msg, SP, p, P66, n66, p, want_pot);
+        else if (p < n66 + n36) en += bp2_pair_marginal<3, 6>(bel, nRp, F, S, msg, SP, p, P36, n36, p - n66, want_pot);
+        else en += bp2_pair_marginal<3, 3>(bel, nRp, F, S, msg, SP, p, P33, n33, p - n66 - n36, want_pot);
     }
+    __syncthreads();
+    // backward-pass weight of every bead-pair entry, read from the marginals while they are in shared memory
+    emit_entry_weights(P, r, BP2_TPB,
+        [&](int cd) {
+            const int slot = cd / 36, ab = cd - slot * 36, a = ab / 6, b = ab - a * 6;
+            const int p = pos[slot];
+            const bool sw = fs[2 * p] >> 15;
+            const int f = sw ? b : a, s2 = sw ? a : b;
+            if (p < n66) return P66[(f * 6 + s2) * n66 + p];
+            if (p < n66 + n36) return P36[(f * 6 + s2) * n36 + (p - n66)];
+            return P33[(f * 3 + s2) * n33 + (p - n66 - n36)];
+        },
+        [&](int node) { const int A = node / MAXR; return bel[(node - A * MAXR) * nRp + A]; });
     if (want_pot) {
         float tot = block_sum(en, red);
         if (tid == 0) P.potential[r] = tot + P.e11[r];
@@ -1055,9 +1118,10 @@ struct RotamerSidechain : PotentialNode {
     float knot_spacing = 0.5f;
     int n_res = 0, n_words = 0, max_pairs = 0, smem_pairs = 0, multi_bead_states = 0;
     std::vector<int> bead_res, bead_rot, res_nrot, res_key;
-    DevBuf<int> d_bead_res, d_bead_rot, d_res_nrot, inc, istart, stats, code, lower;
-    DevBuf<float> pmat, node_marg, enode, fold, e11, table;
-    DevBuf<unsigned short> pair_ab;
+    DevBuf<int> d_bead_res, d_bead_rot, d_res_nrot, inc, istart, stats, code, rowstart;
+    DevBuf<float> pmat, node_marg, enode, fold, e11, table, ss;
+    DevBuf<unsigned short> pair_ab, dj, lower, order_e, order_d;
+    int cap_e = 0, edge_tpb = EDGE_TPB, edge_split = 1;
     float damping, tol;
     int max_iter, chunk;
     size_t smem_prep = 0, smem_edge = 0, smem_bp = 0, smem_bp2 = 0;
@@ -1145,8 +1209,27 @@ struct RotamerSidechain : PotentialNode {
         size_t budget = std::min<size_t>(device_smem, 110 * 1024);
         smem_pairs = budget > fixed_bp ? (int)std::min<size_t>(max_pairs, (budget - fixed_bp) / per_pair) : 0;
         smem_bp = fixed_bp + size_t(smem_pairs) * per_pair + 16;
-        smem_prep = sizeof(unsigned) * size_t(n_res) * n_words + sizeof(int) * (4 * n_res + 2) + sizeof(float) * n_res * MAXR + sizeof(int) * ig.n1 +
-                    sizeof(unsigned short) * size_t(n_res) * n_words + 16;
+        smem_prep = sizeof(unsigned) * size_t(n_res) * n_words + sizeof(int) * (4 * n_res + 2) + sizeof(float) * n_res * MAXR +
+                    sizeof(int) * (2 * size_t(ig.n1) + 1 + 33 + 256) + sizeof(unsigned short) * (size_t(n_res) * n_words + 2 * size_t(ig.n1)) + 16;
+        // CSR capacity: 64 partners per bead on average (a collapsed 100-residue globule has ~50 within 7 A), never more than
+        // the ELL rows can hold; an overflow raises the engine's error flag
+        {
+            double scale = 1.0;
+            if (const char* sc = getenv("UPSIDE_B200_NEIGHBOR_SCALE")) scale = std::max(0.05, atof(sc));
+            long want = (long)std::ceil(64 * scale * ig.n1);
+            cap_e = (int)std::max<long>(16, std::min<long>(long(ig.n1) * ig.K1, want));
+            cap_e = (cap_e + 7) & ~7;   // keeps the per-replica arrays 16-byte aligned
+        }
+        // one thread per bead row: the smallest block (whole warps, <= 256 threads) that covers the rows in equal passes;
+        // with a small batch the rows are split over several CTAs instead
+        if (engine->n_rep >= 148) {
+            int passes = (ig.n1 + EDGE_TPB - 1) / EDGE_TPB;
+            edge_tpb = std::min(EDGE_TPB, (((ig.n1 + passes - 1) / passes) + 31) & ~31);
+            edge_split = 1;
+        } else {
+            edge_tpb = 64;
+            edge_split = std::max(1, std::min((ig.n1 + 63) / 64, 600 / std::max(1, engine->n_rep)));
+        }
         smem_edge = sizeof(BeadRec) * size_t(ig.n1) + sizeof(float) * (table.n + 4) + sizeof(int) * size_t(ig.n_type1) * ig.n_type1 + 64;
         if (ig.n_type1 > 255) throw std::string("rotamer node: more than 255 bead types");
         if (smem_prep > (size_t)device_smem || smem_edge > (size_t)device_smem || fixed_bp > (size_t)device_smem)
@@ -1169,8 +1252,13 @@ struct RotamerSidechain : PotentialNode {
         fold.alloc(B * ig.n1);
         e11.alloc(B);
         stats.alloc(B * 4);
-        code.alloc(B * size_t(ig.n1) * ig.K1);
+        code.alloc(B * size_t(cap_e));
+        dj.alloc(B * size_t(cap_e));
+        ss.alloc(B * size_t(cap_e));
+        rowstart.alloc(B * (ig.n1 + 1));
         lower.alloc(B * ig.n1);
+        order_e.alloc(B * ig.n1);
+        order_d.alloc(B * ig.n1);
     }
     // Shared-memory plan of k_rot_bp2: the most resident CTAs per SM (at most 3) whose pair capacity still covers a typical
     // replica (3.8 residue pairs per residue; measured 2.6-3.3 on coil-like chains) with 26 floats of
@@ -1222,9 +1310,9 @@ struct RotamerSidechain : PotentialNode {
         }
         P.damping = damping; P.tol = tol; P.max_iter = max_iter; P.chunk = chunk; P.max_pairs = max_pairs;
         P.smem_pairs = smem_pairs; P.multi_bead_states = multi_bead_states;
-        // split a replica's beads over several CTAs only when the batch alone cannot fill the GPU
-        P.n_chunk = std::max(1, std::min(8, 600 / std::max(1, engine->n_rep)));
-        P.code = code.p; P.lower = lower.p; P.enode = enode.p; P.fold = fold.p; P.e11 = e11.p;
+        P.cap_e = cap_e;
+        P.code = code.p; P.dj = dj.p; P.ss = ss.p; P.rowstart = rowstart.p; P.lower = lower.p; P.order_e = order_e.p; P.order_d = order_d.p;
+        P.enode = enode.p; P.fold = fold.p; P.e11 = e11.p;
         P.pmat = pmat.p; P.pair_ab = pair_ab.p; P.inc = inc.p; P.istart = istart.p; P.node_marg = node_marg.p; P.stats = stats.p;
         P.potential = potential; P.error_flag = engine->error_flag.p;
         P.slow_list = slow_list.p; P.n_slow = n_slow.p; P.n_rep = engine->n_rep;
@@ -1241,8 +1329,8 @@ struct RotamerSidechain : PotentialNode {
         k_rot_prep<<<engine->n_rep, PREP_TPB, smem_prep, s>>>(P);
         engine->mark(s, "rotamer/prep");
         const bool ff1_knots = nka == 15 && nk == 16;   // the PARAM_7A_CUTOFF build of the reference (bead_interaction.h:12-27)
-        if (ff1_knots) k_rot_energy<15, 16><<<dim3(P.n_chunk, persist), EDGE_TPB, smem_edge, s>>>(P, want, engine->n_rep);
-        else k_rot_energy<0, 0><<<dim3(P.n_chunk, persist), EDGE_TPB, smem_edge, s>>>(P, want, engine->n_rep);
+        if (ff1_knots) k_rot_energy<15, 16><<<dim3(edge_split, persist), edge_tpb, smem_edge, s>>>(P, want, engine->n_rep);
+        else k_rot_energy<0, 0><<<dim3(edge_split, persist), edge_tpb, smem_edge, s>>>(P, want, engine->n_rep);
         engine->mark(s, "rotamer/energy");
         if (fast_bp) {
             k_rot_bp2<<<engine->n_rep, BP2_TPB, smem_bp2, s>>>(P, lay2, want);
@@ -1251,8 +1339,8 @@ struct RotamerSidechain : PotentialNode {
             k_rot_bp<<<engine->n_rep, BP_TPB, smem_bp, s>>>(P, want, 0);
         }
         engine->mark(s, "rotamer/bp");
-        if (ff1_knots) k_rot_deriv<15, 16><<<dim3(P.n_chunk, persist), EDGE_TPB, smem_edge, s>>>(P, engine->n_rep);
-        else k_rot_deriv<0, 0><<<dim3(P.n_chunk, persist), EDGE_TPB, smem_edge, s>>>(P, engine->n_rep);
+        if (ff1_knots) k_rot_deriv<15, 16><<<dim3(edge_split, persist), edge_tpb, smem_edge, s>>>(P, engine->n_rep);
+        else k_rot_deriv<0, 0><<<dim3(edge_split, persist), edge_tpb, smem_edge, s>>>(P, engine->n_rep);
         engine->mark(s, "rotamer/deriv");
     }
     bool get_pairlist(int replica, std::vector<int>& i1, std::vector<int>& i2) override { return ig.pairlist(replica, i1, i2); }
