@@ -1,9 +1,10 @@
 """Aggregate an ncu SASS source page by CUDA source line (needs -lineinfo): joins `ncu --page source --csv
 --print-source sass` with `nvdisasm -g` line markers of the same cubin.
-usage: ncu_lines.py <report.ncu-rep> <cubin> <kernel-substring> [top_n]"""
+usage: ncu_lines.py <report.ncu-rep> <cubin> <kernel-substring> [top_n] [nth-match]"""
 import csv, re, subprocess, sys, collections, io
 rep, cubin, kern = sys.argv[1:4]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
+nth = int(sys.argv[5]) if len(sys.argv) > 5 else 0
 dis = subprocess.run(['nvdisasm', '-g', '-c', cubin], capture_output=True, text=True).stdout
 addr2line = {}
 cur = None; inside = False
@@ -19,7 +20,8 @@ out = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '--print-so
 rows = list(csv.reader(io.StringIO(out)))
 # the page holds one section per profiled kernel: pick the one whose 'Kernel Name' row matches
 starts = [i for i, r in enumerate(rows) if r and r[0] == 'Kernel Name']
-sec = next((i for i in starts if kern in rows[i][1]), starts[0] if starts else 0)
+match = [i for i in starts if kern in rows[i][1]]
+sec = match[min(nth, len(match) - 1)] if match else (starts[0] if starts else 0)
 end = next((i for i in starts if i > sec), len(rows))
 rows = rows[sec:end]
 hi = next(i for i, r in enumerate(rows) if r and r[0] == 'Address')

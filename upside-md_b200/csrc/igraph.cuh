@@ -151,39 +151,60 @@ static __global__ void k_cache_check(IGraphSide A, IGraphSide Bs, int two_groups
 // compaction keeps the ascending order); for an asymmetric graph the transposed table is refined in the same launch.
 struct RefineTable { const unsigned short* cand; const int* ccnt; int Kc; unsigned short* nbr; int* cnt; int K; };
 
-// one thread per candidate row; a slice of eight candidates per 16-byte load, no bounds tests (padding entries index the
-// sentinel position, which is never in range); sequential compaction keeps the ascending order
-__device__ __forceinline__ void refine_rows(int r, int nA, const float4* posA, const float4* posB, RefineTable T, float cutoff2,
-                                            int a_is_first, int* error_flag, int t0, int n_thread) {
-    for (int i = t0; i < nA; i += n_thread) {
-        const float4 pi = posA[i];
-        const int c = T.ccnt[size_t(r) * nA + i];
+// One thread per candidate row; a slice of eight candidates per 16-byte load, no bounds tests (padding entries index the
+// sentinel position, which is never in range).  Hits are packed four to a 64-bit register and leave as 8-byte stores, in
+// candidate order (ascending).  The count and the first four slices of a thread's first row are fetched BEFORE the CTA
+// stages positions (RefinePrefetch), so that their latency overlaps the staging and its barrier.
+struct RefineRole {          // which rows of which table this thread refines
+    RefineTable T;
+    int nA, a_is_first, t0, n_thread;
+    const float4 *posA, *posB;
+};
+struct RefinePrefetch { int c; uint4 v[4]; };
+
+__device__ __forceinline__ void refine_prefetch(int r, const RefineRole& R, int i, RefinePrefetch& F) {
+    F.c = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) F.v[q] = make_uint4(0, 0, 0, 0);
+    if (i >= R.nA) return;
+    F.c = R.T.ccnt[size_t(r) * R.nA + i];
+    const uint4* cs = reinterpret_cast<const uint4*>(R.T.cand + size_t(r) * R.T.Kc * R.nA) + i;
+    const int n_slice_max = R.T.Kc >> 3;   // slices past the row's count hold stale entries: loaded, never used
+#pragma unroll
+    for (int q = 0; q < 4; ++q) if (q < n_slice_max) F.v[q] = cs[size_t(q) * R.nA];
+}
+
+__device__ __forceinline__ void refine_rows(int r, const RefineRole& R, float cutoff2, int* error_flag, RefinePrefetch& F) {
+    const RefineTable& T = R.T;
+    const int nA = R.nA;
+    for (int i = R.t0; i < nA; i += R.n_thread) {
+        if (i != R.t0) refine_prefetch(r, R, i, F);
+        const float4 pi = R.posA[i];
+        const int c = F.c;
         const uint4* cs = reinterpret_cast<const uint4*>(T.cand + size_t(r) * T.Kc * nA) + i;
-        unsigned short* row = T.nbr + (size_t(r) * nA + i) * T.K;
+        unsigned short* row = T.nbr + (size_t(r) * nA + i) * T.K;   // 16-byte aligned (K is a multiple of 8)
         int n = 0;
-        const int n_slice = (c + 7) >> 3;
+        const int n_slice = (c + 7) >> 3, last = T.K - 1;
         // slices are fetched four at a time (independent 16-byte loads: one memory round trip per 32 candidates)
         for (int s0 = 0; s0 < n_slice; s0 += 4) {
             uint4 v[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) v[q] = s0 + q < n_slice ? cs[size_t(s0 + q) * nA] : make_uint4(0, 0, 0, 0);
+            for (int q = 0; q < 4; ++q) v[q] = s0 == 0 ? F.v[q] : (s0 + q < n_slice ? cs[size_t(s0 + q) * nA] : make_uint4(0, 0, 0, 0));
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 if (s0 + q >= n_slice) break;
                 const unsigned w[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
-                    const int j = (u & 1) ? int(w[u >> 1] >> 16) : int(w[u >> 1] & 0xffffu);
-                    const float4 pj = posB[j];
-                    // group 1 minus group 2, as in the reference refine step; the squares make the order immaterial
-                    const float dx = a_is_first ? pi.x - pj.x : pj.x - pi.x;
-                    const float dy = a_is_first ? pi.y - pj.y : pj.y - pi.y;
-                    const float dz = a_is_first ? pi.z - pj.z : pj.z - pi.z;
+                    const unsigned j = (u & 1) ? (w[u >> 1] >> 16) : (w[u >> 1] & 0xffffu);
+                    const float4 pj = R.posB[j];
+                    // the reference subtracts group 2 from group 1 (interaction_graph.h:230-232); the squares are the same
+                    // either way, bit for bit
+                    const float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
                     const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-                    if (d2 < cutoff2) {
-                        if (n < T.K) row[n] = (unsigned short)j;
-                        ++n;
-                    }
+                    const bool hit = d2 < cutoff2;
+                    if (hit) row[min(n, last)] = (unsigned short)j;   // predicated store; an overflowing row is reported below
+                    n += hit;
                 }
             }
         }
@@ -198,6 +219,18 @@ __global__ void k_refine(IGraphSide A, IGraphSide Bs, int two_groups, RefineTabl
     const int r = blockIdx.x;
     float4* posA = sm_pos;                                  // [A.n + 1], last = sentinel
     float4* posB = two_groups ? sm_pos + A.n + 1 : sm_pos;  // [Bs.n + 1]
+    // one row per thread where the block is large enough; with two groups the first A.n threads (rounded up to whole
+    // warps) refine table 1 while the others refine the transposed table
+    const int T = blockDim.x;
+    const int split = two_groups ? min(T - 32, (A.n + 31) & ~31) : 0;
+    RefineRole R1{T1, A.n, 1, (int)threadIdx.x, T, posA, posB}, R2{T2, Bs.n, 0, (int)threadIdx.x, T, posB, posA};
+    const bool both = two_groups && split <= 0;      // block too small to split: every thread does both tables in turn
+    if (two_groups && split > 0) {
+        if ((int)threadIdx.x < split) R1.n_thread = split;
+        else { R1 = R2; R1.t0 = threadIdx.x - split; R1.n_thread = T - split; }
+    }
+    RefinePrefetch F;
+    refine_prefetch(r, R1, R1.t0, F);
     const float4 far = make_float4(1e18f, 1e18f, 1e18f, 0.f);
     for (int i = threadIdx.x; i < A.n; i += blockDim.x) {
         const float* p = A.out + (size_t(r) * A.n_node + A.loc[i]) * A.wp;
@@ -212,16 +245,11 @@ __global__ void k_refine(IGraphSide A, IGraphSide Bs, int two_groups, RefineTabl
         if (threadIdx.x == 0) posB[Bs.n] = far;
     }
     __syncthreads();
-    // one row per thread where the block is large enough; with two groups the first A.n threads (rounded up to whole
-    // warps) refine table 1 while the others refine the transposed table
-    const int T = blockDim.x;
-    if (!two_groups) { refine_rows(r, A.n, posA, posB, T1, cutoff2, 1, error_flag, threadIdx.x, T); return; }
-    const int split = min(T - 32, (A.n + 31) & ~31);
-    if (split <= 0) {
-        refine_rows(r, A.n, posA, posB, T1, cutoff2, 1, error_flag, threadIdx.x, T);
-        refine_rows(r, Bs.n, posB, posA, T2, cutoff2, 0, error_flag, threadIdx.x, T);
-    } else if ((int)threadIdx.x < split) refine_rows(r, A.n, posA, posB, T1, cutoff2, 1, error_flag, threadIdx.x, split);
-    else refine_rows(r, Bs.n, posB, posA, T2, cutoff2, 0, error_flag, threadIdx.x - split, T - split);
+    refine_rows(r, R1, cutoff2, error_flag, F);
+    if (both) {
+        refine_prefetch(r, R2, R2.t0, F);
+        refine_rows(r, R2, cutoff2, error_flag, F);
+    }
 }
 
 // ---- row scheduling ---------------------------------------------------------------------------------------

@@ -62,7 +62,7 @@ struct RotamerDev {
     unsigned short* dj;       // [B][cap_e]  partner bead
     int* code;                // [B][cap_e]  where the pair energy goes / which marginal weights its derivative
     float* ss;                // [B][cap_e]  that marginal (written by the BP kernels)
-    unsigned short* lower;    // [B][n_bead] partners with a smaller bead index | bit 15: some of them fold into this bead
+    unsigned short* lower;    // [B][n_bead] first row entry the energy kernel evaluates
     unsigned short* order_e;  // [B][n_bead] rows by falling number of entries the energy kernel evaluates
     unsigned short* order_d;  // [B][n_bead] rows by falling length
     float* enode;             // [B][n_res][6]  1-body energy per (residue, state)
@@ -234,39 +234,58 @@ __global__ void __launch_bounds__(PREP_TPB) k_rot_prep(RotamerDev P) {
         float4* pm4 = reinterpret_cast<float4*>(P.pmat + size_t(r) * P.max_pairs * 36);
         for (int i = tid; i < n_pair * 9; i += PREP_TPB) pm4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    // CSR rows: partner + code per entry; per row the number of lower partners and of entries the energy kernel evaluates
+    // CSR rows: partner + code per entry.  Inside a row the partners below the bead come first, those of them whose energy
+    // folds into this bead last among them, then the partners above in ascending order: the energy kernel evaluates the
+    // contiguous tail that starts at `lower` = (partners below) - (folding partners below).
     unsigned short* dj = P.dj + size_t(r) * P.cap_e;
     int* code = P.code + size_t(r) * P.cap_e;
+    const int gsh = ((tid & 31) / RG) * RG;   // first lane of this lane group inside its warp
     for (int i0 = 0; i0 < nb; i0 += n_grp) {
-        int i = i0 + grp;
+        const int i = i0 + grp;
+        const bool live = i < nb;
+        const int me = live ? rr[i] : 0, A = me >> 4, ra = (me >> 1) & 7;
+        const bool mA = me & 1;
+        const unsigned short* row = nbr + size_t(live ? i : 0) * K;
+        const int c = live ? cnt[i] : 0, base = live ? rs[i] : 0;
+        int cmax = c;   // ballots below need warp-uniform trip counts
+        cmax = max(cmax, __shfl_xor_sync(UB_FULL_MASK, cmax, 8));
+        cmax = max(cmax, __shfl_xor_sync(UB_FULL_MASK, cmax, 16));
         int lo = 0, nfl = 0, nev = 0;
-        if (i < nb) {
-            int me = rr[i], A = me >> 4, ra = (me >> 1) & 7;
-            bool mA = me & 1;
-            const unsigned short* row = nbr + size_t(i) * K;
-            const int c = cnt[i], base = rs[i];
-            for (int k = lane; k < c; k += RG) {
-                const int j = row[k];
-                int other = rr[j], Bq = other >> 4, rb = (other >> 1) & 7;
-                bool mB = other & 1;
-                int cd;
-                if (mA && mB) cd = A < Bq ? slot_of(A, Bq) * 36 + ra * 6 + rb : slot_of(Bq, A) * 36 + rb * 6 + ra;
-                else if (mA) cd = code_node(A * MAXR + ra, true);
-                else if (mB) cd = code_node(Bq * MAXR + rb, false);
-                else cd = CODE_SS;
-                dj[base + k] = (unsigned short)j;
-                code[base + k] = cd;
-                const bool below = j < i;
-                lo += below;
-                nfl += below && mA && !mB;
-                nev += below ? (mA && !mB) : (mA || !mB);   // upper entries of a single-state bead with a multi-state partner are skipped
-            }
+        for (int k = lane; k < c; k += RG) {
+            const int j = row[k];
+            const bool mB = rr[j] & 1, below = j < i;
+            lo += below;
+            nfl += below && mA && !mB;
+            nev += below ? (mA && !mB) : (mA || !mB);   // entries above a single-state bead with a multi-state partner are skipped
         }
 #pragma unroll
         for (int o = RG / 2; o > 0; o >>= 1) {
             lo += __shfl_xor_sync(UB_FULL_MASK, lo, o); nfl += __shfl_xor_sync(UB_FULL_MASK, nfl, o); nev += __shfl_xor_sync(UB_FULL_MASK, nev, o);
         }
-        if (i < nb && lane == 0) { lo_s[i] = (unsigned short)(lo | (nfl ? 0x8000 : 0)); ce_s[i] = (unsigned short)nev; }
+        int run_f = lo - nfl, run_o = 0;
+        for (int k0 = 0; k0 < cmax; k0 += RG) {
+            const int k = k0 + lane;
+            const bool have = k < c;
+            const int j = have ? row[k] : 0;
+            const int other = rr[j], Bq = other >> 4, rb = (other >> 1) & 7;
+            const bool mB = other & 1, below = have && j < i;
+            const bool isf = below && mA && !mB, iso = below && !isf;
+            const unsigned bf = (__ballot_sync(UB_FULL_MASK, isf) >> gsh) & 0xffu, bo = (__ballot_sync(UB_FULL_MASK, iso) >> gsh) & 0xffu;
+            if (have) {
+                int cd;
+                if (mA && mB) cd = A < Bq ? slot_of(A, Bq) * 36 + ra * 6 + rb : slot_of(Bq, A) * 36 + rb * 6 + ra;
+                else if (mA) cd = code_node(A * MAXR + ra, true);
+                else if (mB) cd = code_node(Bq * MAXR + rb, false);
+                else cd = CODE_SS;
+                const unsigned before = (1u << lane) - 1u;
+                const int at = isf ? run_f + __popc(bf & before) : (iso ? run_o + __popc(bo & before) : k);
+                dj[base + at] = (unsigned short)j;
+                code[base + at] = cd;
+            }
+            run_f += __popc(bf);
+            run_o += __popc(bo);
+        }
+        if (live && lane == 0) { lo_s[i] = (unsigned short)(lo - nfl); ce_s[i] = (unsigned short)nev; }
     }
     __syncthreads();
     for (int i = tid; i < nb; i += PREP_TPB) P.lower[size_t(r) * nb + i] = lo_s[i];
@@ -400,16 +419,16 @@ __global__ void __launch_bounds__(EDGE_TPB, 3) k_rot_energy(RotamerDev P, int wa
         const unsigned short* lower = P.lower + size_t(r) * nb;
         float* pmat = P.pmat + size_t(r) * P.max_pairs * 36;
         float e11 = 0.f;
-        for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nb; t += gridDim.x * blockDim.x) {
+        // boustrophedon over the length-sorted rows: a thread's long row of one pass is followed by a short one in the next
+        for (int t0 = 0, pass = 0; t0 < nb; t0 += gridDim.x * blockDim.x, ++pass) {
+            const int tl = blockIdx.x * blockDim.x + threadIdx.x;
+            const int t = t0 + ((pass & 1) ? gridDim.x * blockDim.x - 1 - tl : tl);
+            if (t >= nb) continue;
             const int i = order[t];
             const BeadRec bi = beads[i];
             const int base = rowstart[i], c = rowstart[i + 1] - base;
-            const int lw = lower[i], lo = lw & 0x7fff;
+            const int lo = lower[i];   // first entry to evaluate: folding partners below the bead, then the partners above
             float fold = 0.f;
-            // partners with a smaller index only matter when they have a single state (their energy folds into bead i)
-            if (lw & 0x8000)
-                for (int k = 0; k < lo; ++k)
-                    if (code_is_fold(code[base + k])) fold += pair_term<false, NKA, NK>(P, T, beads[dj[base + k]], bi, nullptr, nullptr);
             for (int k0 = lo; k0 < c; k0 += PF) {
                 int js[PF], cds[PF];
 #pragma unroll
@@ -457,7 +476,11 @@ __global__ void __launch_bounds__(EDGE_TPB, 3) k_rot_deriv(RotamerDev P, int n_r
         const float* ssr = P.ss + size_t(r) * P.cap_e;
         const unsigned short* order = P.order_d + size_t(r) * nb;
         const float* nm = P.node_marg + size_t(r) * P.n_res * MAXR;
-        for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nb; t += gridDim.x * blockDim.x) {
+        // boustrophedon over the length-sorted rows: a thread's long row of one pass is followed by a short one in the next
+        for (int t0 = 0, pass = 0; t0 < nb; t0 += gridDim.x * blockDim.x, ++pass) {
+            const int tl = blockIdx.x * blockDim.x + threadIdx.x;
+            const int t = t0 + ((pass & 1) ? gridDim.x * blockDim.x - 1 - tl : tl);
+            if (t >= nb) continue;
             const int i = order[t];
             const BeadRec bi = beads[i];
             const int base = rowstart[i], c = rowstart[i + 1] - base;
