@@ -205,7 +205,9 @@ def kernel_rooflines(eng, stream, torch):
     group with CUDA events on the engine's stream (after warm-up, mean of 3); the algorithmic flops of SURVEY.md
     section 8(d) are attributed group by group from live counts (edges, BP sweeps, residue-pair classes)."""
     peaks, how = measured_peaks()
-    fp32_peak = 148 * 128 * 2 * peaks.get('sm_max_mhz', 1965.0) * 1e6 / 1e12
+    fp32_nominal = 148 * 128 * 2 * peaks.get('sm_max_mhz', 1965.0) * 1e6 / 1e12
+    from upside_md_b200 import upside_engine as ue
+    fp32_peak, _ = ue.measure_fp32_peak(int(os.environ.get('LOCAL_RANK', 0)))   # FFMA microbenchmark on this GPU (csrc/peaks.cu)
     n = 5
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with torch.cuda.stream(stream):
@@ -253,11 +255,17 @@ def kernel_rooflines(eng, stream, torch):
     table.append(dict(kernel='rotamer prep (k_rot_prep)', ms=acc.get('rotamer/prep', 0.0)))
     top = max(table[:5], key=lambda t: t['ms'])
     flops_total = e_rot * 324 + e_cov * 324 + e_hb * 314 + e_env * 110 + f_bp + 2000 * N_RES
-    traffic = None
+    traffic, ncu = None, None
     tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(top['kernel'])
-    return dict(bound='fp32', achieved=top['achieved_tflops'], peak=fp32_peak, unit='TFLOP/s', frac=top['frac'], traffic=traffic,
+        tj = json.load(open(tpath))
+        for t in table:
+            if t['kernel'] in tj:
+                t['ncu'] = tj[t['kernel']]
+        ncu = tj.get(top['kernel'])
+        traffic = ncu and ncu.get('dram_bytes_per_launch')
+    return dict(bound='fp32', achieved=top['achieved_tflops'], peak=fp32_peak, unit='TFLOP/s', frac=top['frac'], traffic=traffic, ncu=ncu,
+                peak_nominal=fp32_nominal,
                 kernel=top['kernel'], ms_per_launch=top['ms'], algorithmic_flops_per_replica=top['algorithmic_flops_per_replica'],
                 whole_evaluation=dict(ms=ms_eval, algorithmic_flops_per_replica=flops_total,
                                       achieved_tflops=flops_total * eng.n_replica / (ms_eval * 1e-3) / 1e12,
@@ -266,8 +274,10 @@ def kernel_rooflines(eng, stream, torch):
                 kernels=table,
                 counts=dict(rotamer_edges=e_rot, coverage_edges=e_cov, env_edges=e_env, hbond_edges=e_hb, bp_sweeps=sweeps, bp_pairs=pairs,
                             bp_pairs_6x6=n66, bp_pairs_3x6=n36),
-                peak_source='FP32 FMA pipe: 148 SM x 128 lanes x 2 x sm_max_mhz (%s clocks); MEASURED_PEAKS.json has no FP32 entry, '
-                            'the path has no dense contraction and moves ~1.4 TB/s of HBM (profiles/)' % how)
+                peak_source='FP32 FMA pipe measured live by an FFMA microbenchmark (ub_measure_fp32_peak, csrc/peaks.cu); nominal = 148 SM x '
+                            '128 lanes x 2 x sm_max_mhz (%s clocks).  MEASURED_PEAKS.json has no FP32 entry; the path has no dense '
+                            'contraction and moves ~1.5 TB/s of HBM (profiles/).  `traffic` and `ncu` come from profiles/traffic.json '
+                            '(ncu --set full of the same workload), not from this run' % how)
 
 
 def reference_arm(args):

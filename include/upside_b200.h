@@ -111,6 +111,10 @@ int ub_profile_eval(UbEngine* e, int max_entry, char* labels, int label_len, flo
 /* known-answer access to the device RNG (src/random.h:19-66): threefry bits, normal3 and u01(word0) */
 int ub_rng_probe(uint32_t seed, uint32_t stream, uint32_t atom, uint64_t timestep, uint32_t* bits4, float* normal3_u01);
 
+/* FP32 FMA throughput this GPU sustains (independent FFMA chains on every SM, CUDA-event timed, best of 4 after warm-up):
+ * the measured denominator of the FP32 roofline bench.py reports (MEASURED_PEAKS.json holds only HBM and bf16 numbers). */
+int ub_measure_fp32_peak(int device, float* tflops, float* sm_mhz_nominal);
+
 #ifdef __cplusplus
 }
 #endif

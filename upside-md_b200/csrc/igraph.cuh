@@ -222,7 +222,7 @@ __global__ void k_refine(IGraphSide A, IGraphSide Bs, int two_groups, RefineTabl
     // one row per thread where the block is large enough; with two groups the first A.n threads (rounded up to whole
     // warps) refine table 1 while the others refine the transposed table
     const int T = blockDim.x;
-    const int split = two_groups ? min(T - 32, (A.n + 31) & ~31) : 0;
+    const int split = two_groups ? max(32, min(T - 32, ((T * A.n / (A.n + Bs.n)) + 16) & ~31)) : 0;   // threads in proportion to rows
     RefineRole R1{T1, A.n, 1, (int)threadIdx.x, T, posA, posB}, R2{T2, Bs.n, 0, (int)threadIdx.x, T, posB, posA};
     const bool both = two_groups && split <= 0;      // block too small to split: every thread does both tables in turn
     if (two_groups && split > 0) {

@@ -76,6 +76,7 @@ def lib():
     L.ub_stream.argtypes = [ct.c_void_p]
     L.ub_launches_per_eval.argtypes = [ct.c_void_p]
     L.ub_profile_eval.argtypes = [ct.c_void_p, ct.c_int, ct.c_char_p, ct.c_int, _fp, _ip]
+    L.ub_measure_fp32_peak.argtypes = [ct.c_int, _fp, _fp]
     L.ub_rng_probe.argtypes = [ct.c_uint32, ct.c_uint32, ct.c_uint32, ct.c_uint64, ct.POINTER(ct.c_uint32), _fp]
     L.upside_main.argtypes = [ct.c_int, ct.POINTER(ct.c_char_p), ct.c_int]
     L.ub_md_init_seeds.argtypes = [ct.c_void_p, ct.POINTER(ct.c_uint32), _fp, ct.c_float, ct.c_float, ct.c_int]
@@ -370,6 +371,13 @@ class BatchEngine(object):
 
     def launches_per_eval(self):
         return self.L.ub_launches_per_eval(self.e)
+
+
+def measure_fp32_peak(device=0):
+    """TFLOP/s of the FP32 FMA pipe measured on `device` (csrc/peaks.cu), and the nominal SM clock in MHz"""
+    tf, mhz = np.zeros(1, dtype='f4'), np.zeros(1, dtype='f4')
+    if lib().ub_measure_fp32_peak(int(device), _f(tf), _f(mhz)): raise _err('measure_fp32_peak')
+    return float(tf[0]), float(mhz[0])
 
 
 def rng_probe(seed, stream, atom, timestep):
