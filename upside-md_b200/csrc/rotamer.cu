@@ -28,7 +28,6 @@ constexpr int MAXR = 6;            // most rotamer states per residue (UPPER_ROT
 constexpr int PREP_TPB = 256;
 constexpr int EDGE_TPB = 256;
 constexpr int BP_TPB = 384;
-constexpr int RG = 8;              // lanes per bead row
 constexpr int MAX_PROB_NODES = 4;
 constexpr int CODE_SS = INT_MIN;   // (single, single)
 // Entry codes.  code >= 0: index into the replica's pair-matrix array (slot*36 + a*6 + b).  Otherwise, unless CODE_SS,
@@ -137,22 +136,35 @@ __global__ void __launch_bounds__(PREP_TPB) k_rot_prep(RotamerDev P) {
         rr[i] = (A << 4) | (ra << 1) | (P.res_nrot[A] > 1 ? 1 : 0);
     }
     __syncthreads();
-    const int grp = tid / RG, lane = tid % RG, n_grp = PREP_TPB / RG;
-    for (int i0 = 0; i0 < nb; i0 += n_grp) {   // RG lanes per bead row: adjacency bits
-        int i = i0 + grp;
-        if (i < nb) {
-            const unsigned short* row = nbr + size_t(i) * K;
-            int c = cnt[i], me = rr[i];
-            for (int k = lane; k < c; k += RG) {
-                int other = rr[row[k]];
-                if (me & other & 1) {
+    // Pass 1, one thread per bead row (16-byte loads: eight partners each): residue adjacency bits; the number of partners
+    // below the bead, how many of those fold into it, and how many entries the energy kernel will evaluate.
+    for (int i = tid; i < nb; i += PREP_TPB) {
+        const uint4* row4 = reinterpret_cast<const uint4*>(nbr + size_t(i) * K);   // rows are 16-byte aligned (K % 8 == 0)
+        const int c = cnt[i], me = rr[i];
+        const bool mA = me & 1;
+        int lo = 0, nfl = 0, nev = 0;
+        for (int k0 = 0; k0 < c; k0 += 8) {
+            const uint4 v = row4[k0 >> 3];
+            const unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                if (k0 + u >= c) break;
+                const int j = (u & 1) ? int(w[u >> 1] >> 16) : int(w[u >> 1] & 0xffffu);
+                const int other = rr[j];
+                const bool mB = other & 1, below = j < i;
+                if (mA && mB) {
                     // both directions, so that the adjacency stays symmetric even if a row was truncated by a capacity
                     // overflow (reported through error_flag): every index derived below relies on that symmetry
                     atomicOr(&bitmap[(me >> 4) * nW + (other >> 9)], 1u << ((other >> 4) & 31));
                     atomicOr(&bitmap[(other >> 4) * nW + (me >> 9)], 1u << ((me >> 4) & 31));
                 }
+                lo += below;
+                nfl += below && mA && !mB;
+                nev += below ? (mA && !mB) : (mA || !mB);   // entries above a single-state bead with a multi-state partner are skipped
             }
         }
+        lo_s[i] = (unsigned short)(lo - nfl);
+        ce_s[i] = (unsigned short)nev;
     }
     scan_row_lengths(nb, [&](int i) { return cnt[i]; }, rs, wtot);   // (ends with a barrier: the bitmap is complete too)
     // Per residue: running popcounts of its adjacency row (wpre), degree, and the number of neighbours below itself.  With
@@ -239,53 +251,31 @@ __global__ void __launch_bounds__(PREP_TPB) k_rot_prep(RotamerDev P) {
     // contiguous tail that starts at `lower` = (partners below) - (folding partners below).
     unsigned short* dj = P.dj + size_t(r) * P.cap_e;
     int* code = P.code + size_t(r) * P.cap_e;
-    const int gsh = ((tid & 31) / RG) * RG;   // first lane of this lane group inside its warp
-    for (int i0 = 0; i0 < nb; i0 += n_grp) {
-        const int i = i0 + grp;
-        const bool live = i < nb;
-        const int me = live ? rr[i] : 0, A = me >> 4, ra = (me >> 1) & 7;
+    for (int i = tid; i < nb; i += PREP_TPB) {   // pass 2, one thread per row: place the entries
+        const uint4* row4 = reinterpret_cast<const uint4*>(nbr + size_t(i) * K);
+        const int c = cnt[i], base = rs[i], me = rr[i], A = me >> 4, ra = (me >> 1) & 7;
         const bool mA = me & 1;
-        const unsigned short* row = nbr + size_t(live ? i : 0) * K;
-        const int c = live ? cnt[i] : 0, base = live ? rs[i] : 0;
-        int cmax = c;   // ballots below need warp-uniform trip counts
-        cmax = max(cmax, __shfl_xor_sync(UB_FULL_MASK, cmax, 8));
-        cmax = max(cmax, __shfl_xor_sync(UB_FULL_MASK, cmax, 16));
-        int lo = 0, nfl = 0, nev = 0;
-        for (int k = lane; k < c; k += RG) {
-            const int j = row[k];
-            const bool mB = rr[j] & 1, below = j < i;
-            lo += below;
-            nfl += below && mA && !mB;
-            nev += below ? (mA && !mB) : (mA || !mB);   // entries above a single-state bead with a multi-state partner are skipped
-        }
+        int run_f = lo_s[i], run_o = 0;   // next slot of a folding / other partner below the bead
+        for (int k0 = 0; k0 < c; k0 += 8) {
+            const uint4 v = row4[k0 >> 3];
+            const unsigned w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-        for (int o = RG / 2; o > 0; o >>= 1) {
-            lo += __shfl_xor_sync(UB_FULL_MASK, lo, o); nfl += __shfl_xor_sync(UB_FULL_MASK, nfl, o); nev += __shfl_xor_sync(UB_FULL_MASK, nev, o);
-        }
-        int run_f = lo - nfl, run_o = 0;
-        for (int k0 = 0; k0 < cmax; k0 += RG) {
-            const int k = k0 + lane;
-            const bool have = k < c;
-            const int j = have ? row[k] : 0;
-            const int other = rr[j], Bq = other >> 4, rb = (other >> 1) & 7;
-            const bool mB = other & 1, below = have && j < i;
-            const bool isf = below && mA && !mB, iso = below && !isf;
-            const unsigned bf = (__ballot_sync(UB_FULL_MASK, isf) >> gsh) & 0xffu, bo = (__ballot_sync(UB_FULL_MASK, iso) >> gsh) & 0xffu;
-            if (have) {
+            for (int u = 0; u < 8; ++u) {
+                const int k = k0 + u;
+                if (k >= c) break;
+                const int j = (u & 1) ? int(w[u >> 1] >> 16) : int(w[u >> 1] & 0xffffu);
+                const int other = rr[j], Bq = other >> 4, rb = (other >> 1) & 7;
+                const bool mB = other & 1, below = j < i;
                 int cd;
                 if (mA && mB) cd = A < Bq ? slot_of(A, Bq) * 36 + ra * 6 + rb : slot_of(Bq, A) * 36 + rb * 6 + ra;
                 else if (mA) cd = code_node(A * MAXR + ra, true);
                 else if (mB) cd = code_node(Bq * MAXR + rb, false);
                 else cd = CODE_SS;
-                const unsigned before = (1u << lane) - 1u;
-                const int at = isf ? run_f + __popc(bf & before) : (iso ? run_o + __popc(bo & before) : k);
+                const int at = !below ? k : ((mA && !mB) ? run_f++ : run_o++);
                 dj[base + at] = (unsigned short)j;
                 code[base + at] = cd;
             }
-            run_f += __popc(bf);
-            run_o += __popc(bo);
         }
-        if (live && lane == 0) { lo_s[i] = (unsigned short)(lo - nfl); ce_s[i] = (unsigned short)nev; }
     }
     __syncthreads();
     for (int i = tid; i < nb; i += PREP_TPB) P.lower[size_t(r) * nb + i] = lo_s[i];
