@@ -141,6 +141,14 @@ def compare_engines(cfg, pos, verbose=True):
         mr = ref.rotamer_bead_marginals()
         rep['marginal_maxabs'] = float(np.abs(mg - mr).max())
         rep['bp_stats'] = (be.get_value_by_name('rotamer', 'solve_stats', r).tolist(), ref.rotamer_solve_stats())
+        # tooling accessors of the rotamer node (reference rotamer.cpp:675-773)
+        n_node = int(ref.get_value_by_name('rotamer', 'n_node', 1)[0])
+        n_prob = len(h5lite.load(cfg)['input/potential/rotamer'].attrs['arguments']) - 1
+        rep['accessors'] = {}
+        for nm, n in (('rotamer_1body_energy', n_node * n_prob), ('node_energy', n_node * 6)):
+            a, b = be.get_value_by_name('rotamer', nm, r), ref.get_value_by_name('rotamer', nm, n)
+            rep['accessors'][nm] = (a.shape == b.shape, float(np.abs(a - b).max()) if a.shape == b.shape else np.inf,
+                                    float(np.abs(b[b < 1e4]).max()))
         report.append(rep)
         if verbose:
             print_report(rep)

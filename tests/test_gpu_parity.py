@@ -30,6 +30,8 @@ def _check_report(rep):
             # rounding, so a pair sitting exactly on the cutoff may flip; such edges must be on the cutoff.
             assert d['exact_given_same_coords'], (name, d)
             assert d['identical'] or d['boundary_gap'] < 2e-4, (name, d)
+        for name, (same_shape, diff, scale) in r.get('accessors', {}).items():
+            assert same_shape and diff <= 2e-3 * max(1.0, scale), (name, diff, scale)
         for name, d in r['nodes'].items():
             if 'pot' in d:
                 a, b = d['pot']

@@ -73,6 +73,7 @@ struct RotamerDev {
     int* istart;              // [B][n_res+1]
     float* node_marg;         // [B][n_res][6]
     int* stats;               // [B][4]: n_iter, n_pair, converged, -
+    int* n_bad;               // [B] solves that hit max_iter without converging (n_bad_solve, rotamer.cpp:604,785)
     int* slow_list;           // [B] replicas the fast BP kernel declined
     int* n_slow;              // [1] (reset by k_rot_prep)
     int n_rep;
@@ -726,6 +727,7 @@ __device__ void bp_solve_generic(const RotamerDev& P, int want_pot, int r, float
     if (tid == 0) {
         int* st = P.stats + size_t(r) * 4;
         st[0] = iter; st[2] = max_dev <= P.tol;
+        if (!(max_dev <= P.tol)) P.n_bad[r] += 1;
     }
     // ---- marginals (and Bethe free energy) ----------------------------------------------------------------------------------
     float en = 0.f;
@@ -1082,7 +1084,7 @@ __global__ void __launch_bounds__(BP2_TPB, 3) k_rot_bp2(RotamerDev P, Bp2Lay L, 
         }
         unconverged = __syncthreads_or(dev > P.tol);
     }
-    if (tid == 0) { st[0] = iter; st[2] = !unconverged; st[3] = n66 | (n36 << 16); }   // st[3]: class counts for the flop audit
+    if (tid == 0) { st[0] = iter; st[2] = !unconverged; st[3] = n66 | (n36 << 16); if (unconverged) P.n_bad[r] += 1; }   // st[3]: class counts for the flop audit
 
     // ---- marginals (and Bethe free energy) ----------------------------------------------------------------------------------
     float en = 0.f;
@@ -1140,7 +1142,7 @@ struct RotamerSidechain : PotentialNode {
     size_t smem_prep = 0, smem_edge = 0, smem_bp = 0, smem_bp2 = 0;
     Bp2Lay lay2{0, 0, 0};
     bool fast_bp = false;
-    DevBuf<int> slow_list, n_slow;
+    DevBuf<int> slow_list, n_slow, n_bad;
 
     RotamerSidechain(Engine&, const h5l::Node& g, const ArgList& args)
         : prob_nodes(args.begin() + 1, args.end()), ig(h5_child(g, "pair_interaction"), true, EXCL_ROTAMER, 6, 6, args[0], nullptr) {
@@ -1255,6 +1257,7 @@ struct RotamerSidechain : PotentialNode {
         UB_CUDA(cudaFuncSetAttribute(k_rot_bp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bp));
         plan_fast_bp(device_smem);
         slow_list.alloc(B);
+        n_bad.upload(std::vector<int>(B, 0));
         n_slow.alloc(1);
         pmat.alloc(B * max_pairs * 36);
         pair_ab.alloc(B * max_pairs * 2);
@@ -1328,7 +1331,7 @@ struct RotamerSidechain : PotentialNode {
         P.enode = enode.p; P.fold = fold.p; P.e11 = e11.p;
         P.pmat = pmat.p; P.pair_ab = pair_ab.p; P.inc = inc.p; P.istart = istart.p; P.node_marg = node_marg.p; P.stats = stats.p;
         P.potential = potential; P.error_flag = engine->error_flag.p;
-        P.slow_list = slow_list.p; P.n_slow = n_slow.p; P.n_rep = engine->n_rep;
+        P.slow_list = slow_list.p; P.n_slow = n_slow.p; P.n_bad = n_bad.p; P.n_rep = engine->n_rep;
         return P;
     }
     void compute_value(cudaStream_t s, ComputeMode mode) override {
@@ -1376,6 +1379,57 @@ struct RotamerSidechain : PotentialNode {
             std::vector<int> st(4);
             UB_CUDA(cudaMemcpy(st.data(), stats.p + size_t(replica) * 4, 4 * sizeof(int), cudaMemcpyDeviceToHost));
             return {float(st[0]), float(st[1]), float(st[2]), float(st[3] & 0xffff), float((st[3] >> 16) & 0xffff)};
+        }
+        if (nm == "read n_bad_solve" || nm == "read n_bad_solve and reset") {   // rotamer.cpp:764-770
+            int v = 0;
+            UB_CUDA(cudaMemcpy(&v, n_bad.p + replica, sizeof(int), cudaMemcpyDeviceToHost));
+            if (nm != "read n_bad_solve") UB_CUDA(cudaMemset(n_bad.p + replica, 0, sizeof(int)));
+            return {float(v)};
+        }
+        // residues in the reference's reporting order: grouped by state count (1, 3, 6), inside a group by the index the
+        // bead ids carry (nodes1/nodes3/nodes6, rotamer.cpp:695-707); arrange_energies (:929-955) lists them in order of
+        // first appearance instead
+        auto download = [&](const float* p, size_t n) {
+            std::vector<float> v(n);
+            UB_CUDA(cudaMemcpy(v.data(), p, n * sizeof(float), cudaMemcpyDeviceToHost));
+            return v;
+        };
+        if (nm == "rotamer_1body_energy") {   // marginal-weighted 1-body energy per residue and probability node (:680-691,904-927)
+            std::vector<float> nmg = download(node_marg.p + size_t(replica) * n_res * MAXR, size_t(n_res) * MAXR);
+            const int n_prob = (int)prob_nodes.size();
+            std::vector<float> out(size_t(n_res) * n_prob, 0.f);
+            for (int p = 0; p < n_prob; ++p) {
+                CoordNode* pn = prob_nodes[p];
+                std::vector<float> o = download(pn->output + size_t(replica) * pn->stride(), pn->stride());
+                for (int b = 0; b < ig.n1; ++b)
+                    out[size_t(bead_res[b]) * n_prob + p] += nmg[bead_res[b] * MAXR + bead_rot[b]] * o[size_t(ig.loc1[b]) * pn->wp];
+            }
+            return out;
+        }
+        if (nm == "node_energy") {   // -log(prob) per (node, state), 1e5 for absent states (:698-711)
+            std::vector<float> en = download(enode.p + size_t(replica) * n_res * MAXR, size_t(n_res) * MAXR);
+            std::vector<float> fo = download(fold.p + size_t(replica) * ig.n1, ig.n1);
+            std::vector<float> tot(en);
+            std::vector<float> offs(n_res, 0.f);
+            for (int A = 0; A < n_res; ++A) {
+                float m = en[A * MAXR];
+                for (int a = 1; a < res_nrot[A]; ++a) m = std::min(m, en[A * MAXR + a]);
+                offs[A] = m;
+            }
+            for (int b = 0; b < ig.n1; ++b) tot[bead_res[b] * MAXR + bead_rot[b]] += fo[b];
+            std::vector<int> order;
+            for (int n_rot : {1, 3, 6}) {
+                std::vector<std::pair<int, int>> grp;
+                for (int A = 0; A < n_res; ++A) if (res_nrot[A] == n_rot) grp.push_back({res_key[A] >> 4, A});
+                std::sort(grp.begin(), grp.end());
+                for (auto& g : grp) order.push_back(g.second);
+            }
+            std::vector<float> out(order.size() * 6, 1e5f);
+            for (size_t nn = 0; nn < order.size(); ++nn) {
+                int A = order[nn];
+                for (int a = 0; a < res_nrot[A]; ++a) out[nn * 6 + a] = tot[A * MAXR + a] - offs[A];
+            }
+            return out;
         }
         throw std::string("Value ") + log_name + " not implemented";
     }
