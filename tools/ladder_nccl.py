@@ -13,7 +13,7 @@ from upside_md_b200 import upside_engine as ue, replica_exchange as rx, h5lite, 
 
 CFG = os.path.join(ROOT, 'configs', 'config4_150res.up')
 N_RUNG, INTERVAL, SEED = 48, 10, 42
-rounds = int(sys.argv[1]) if len(sys.argv) > 1 else 60
+rounds = int(sys.argv[1]) if len(sys.argv) > 1 else 200
 rank, world, local = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1)), int(os.environ.get('LOCAL_RANK', 0))
 group = None
 if world > 1:
@@ -30,6 +30,7 @@ be.set_pos(pos)
 be.md_init_seeds(T[lo:hi], SEED + np.arange(lo, hi))          # seed of system ns = base + ns (main.cpp:459)
 be.md_run(30)                                                 # relax the random starts
 lad = rx.ShardedLadder(rx.batch_engine_adapter(be), T, sets, seed=SEED, group=group, device=torch.device('cuda', local))
+lad.run(2 * INTERVAL, INTERVAL)                                # untimed: NCCL opens its all-gather and send/recv channels lazily
 torch.cuda.synchronize()
 if world > 1: dist.barrier()
 t0 = time.perf_counter()
