@@ -818,60 +818,6 @@ __device__ __forceinline__ void bp2_pair(const float* __restrict__ bel, int nRp,
     for (int b = 0; b < NB; ++b) msg[(6 + b) * SP + p] = m2[b] * i2;
 }
 
-// The same update with the new messages returned in o[0..NA) (to the first residue) and o[NA..NA+NB) (to the second)
-// instead of stored: the caller stores after a __syncwarp, because a 6x6 pair is shared by two lanes (bp2_half66).
-template <int NA, int NB>
-__device__ __forceinline__ void bp2_pair_calc(const float* __restrict__ bel, int nRp, int F, int S, const float* __restrict__ msg, int SP,
-                                              int p, const float* __restrict__ Pc, int nc, int q, float* __restrict__ o) {
-    float v1[NA], v2[NB], m1[NA], m2[NB];
-#pragma unroll
-    for (int a = 0; a < NA; ++a) { v1[a] = __fdividef(bel[a * nRp + F], 1e-10f + msg[a * SP + p]); m1[a] = 0.f; }
-#pragma unroll
-    for (int b = 0; b < NB; ++b) { v2[b] = __fdividef(bel[b * nRp + S], 1e-10f + msg[(6 + b) * SP + p]); m2[b] = 0.f; }
-#pragma unroll
-    for (int a = 0; a < NA; ++a)
-#pragma unroll
-        for (int b = 0; b < NB; ++b) {
-            float pr = Pc[(a * NB + b) * nc + q];
-            m1[a] = fmaf(pr, v2[b], m1[a]);   // apply_left : message to the first residue
-            m2[b] = fmaf(v1[a], pr, m2[b]);   // apply_right: message to the second residue
-        }
-    float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-    for (int a = 0; a < NA; ++a) s1 += m1[a];
-#pragma unroll
-    for (int b = 0; b < NB; ++b) s2 += m2[b];
-    const float i1 = __fdividef(1.f, s1), i2 = __fdividef(1.f, s2);
-#pragma unroll
-    for (int a = 0; a < NA; ++a) o[a] = m1[a] * i1;
-#pragma unroll
-    for (int b = 0; b < NB; ++b) o[NA + b] = m2[b] * i2;
-}
-// One direction of a 6x6 pair: dir 0 = message to the first residue (rows of the pair matrix against the second residue's
-// cavity belief), dir 1 = message to the second (columns against the first residue's).  Same operations in the same order
-// as bp2_pair_calc<6,6> computes for that direction, so the split changes no bit; a 6x6 pair then costs a lane no more than
-// a 3x6 pair and the message phase is balanced over the CTA.  Rin/msg_in: the residue and message column that feed it.
-__device__ __forceinline__ void bp2_half66(const float* __restrict__ bel, int nRp, int Rin, const float* __restrict__ msg_in, int SP,
-                                           const float* __restrict__ Pq, int nc, int dir, float* __restrict__ o) {
-    float v[6], m[6];
-#pragma unroll
-    for (int y = 0; y < 6; ++y) v[y] = __fdividef(bel[y * nRp + Rin], 1e-10f + msg_in[y * SP]);
-    const int sx = (dir ? 1 : 6) * nc, sy = (dir ? 6 : 1) * nc;
-#pragma unroll
-    for (int x = 0; x < 6; ++x) {
-        float acc = 0.f;
-#pragma unroll
-        for (int y = 0; y < 6; ++y) acc = fmaf(Pq[x * sx + y * sy], v[y], acc);
-        m[x] = acc;
-    }
-    float s = 0.f;
-#pragma unroll
-    for (int x = 0; x < 6; ++x) s += m[x];
-    const float inv = __fdividef(1.f, s);
-#pragma unroll
-    for (int x = 0; x < 6; ++x) o[x] = m[x] * inv;
-}
-
 // pair marginal (rotamer.cpp:403-429), in place of the pair's probability matrix in shared memory, plus its Bethe term
 // (:431-451)
 template <int NA, int NB>
@@ -1097,39 +1043,12 @@ __global__ void __launch_bounds__(BP2_TPB, 3) k_rot_bp2(RotamerDev P, Bp2Lay L, 
     __syncthreads();
 
     // ---- sweeps -------------------------------------------------------------------------------------------------------------
-    // Message phase work items: every 6x6 pair is split into its two directions (two adjacent lanes), so that no lane carries
-    // more than a 3x6 pair; items = [2*n66 halves | n36 | n33].  The two lanes of a 6x6 pair read the message the other one
-    // replaces, hence compute -> __syncwarp -> store.
-    const int n_item = 2 * n66 + n36 + n33;
     auto messages = [&]() {
-        for (int w0 = 0; w0 < n_item; w0 += BP2_TPB) {
-            const int w = w0 + tid;
-            float o[9];
-            int kind = -1, p = 0;   // 0/1: 6x6 half toward the first/second residue, 2: 3x6, 3: 3x3
-            if (w < n_item) {
-                if (w < 2 * n66) { p = w >> 1; kind = w & 1; }
-                else { p = w - n66; kind = p < n66 + n36 ? 2 : 3; }
-                const int F = fs[2 * p] & 0x7fff, S = fs[2 * p + 1];
-                if (kind < 2) bp2_half66(bel, nRp, kind ? F : S, msg + (kind ? 0 : 6 * SP) + p, SP, P66 + p, n66, kind, o);
-                else if (kind == 2) bp2_pair_calc<3, 6>(bel, nRp, F, S, msg, SP, p, P36, n36, p - n66, o);
-                else bp2_pair_calc<3, 3>(bel, nRp, F, S, msg, SP, p, P33, n33, p - n66 - n36, o);
-            }
-            __syncwarp();
-            if (kind == 0 || kind == 1) {
-                float* dst = msg + (kind ? 6 * SP : 0) + p;
-#pragma unroll
-                for (int x = 0; x < 6; ++x) dst[x * SP] = o[x];
-            } else if (kind == 2) {
-#pragma unroll
-                for (int a = 0; a < 3; ++a) msg[a * SP + p] = o[a];
-#pragma unroll
-                for (int b = 0; b < 6; ++b) msg[(6 + b) * SP + p] = o[3 + b];
-            } else if (kind == 3) {
-#pragma unroll
-                for (int a = 0; a < 3; ++a) msg[a * SP + p] = o[a];
-#pragma unroll
-                for (int b = 0; b < 3; ++b) msg[(6 + b) * SP + p] = o[3 + b];
-            }
+        for (int p = tid; p < n_pair; p += BP2_TPB) {
+            const int F = fs[2 * p] & 0x7fff, S = fs[2 * p + 1];
+            if (p < n66) bp2_pair<6, 6>(bel, nRp, F, S, msg, SP, p, P66, n66, p);
+            else if (p < n66 + n36) bp2_pair<3, 6>(bel, nRp, F, S, msg, SP, p, P36, n36, p - n66);
+            else bp2_pair<3, 3>(bel, nRp, F, S, msg, SP, p, P33, n33, p - n66 - n36);
         }
     };
     const int n_multi = n_multi_s;
