@@ -19,6 +19,8 @@ CONFIGS = {
     3: os.path.join(ROOT, 'configs', 'config3_100res.up'),
     4: os.path.join(ROOT, 'configs', 'config4_150res.up'),
     5: os.path.join(ROOT, 'configs', 'config5_300res.up'),
+    6: os.path.join(ROOT, 'configs', 'config6_restraints_20res.up'),
+    7: os.path.join(ROOT, 'configs', 'config7_concat_20res.up'),       # config 1 + slice/constant/concat -> tether springs   # config 1 + restraint / plumbing nodes (tools/make_restraint_config.py)
 }
 PAIRLIST_NODES = ['rotamer', 'hbond_coverage', 'hbond_coverage_hydrophobe', 'environment_coverage', 'protein_hbond',
                   'backbone_pairs']

@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 import parity
-from parity import ue
+from parity import ue, h5lite
 from oracle import ref_engine, restate
 
 pytestmark = pytest.mark.gpu
@@ -42,7 +42,7 @@ def _check_report(rep):
 
 
 @pytest.mark.skipif(not ref_engine.available('pinned'), reason='oracle/_ref not shipped')
-@pytest.mark.parametrize('cid,n_rep', [(1, 4), (2, 2), (3, 3), (4, 2), (5, 2)])
+@pytest.mark.parametrize('cid,n_rep', [(1, 4), (2, 2), (3, 3), (4, 2), (5, 2), (6, 3)])
 def test_every_node_matches_oracle(cid, n_rep):
     cfg = parity.CONFIGS[cid]
     pos = parity.test_positions(cfg, n_rep + 1)[1:]     # relaxed structures (see DESIGN.md on /input/pos itself)
@@ -99,6 +99,23 @@ def test_device_rng_known_answers():
         assert u == pytest.approx(float(restate.u01(int(bits[0]))), rel=1e-7)
 
 
+@pytest.mark.skipif(not ref_engine.available('pinned'), reason='oracle/_ref not shipped')
+def test_restraint_nodes_trajectory_and_afm_clock():
+    """config 6 (restraints, AFM with a moving tip, slice): 10 MD rounds from the same start with the same seeds on both
+    engines; the AFM tip advances once per DerivMode evaluation on both sides (bonds.cpp:151-154)"""
+    cfg = parity.CONFIGS[6]
+    pos = parity.test_positions(cfg, 3)[1:]
+    ref = ref_engine.md_run(cfg, pos, 0.8, 10, seed=42, n_thread=2, flavour='pinned')
+    be = ue.BatchEngine(cfg, len(pos))
+    be.set_pos(pos); be.md_init(0.8, seed=42); be.md_run(10)
+    assert np.abs(be.get_pos() - ref['pos']).max() <= 5e-3
+    t = be.get_value_by_name('AFM', 'time_estimate', 0)
+    assert t[0] == pytest.approx(0.009 * 3 * 30, rel=1e-5)            # 30 DerivMode evaluations
+    tip = be.get_value_by_name('AFM', 'tip_pos', 0).reshape(-1, 3)
+    np.testing.assert_allclose(tip[0], [-10. - 0.01 * t[0], 0., 0.], rtol=1e-5, atol=1e-5)
+    be.close()
+
+
 @pytest.mark.parametrize('cid', [1, 3])
 def test_trajectory_matches_golden(cid):
     g = np.load(os.path.join(GOLD, 'config%d.npz' % cid))
@@ -109,6 +126,38 @@ def test_trajectory_matches_golden(cid):
     be.set_pos(g['pos']); be.md_init(0.8, seed=42); be.md_run(10)       # 30 timesteps
     assert np.abs(be.get_pos() - g['traj_pos_10']).max() <= 5e-3
     be.close()
+
+
+def test_constant_and_concat_nodes():
+    """slice + constant -> concat -> springs (config 7): the tether energy is what numpy computes from the positions, and
+    dV/dx agrees with central differences (the reference cannot construct its Concat node)"""
+    cfg = parity.CONFIGS[7]
+    g = h5lite.load(cfg)['input/potential']
+    p0 = parity.initial_pos(cfg)
+    pts = np.concatenate((p0[np.array(g['slice_some/id'].data)], np.array(g['constant_anchor/value'].data, dtype='f4')))
+    ids, eq, k = (np.array(g['dist_spring_tethers/' + n].data) for n in ('id', 'equil_dist', 'spring_const'))
+    d = np.sqrt(((pts[ids[:, 0]] - pts[ids[:, 1]]) ** 2).sum(axis=1))
+    be = ue.BatchEngine(cfg, 1)
+    be.evaluate(p0[None])
+    assert float(be.node_potential('dist_spring_tethers')[0]) == pytest.approx(float((0.5 * k * (d - eq) ** 2).sum()), rel=1e-5)
+    np.testing.assert_allclose(be.get_output('concat_points', 0), pts, rtol=1e-6, atol=1e-6)
+    be.close()
+    atoms = np.array(g['slice_some/id'].data)
+    idx = np.concatenate([3 * atoms + c for c in range(3)])
+    eps = 2e-3
+    pos = np.repeat(p0.reshape(1, -1), 2 * len(idx), 0)
+    for kk, i in enumerate(idx):
+        pos[2 * kk, i] += eps
+        pos[2 * kk + 1, i] -= eps
+    be = ue.BatchEngine(cfg, len(pos))
+    be.evaluate(pos.reshape(len(pos), -1, 3))
+    tether = be.node_potential('dist_spring_tethers')
+    _, dv = ue.BatchEngine(cfg, 1).evaluate(p0[None])
+    be.close()
+    # derivative of the tether term alone: total derivative minus that of plain config 1 (same nodes otherwise)
+    _, dv1 = ue.BatchEngine(parity.CONFIGS[1], 1).evaluate(p0[None])
+    fd = (tether[0::2] - tether[1::2]) / (2 * eps)
+    np.testing.assert_allclose((dv[0] - dv1[0]).ravel()[idx], fd, rtol=2e-2, atol=2e-3)
 
 
 def test_finite_difference_agreement():

@@ -169,6 +169,7 @@ class ConfigWriter:
         self.fasta = np.array([_s(x) for x in fasta])
         self.n_res = len(self.fasta)
         self.n_atom = 3 * self.n_res
+        self.pos = np.asarray(pos, dtype='f8').reshape(self.n_atom, 3)
         self.root = h5lite.File()
         self.compress = compress
         inp = self.root.create_group('input')
@@ -194,6 +195,73 @@ class ConfigWriter:
         g = self.potential.create_group(name)
         g.attrs['arguments'] = np.array(arguments, dtype='S')
         return g
+
+    # -- restraints (upside_config.py:37-160, 383-415, 814-853); tables are passed as arrays instead of text files ------
+    def write_cavity_radial(self, cavity_radius, spring_constant=5.):
+        g = self.group('cavity_radial', ['pos'])
+        self.arr(g, 'id', np.arange(self.n_atom))
+        self.arr(g, 'radius', np.ones(self.n_atom) * cavity_radius)
+        self.arr(g, 'spring_constant', np.ones(self.n_atom) * spring_constant)
+
+    def _ca(self, residues):
+        residues = np.asarray(residues, dtype='i')
+        if residues.size and not (0 <= residues.min() and residues.max() < len(self.fasta)):
+            raise ValueError('restraint specified for a residue outside the FASTA (zero is first residue)')
+        return residues * 3 + 1   # restrain the CA atom in each residue
+
+    def write_z_flat_bottom(self, residues, z0, radius, spring_constant):
+        g = self.group('z_flat_bottom', ['pos'])
+        self.arr(g, 'atom', self._ca(residues))
+        self.arr(g, 'z0', np.asarray(z0, dtype='f8'))
+        self.arr(g, 'radius', np.asarray(radius, dtype='f8'))
+        self.arr(g, 'spring_constant', np.asarray(spring_constant, dtype='f8'))
+
+    def write_tension(self, residues, tension):
+        g = self.group('tension', ['pos'])
+        self.arr(g, 'atom', self._ca(residues))
+        self.arr(g, 'tension_coeff', np.asarray(tension, dtype='f8').reshape(-1, 3))
+
+    def write_AFM(self, residues, spring_const, starting_tip_pos, pulling_vel, time_initial, time_step):
+        g = self.group('AFM', ['pos'])
+        self.arr(g, 'atom', self._ca(residues))
+        self.arr(g, 'spring_const', np.asarray(spring_const, dtype='f8'))
+        self.arr(g, 'starting_tip_pos', np.asarray(starting_tip_pos, dtype='f8').reshape(-1, 3))
+        d = self.arr(g, 'pulling_vel', np.asarray(pulling_vel, dtype='f8').reshape(-1, 3))
+        d.attrs['time_initial'] = np.float64(time_initial)
+        d.attrs['time_step'] = np.float64(time_step)
+
+    def write_pos_spring(self, atoms, x0, spring_const):
+        """atom_pos_spring (bonds.cpp:9-50); the reference's Python has no writer for it"""
+        g = self.group('atom_pos_spring', ['pos'])
+        self.arr(g, 'id', np.asarray(atoms, dtype='i'))
+        self.arr(g, 'x0', np.asarray(x0, dtype='f8').reshape(-1, 3))
+        self.arr(g, 'spring_const', np.asarray(spring_const, dtype='f8'))
+
+    def write_contact_energies(self, pairs, energy, distance, width, argument='placement_fixed_point_only_CB'):
+        if np.min(width) <= 0.:
+            raise ValueError('Cannot have negative contact transition_width')
+        g = self.group('contact', [argument])
+        self.arr(g, 'id', np.asarray(pairs, dtype='i').reshape(-1, 2))
+        self.arr(g, 'energy', np.asarray(energy, dtype='f8'))
+        self.arr(g, 'distance', np.asarray(distance, dtype='f8'))
+        self.arr(g, 'width', np.asarray(width, dtype='f8'))
+
+    def make_restraint_group(self, residues, strength):
+        """random intra-group springs appended to dist_spring (upside_config.py:383-415; same pairing rule, numpy Generator
+        instead of the legacy global seed)"""
+        rng = np.random.default_rng(314159)
+        g = self.potential['dist_spring']
+        old = {k: np.array(g[k].data) for k in ('id', 'equil_dist', 'spring_const', 'bonded_atoms')}
+        r_atoms = np.array([(3 * i, 3 * i + 1, 3 * i + 2) for i in sorted(residues)]).reshape(-1)
+        pairs = np.concatenate([np.column_stack((r_atoms, rng.permutation(r_atoms))) for _ in range(2)], axis=0)
+        pairs = np.array(sorted(set((min(x, y), max(x, y)) for x, y in pairs if x // 3 != y // 3)))
+        dist = np.sqrt(((self.pos[pairs[:, 0]] - self.pos[pairs[:, 1]]) ** 2).sum(axis=-1))
+        for k in old:
+            del g.children[k]
+        self.arr(g, 'id', np.concatenate((old['id'], pairs), axis=0))
+        self.arr(g, 'equil_dist', np.concatenate((old['equil_dist'], dist), axis=0))
+        self.arr(g, 'spring_const', np.concatenate((old['spring_const'], strength * np.ones(len(pairs))), axis=0))
+        self.arr(g, 'bonded_atoms', np.concatenate((old['bonded_atoms'], np.zeros(len(pairs), dtype='int')), axis=0))
 
     # -- bonded (upside_config.py:480-525) -------------------------------------------------------
     def write_dist_spring(self, bond_stiffness=48.):
@@ -481,6 +549,19 @@ class ConfigWriter:
 
     def save(self, path):
         h5lite.save(self.root, path)
+
+    @classmethod
+    def from_file(cls, path, compress=True):
+        """reopen a written configuration to add nodes (restraints) to it"""
+        root = h5lite.load(path)
+        w = cls.__new__(cls)
+        w.fasta = np.array([_s(x) for x in root['input/sequence'].data])
+        w.n_res = len(w.fasta)
+        w.n_atom = 3 * w.n_res
+        w.pos = np.asarray(root['input/pos'].data[:, :, 0], dtype='f8')
+        w.root, w.compress = root, compress
+        w.potential = root['input/potential']
+        return w
 
 
 def load_rama_reference(path):

@@ -124,6 +124,14 @@ template <typename NodeClass> struct RegisterNodeType<NodeClass, -1> {
         });
     }
 };
+template <typename NodeClass> struct RegisterNodeType<NodeClass, 0> {
+    explicit RegisterNodeType(std::string p) {
+        add_node_creation_function(p, [](Engine& e, const h5l::Node& g, const ArgList& a) -> DerivComputation* {
+            check_arguments_length(a, 0);
+            return new NodeClass(e, g);
+        });
+    }
+};
 template <typename NodeClass> struct RegisterNodeType<NodeClass, 1> {
     explicit RegisterNodeType(std::string p) {
         add_node_creation_function(p, [](Engine& e, const h5l::Node& g, const ArgList& a) -> DerivComputation* {
