@@ -111,6 +111,16 @@ int ub_profile_eval(UbEngine* e, int max_entry, char* labels, int label_len, flo
 /* known-answer access to the device RNG (src/random.h:19-66): threefry bits, normal3 and u01(word0) */
 int ub_rng_probe(uint32_t seed, uint32_t stream, uint32_t atom, uint64_t timestep, uint32_t* bits4, float* normal3_u01);
 
+/* Monte-Carlo pivot / jump moves (reference src/monte_carlo_sampler.cpp:255-308, src/main.cpp:545,630-631).  The samplers
+ * are read from /input/pivot_moves and /input/jump_moves of the configuration when the engine is created.  One execute =
+ * one Metropolis step of every sampler for EVERY replica: two batched energy evaluations per sampler, proposal and
+ * acceptance on the device with the reference's random stream RandomGenerator(seed_r, stream, 0, round); seeds and
+ * temperatures are those of ub_md_init*.  Asynchronous like ub_md_run.  Stats are per replica (n_success, n_attempt). */
+int ub_mc_n_samplers(UbEngine* e);
+int ub_mc_sampler_name(UbEngine* e, int index, char* buf, int buf_len);   /* "pivot", "jump" */
+int ub_mc_execute(UbEngine* e, uint64_t round);
+int ub_mc_stats(UbEngine* e, int index, uint64_t* n_success /* n_replica */, uint64_t* n_attempt, int reset);
+
 /* FP32 FMA throughput this GPU sustains (independent FFMA chains on every SM, CUDA-event timed, best of 4 after warm-up):
  * the measured denominator of the FP32 roofline bench.py reports (MEASURED_PEAKS.json holds only HBM and bf16 numbers). */
 int ub_measure_fp32_peak(int device, float* tflops, float* sm_mhz_nominal);

@@ -5,6 +5,8 @@
 //                        integration_cycle, :618 one OpenMP thread per system) without HDF5 output, used as the
 //                        CPU baseline and for trajectory parity.  Calls only the reference's own functions.
 //  * ref_rng_*         - known-answer access to the reference's RandomGenerator (random.h)
+//  * ref_mc_steps      - the reference's Monte-Carlo samplers (monte_carlo_sampler.cpp) executed on n_sys copies of one
+//                        configuration exactly as main.cpp:545,630-631 does, for Monte-Carlo parity
 #include <chrono>
 #include <cstring>
 #include <memory>
@@ -14,7 +16,9 @@
 
 #include "deriv_engine.h"
 #include "engine_c_library.h"
+#include "monte_carlo_sampler.h"
 #include "random.h"
+#include "state_logger.h"
 #include "thermostat.h"
 
 extern "C" {
@@ -117,4 +121,36 @@ int ref_md_run(const char* config_path, int n_sys, int n_atom, float* pos, float
     fprintf(stderr, "ref_md_run: %s\n", e.c_str());
     return 1;
 } catch(...) { return 1; }
+
+// n_step Monte-Carlo executes (rounds first_round, first_round+1, ...) on n_sys copies of the configuration `rw_copy_path`
+// (a scratch copy without /output: the samplers register loggers, which need a writable file; use n_sys = 1 per copy).  pos: [n_sys][n_atom][3] in/out;
+// stats_out: [n_sys][n_sampler][2] (n_success, n_attempt); returns the number of samplers, negative on error.
+int ref_mc_steps(const char* rw_copy_path, int n_sys, int n_atom, float* pos, const float* temperature, uint32_t base_seed,
+                 uint64_t first_round, int n_step, long* stats_out, int max_sampler) try {
+    int n_sampler = 0;
+    for(int s=0; s<n_sys; ++s) {
+        auto config = h5::h5_obj(H5Fclose, H5Fopen(rw_copy_path, H5F_ACC_RDWR, H5P_DEFAULT));
+        auto logger = std::make_shared<H5Logger>(config, "output", LOG_BASIC);
+        DerivEngine* e = construct_deriv_engine(n_atom, rw_copy_path, true);
+        if(!e) return -1;
+        for(int na=0; na<n_atom; ++na) for(int d=0; d<3; ++d) e->pos->output(d,na) = pos[(size_t(s)*n_atom+na)*3+d];
+        {
+            MultipleMonteCarloSampler mc{h5::open_group(config.get(), "/input").get(), *logger};
+            n_sampler = (int)mc.samplers.size();
+            for(int k=0; k<n_step; ++k) mc.execute(base_seed + s, first_round + k, temperature[s], *e);
+            for(int m=0; m<n_sampler && m<max_sampler; ++m) {
+                stats_out[(size_t(s)*max_sampler+m)*2+0] = (long)mc.samplers[m]->move_stats.n_success;
+                stats_out[(size_t(s)*max_sampler+m)*2+1] = (long)mc.samplers[m]->move_stats.n_attempt;
+            }
+            for(int na=0; na<n_atom; ++na) for(int d=0; d<3; ++d) pos[(size_t(s)*n_atom+na)*3+d] = e->pos->output(d,na);
+            logger->collect_samples();   // (an empty logger cannot be flushed)
+            logger.reset();              // the loggers hold references into mc: flush before it goes away
+        }
+        free_deriv_engine(e);
+    }
+    return n_sampler;
+} catch(const std::string& e) {
+    fprintf(stderr, "ref_mc_steps: %s\n", e.c_str());
+    return -1;
+} catch(...) { return -1; }
 }

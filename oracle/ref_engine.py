@@ -177,3 +177,30 @@ def md_run(config_path, pos, temperature, n_round, seed=42, dt=0.009, timescale=
     if rc:
         raise RuntimeError('ref_md_run failed')
     return dict(pos=pos, mom=mom, potential=pot, seconds=sec.value)
+
+
+def mc_steps(config_path, pos, temperature, base_seed, first_round, n_step, flavour='pinned', max_sampler=4):
+    """Reference Monte-Carlo samplers (ref_driver.cpp:ref_mc_steps) on copies of `pos` (n_sys, n_atom, 3), system s seeded
+    base_seed + s.  Returns (new positions, stats[n_sys, n_sampler, 2] = n_success, n_attempt)."""
+    import shutil
+    import tempfile
+    L = load(flavour)
+    pos = np.array(pos, dtype='f4', order='C')
+    n_sys, n_atom = pos.shape[0], pos.shape[1]
+    T = np.ascontiguousarray(np.broadcast_to(np.asarray(temperature, dtype='f4'), (n_sys,)))
+    stats = np.zeros((n_sys, max_sampler, 2), dtype=np.int64)
+    L.ref_mc_steps.restype = ct.c_int
+    L.ref_mc_steps.argtypes = [ct.c_char_p, ct.c_int, ct.c_int, ct.POINTER(ct.c_float), ct.POINTER(ct.c_float), ct.c_uint32,
+                               ct.c_uint64, ct.c_int, ct.POINTER(ct.c_long), ct.c_int]
+    n = 0
+    with tempfile.TemporaryDirectory() as tmp:
+        for s in range(n_sys):   # a fresh scratch copy per system: the samplers' loggers create /output datasets in it
+            scratch = os.path.join(tmp, 'mc%d.up' % s)
+            shutil.copy(config_path, scratch)
+            n = L.ref_mc_steps(scratch.encode(), 1, n_atom, _fp(pos[s]), _fp(T[s:s + 1]), int(base_seed) + s, int(first_round),
+                               int(n_step), stats[s].ctypes.data_as(ct.POINTER(ct.c_long)), max_sampler)
+            if n < 0:
+                break
+    if n < 0:
+        raise RuntimeError('ref_mc_steps failed')
+    return pos, stats[:, :n]

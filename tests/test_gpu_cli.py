@@ -43,6 +43,35 @@ def test_cli_replica_exchange_matches_reference_binary(tmp_path):
         assert 'invocation' in o.attrs
 
 
+@pytest.mark.skipif(not os.path.exists(os.path.join(parity.ROOT, 'oracle', '_ref', 'upside_ref')), reason='oracle/_ref not shipped')
+def test_cli_monte_carlo_matches_reference_binary(tmp_path):
+    """--monte-carlo-interval: the reference binary and upside_main run the same command line on the same inputs; pivot moves
+    are proposed at the same rounds with the same random streams, so the per-frame pivot_stats and the trajectories agree"""
+    import shutil
+    import subprocess
+    g = np.load(os.path.join(GOLD, 'config1.npz'))
+    args = ['--duration', '0.27', '--frame-interval', '0.054', '--monte-carlo-interval', '0.027', '--temperature', '0.8,0.9',
+            '--seed', '11']
+    mine = _write_inputs(tmp_path, g['start'][:2] if 'start' in g.files else g['pos'][:2])
+    (tmp_path / 'ref').mkdir()
+    theirs = []
+    for p in mine:
+        theirs.append(str(tmp_path / 'ref' / os.path.basename(p)))
+        shutil.copy(p, theirs[-1])
+    exe = os.path.join(parity.ROOT, 'oracle', '_ref', 'upside_ref')
+    r = subprocess.run([exe] + args + theirs, capture_output=True, text=True, env=dict(os.environ, OMP_NUM_THREADS='1'))
+    assert r.returncode == 0, r.stderr
+    ue.in_process_upside(args + mine, verbose=False)
+    for a, b in zip(mine, theirs):
+        oa, ob = h5lite.load(a)['output'], h5lite.load(b)['output']
+        sa, sb = np.array(oa['pivot_stats'].data), np.array(ob['pivot_stats'].data)
+        assert sa.shape == sb.shape and (sa[:, 1] == sb[:, 1]).all()            # attempts per frame
+        assert sb[:, 1].sum() == 9                                              # rounds 1..9 (none at t = 0)
+        assert np.abs(sa[:, 0] - sb[:, 0]).sum() <= 1                           # acceptances (a borderline test may flip)
+        if (sa == sb).all():
+            assert np.abs(np.array(oa['pos'].data) - np.array(ob['pos'].data)).max() < 3e-2
+
+
 def test_cli_errors_and_flags(tmp_path):
     g = np.load(os.path.join(GOLD, 'cli_replex.npz'))
     paths = _write_inputs(tmp_path, g['start'][:2])

@@ -116,6 +116,30 @@ def test_restraint_nodes_trajectory_and_afm_clock():
     be.close()
 
 
+@pytest.mark.skipif(not ref_engine.available('pinned'), reason='oracle/_ref not shipped')
+@pytest.mark.parametrize('cid', [1, 3])
+def test_monte_carlo_pivot_moves_match_reference(cid):
+    """batched pivot moves (csrc/monte_carlo.cu) against the reference sampler: same seeds, same rounds => the same proposals
+    (same random stream), the same accept decisions and the same final coordinates"""
+    cfg = parity.CONFIGS[cid]
+    pos = parity.test_positions(cfg, 7)[1:]
+    rounds = list(range(5, 17))
+    ref_pos, ref_stats = ref_engine.mc_steps(cfg, pos, 0.8, 42, rounds[0], len(rounds))
+    be = ue.BatchEngine(cfg, len(pos))
+    assert be.mc_samplers() == ['pivot']
+    be.set_pos(pos); be.md_init(0.8, seed=42)
+    for nr in rounds:
+        be.mc_execute(nr)
+    ok, tr = be.mc_stats(0)
+    assert (tr == len(rounds)).all() and (ref_stats[:, 0, 1] == len(rounds)).all()
+    assert ref_stats[:, 0, 0].sum() > 0                                  # some moves were accepted: the comparison is not vacuous
+    same = ok == ref_stats[:, 0, 0]
+    assert same.sum() >= len(pos) - 1                                   # a Metropolis test within rounding of its variate may flip
+    got = be.get_pos()
+    assert np.abs(got[same] - ref_pos[same]).max() <= 2e-3
+    be.close()
+
+
 @pytest.mark.parametrize('cid', [1, 3])
 def test_trajectory_matches_golden(cid):
     g = np.load(os.path.join(GOLD, 'config%d.npz' % cid))

@@ -54,6 +54,8 @@ static void load_engine(UbEngine& u, const char* path, int n_atom_expected, int 
     }
     if (n_atom < 0) throw std::string("/input/pos not found and n_atom not given");
     u.eng = ub::initialize_engine_from_hdf5(n_atom, *pot, n_rep, device);
+    const h5l::Node* input = h5l::find(root.get(), "/input");
+    if (input && (ub::h5_has(*input, "pivot_moves") || ub::h5_has(*input, "jump_moves"))) u.eng->mc_init(*input);
 }
 
 static ub::DerivComputation& node_of(UbEngine* e, const char* name) { return e->eng->get(name); }
@@ -215,6 +217,19 @@ int ub_swap_pos(UbEngine* e, int n_pair, const int* pairs) {
 int ub_md_set_temperature(UbEngine* e, const float* temperature) { UB_TRY e->eng->set_temperature(temperature); return 0; UB_CATCH }
 int ub_md_run(UbEngine* e, long n_round) { UB_TRY e->eng->md_run(n_round); return 0; UB_CATCH }
 int ub_sync(UbEngine* e) { UB_TRY e->eng->sync_and_check(); return 0; UB_CATCH }
+int ub_mc_n_samplers(UbEngine* e) { return e->eng->mc_n_samplers(); }
+int ub_mc_sampler_name(UbEngine* e, int index, char* buf, int buf_len) {
+    UB_TRY
+    std::string nm = e->eng->mc_sampler_name(index);
+    strncpy(buf, nm.c_str(), buf_len);
+    if (buf_len > 0) buf[buf_len - 1] = 0;
+    return 0;
+    UB_CATCH
+}
+int ub_mc_execute(UbEngine* e, uint64_t round) { UB_TRY e->eng->mc_execute(round); return 0; UB_CATCH }
+int ub_mc_stats(UbEngine* e, int index, uint64_t* n_success, uint64_t* n_attempt, int reset) {
+    UB_TRY e->eng->mc_stats(index, n_success, n_attempt, reset != 0); return 0; UB_CATCH
+}
 int ub_recenter(UbEngine* e, int xy_only) { UB_TRY e->eng->recenter(xy_only != 0); return 0; UB_CATCH }
 int ub_kinetic_energy(UbEngine* e, float* out) {
     UB_TRY

@@ -7,8 +7,8 @@
 // GPU and advance together, one CUDA graph launch per MD round for the whole group.  Replica exchange needs two batched
 // energy evaluations per swap set instead of 2*n_system serial ones (the reference's serial bottleneck, main.cpp:227-275).
 //
-// Not provided (out of scope): Monte-Carlo pivot/jump moves (--monte-carlo-interval > 0 is an
-// error) and the node-specific "detailed"/"extensive" loggers.
+// Monte-Carlo pivot/jump moves (--monte-carlo-interval) run batched on the device (monte_carlo.cu).  Not provided (out of
+// scope): the node-specific "detailed"/"extensive" loggers.
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -154,6 +154,7 @@ struct System {
     vector<float> pos;
     vector<double> kinetic, potential, time, temperature_log;
     vector<int> replica_index, cumulative_swaps;
+    std::map<string, vector<int>> mc_stats;   // "<sampler>_stats": (n_success, n_attempt) since the previous frame
     size_t n_frame = 0;
 };
 
@@ -172,6 +173,7 @@ void write_output(System& sys, const string& invocation, bool have_replex, const
     put("potential", h5l::make_array(sys.potential, {nf, 1}));
     put("time", h5l::make_array(sys.time, {nf}));
     put("temperature", h5l::make_array(sys.temperature_log, {nf, 1}));
+    for (auto& kv : sys.mc_stats) put(kv.first.c_str(), h5l::make_array(kv.second, {nf, 2}));   // monte_carlo_sampler.h:31-36
     if (have_replex) {
         put("replica_index", h5l::make_array(sys.replica_index, {nf, 1}));
         const auto& ps = plan->participating_swaps[ns];
@@ -195,7 +197,6 @@ int run(int argc, const char* const* argv, int verbose) {
         auto pf = h5l::load(args.set_param);
         for (auto& kv : pf->children) if (!kv.second->is_group) set_param_map[kv.first] = h5l::as<float>(kv.second->data);
     }
-    if (args.mc_interval > 0.) throw string("Monte-Carlo moves (--monte-carlo-interval) are not available in the B200 engine");
 
     const float dt = (float)args.time_step;
     const double duration = args.duration;
@@ -230,6 +231,7 @@ int run(int argc, const char* const* argv, int verbose) {
     };
     int replica_interval = 0;
     if (args.replica_interval) replica_interval = (int)std::max(1., args.replica_interval / (3 * dt));
+    const int mc_interval = args.mc_interval > 0. ? std::max(1, int(args.mc_interval / (3 * dt))) : 0;   // main.cpp:409-411
     if (!args.log_level.empty() && args.log_level != "basic" && args.log_level != "detailed" && args.log_level != "extensive")
         throw string("Illegal value for --log-level");
 
@@ -325,6 +327,11 @@ int run(int argc, const char* const* argv, int verbose) {
             if (verbose) printf("overall potential relative error:  %.5f\n", std::sqrt(num / den));
         }
         g.engine->md_init_seeds(seeds.data(), T.data(), dt, (float)args.thermostat_timescale, thermostat_interval);
+        if (mc_interval) {   // samplers of the group's first system (the systems of a group share /input/potential; main.cpp:543-546)
+            const h5l::Node* input = h5l::find(systems[g.systems[0]].root.get(), "/input");
+            if (!input) throw string("unable to open group /input");
+            g.engine->mc_init(*input);
+        }
     }
     } catch (const string& e) {
         fprintf(stderr, "\n\nERROR: %s\n", e.c_str());
@@ -401,9 +408,16 @@ int run(int argc, const char* const* argv, int verbose) {
             g.engine->get_pos(pos.data());
             auto pot = g.engine->get_potential();
             auto kin = g.engine->kinetic_energy();
+            vector<vector<uint64_t>> mc_ok(g.engine->mc_n_samplers(), vector<uint64_t>(B)), mc_try(mc_ok);
+            for (int m = 0; m < g.engine->mc_n_samplers(); ++m) g.engine->mc_stats(m, mc_ok[m].data(), mc_try[m].data(), true);
             for (int r = 0; r < B; ++r) {
                 const int ns = g.systems[r];
                 System& sys = systems[ns];
+                for (int m = 0; m < g.engine->mc_n_samplers(); ++m) {
+                    auto& v = sys.mc_stats[g.engine->mc_sampler_name(m) + "_stats"];
+                    v.push_back((int)mc_ok[m][r]);
+                    v.push_back((int)mc_try[m][r]);
+                }
                 const float* p = &pos[size_t(r) * 3 * g.n_atom];
                 sys.pos.insert(sys.pos.end(), p, p + 3 * g.n_atom);
                 sys.kinetic.push_back(kin[r]);
@@ -443,9 +457,12 @@ int run(int argc, const char* const* argv, int verbose) {
     auto tstart = std::chrono::high_resolution_clock::now();
     uint64_t nr = 0, last_start = 0;
     while (nr < n_round && !received_signal) {
+        // no pivot at t=0, so that a partially strained system may relax first (main.cpp:628-631)
+        if (nr && mc_interval && !(nr % mc_interval)) for (auto& g : groups) g.engine->mc_execute(nr);
         if (!(nr % frame_interval)) log_frame(nr);
         // rounds that can run on the device without the host: up to the next frame, the next exchange, the next annealing step
         uint64_t n = std::min<uint64_t>(n_round - nr, frame_interval - nr % frame_interval);
+        if (mc_interval) n = std::min<uint64_t>(n, mc_interval - nr % mc_interval);
         uint64_t swap_round = 0;
         if (replica_interval) {   // the reference leaves its inner loop at the first nr > last_start with (nr+1) % interval == 0
             swap_round = ((last_start + 2 + replica_interval - 1) / replica_interval) * replica_interval;
@@ -480,6 +497,21 @@ int run(int argc, const char* const* argv, int verbose) {
     if (verbose) {
         printf("\n\nfinished in %.1f seconds (%.2f us/systems/step, %.1e simulation_time_unit/hour)\n", elapsed,
                elapsed * 1e6 / n_system / std::max<uint64_t>(nr, 1) / 3, nr * 3 * dt / elapsed * 3600.);
+        if (mc_interval) {   // main.cpp:697-724
+            for (const char* nm : {"pivot", "jump"}) {
+                bool any = false;
+                for (auto& sys : systems) any = any || sys.mc_stats.count(string(nm) + "_stats");
+                if (!any) continue;
+                printf("\n%s_success:\n", nm);
+                for (auto& sys : systems) {
+                    long ok = 0, tr = 0;
+                    auto it = sys.mc_stats.find(string(nm) + "_stats");
+                    if (it != sys.mc_stats.end()) for (size_t i = 0; i < it->second.size(); i += 2) { ok += it->second[i]; tr += it->second[i + 1]; }
+                    printf(" % .4f", double(ok) / double(tr));
+                }
+                printf("\n");
+            }
+        }
         printf("\navg_kinetic_energy/1.5kT");
         for (auto& sys : systems) {
             double sum = 0.;

@@ -150,3 +150,26 @@ __device__ __forceinline__ float block_sum(float v, float* scratch) {
     }
     return v;
 }
+
+// Blondel & Karplus dihedral and its gradient; reference vector_math.h:704-735
+__device__ __forceinline__ float dihedral_germ(f3 r1, f3 r2, f3 r3, f3 r4, f3& d1, f3& d2, f3& d3, f3& d4) {
+    f3 F = r1 - r2, G = r2 - r3, H = r4 - r3;
+    f3 A = cross(F, G), B = cross(H, G), C = cross(B, A);
+    float iA = 1.f / mag2(A), iB = 1.f / mag2(B);
+    float G2 = mag2(G), iG = rsqrtf(G2), Gm = G2 * iG;
+    d1 = (-Gm * iA) * A;
+    d4 = (Gm * iB) * B;
+    f3 fm = (dot(F, G) * iA * iG) * A - (dot(H, G) * iB * iG) * B;
+    d2 = fm - d1;
+    d3 = -d4 - fm;
+    return atan2f(dot(C, G), dot(A, B) * Gm);
+}
+
+// rotation matrix (row-major) of `angle` about the unit vector `axis`; reference affine.h:49-64
+__device__ __forceinline__ void axis_angle_to_rot(float* U, float angle, f3 axis) {
+    const float x = axis.x, y = axis.y, z = axis.z;
+    const float c = cosf(angle), s = sinf(angle), C = 1.f - c;
+    U[0] = x * x * C + c;     U[1] = x * y * C - z * s; U[2] = x * z * C + y * s;
+    U[3] = y * x * C + z * s; U[4] = y * y * C + c;     U[5] = y * z * C - x * s;
+    U[6] = z * x * C - y * s; U[7] = z * y * C + x * s; U[8] = z * z * C + c;
+}

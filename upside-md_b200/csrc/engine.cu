@@ -3,6 +3,7 @@
 // (compute), :172-192 (integration_cycle), :195-270 (initialize_engine_from_hdf5); src/thermostat.cpp:9-18;
 // src/random.h:19-66 + Random123 threefry4x32-20, uniform.hpp u01/uneg11, boxmuller.hpp.
 #include "engine.h"
+#include "rng.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -144,6 +145,7 @@ Engine::Engine(int n_atom_, int n_rep_, int device_) : n_rep(n_rep_), n_atom(n_a
 
 Engine::~Engine() {
     cudaSetDevice(device);
+    if (mc) mc_destroy(mc);
     for (auto& g : graph_eval) if (g) cudaGraphExecDestroy(g);
     if (graph_round) cudaGraphExecDestroy(graph_round);
     nodes.clear();
@@ -392,48 +394,7 @@ std::vector<float> Engine::get_potential() {
 }
 
 // ------------------------------------------------------------------------------------------------ RNG
-// Threefry-4x32 with 20 rounds (Random123 threefry.h: rotation constants :110-117, key-schedule parity 0x1BD11BDA)
-__device__ __forceinline__ uint32_t rotl32(uint32_t x, int n) { return (x << n) | (x >> (32 - n)); }
-__device__ void threefry4x32_20(uint32_t out[4], const uint32_t ctr[4], const uint32_t key[4]) {
-    const int R[8][2] = {{10, 26}, {11, 21}, {13, 27}, {23, 5}, {6, 20}, {17, 11}, {25, 10}, {18, 20}};
-    uint32_t ks[5];
-    ks[4] = 0x1BD11BDAu;
-    uint32_t X[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { ks[i] = key[i]; X[i] = ctr[i]; ks[4] ^= key[i]; }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) X[i] += ks[i];
-#pragma unroll
-    for (int r = 0; r < 20; ++r) {
-        int ra = R[r & 7][0], rb = R[r & 7][1];
-        if ((r & 1) == 0) {
-            X[0] += X[1]; X[1] = rotl32(X[1], ra); X[1] ^= X[0];
-            X[2] += X[3]; X[3] = rotl32(X[3], rb); X[3] ^= X[2];
-        } else {
-            X[0] += X[3]; X[3] = rotl32(X[3], ra); X[3] ^= X[0];
-            X[2] += X[1]; X[1] = rotl32(X[1], rb); X[1] ^= X[2];
-        }
-        if ((r & 3) == 3) {
-            int s = r / 4 + 1;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) X[i] += ks[(s + i) % 5];
-            X[3] += (uint32_t)s;
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) out[i] = X[i];
-}
-__device__ __forceinline__ float u01_f(uint32_t w) { return w * 2.3283064365386963e-10f + 1.1641532182693481e-10f; }   // uniform.hpp:145-154
-__device__ __forceinline__ float uneg11_f(uint32_t w) { return (float)(int32_t)w * 4.6566128730773926e-10f + 2.3283064365386963e-10f; }  // :171-180
-__device__ __forceinline__ void boxmuller_f(uint32_t u0, uint32_t u1, float& x, float& y) {   // boxmuller.hpp:109-117
-    const float PI = 3.1415926535897932f;
-    float a = PI * uneg11_f(u0);
-    float s = sinf(a), c = cosf(a);
-    float r = sqrtf(-2.f * logf(u01_f(u1)));
-    x = s * r;
-    y = c * r;
-}
-
+// (Threefry-4x32-20, u01/uneg11 and Box-Muller: rng.cuh)
 // p <- mom_scale*p + noise_scale[r]*N(0,1); key (seed_r, stream 0, 0, 0), counter (t_lo, t_hi, atom, 0)
 __global__ void k_thermostat(float* __restrict__ mom, const uint32_t* __restrict__ seed,
                              const float* __restrict__ noise_scale, const unsigned long long* __restrict__ invocation,

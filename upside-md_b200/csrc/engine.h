@@ -158,6 +158,9 @@ template <typename NodeClass> struct RegisterNodeType<NodeClass, 3> {
 };
 
 // ---- engine -----------------------------------------------------------------------------------------------
+struct MonteCarlo;                 // pivot / jump samplers of the batch (monte_carlo.cu)
+void mc_destroy(MonteCarlo* m);
+
 struct Engine {
     struct Node {
         std::string name;
@@ -254,6 +257,16 @@ struct Engine {
     void recenter(bool xy_only);
     void swap_pos(const std::vector<int>& pairs);   // pairs = (a0,b0,a1,b1,...): exchange coordinates of replicas a_k and b_k
     std::vector<float> kinetic_energy();
+
+    // Monte-Carlo moves (reference monte_carlo_sampler.cpp; main.cpp:545,630-631): samplers read from the /input group of a
+    // configuration (pivot_moves, jump_moves); one execute = one Metropolis step of every sampler for every replica, with
+    // the replica's md_init seed and current temperature
+    MonteCarlo* mc = nullptr;
+    void mc_init(const h5l::Node& input_group);
+    void mc_execute(uint64_t round);
+    int mc_n_samplers() const;
+    std::string mc_sampler_name(int i) const;
+    void mc_stats(int i, uint64_t* n_success, uint64_t* n_attempt, bool reset);   // per replica
 };
 
 std::unique_ptr<Engine> initialize_engine_from_hdf5(int n_atom, const h5l::Node& potential_group, int n_rep,

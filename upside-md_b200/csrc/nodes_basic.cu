@@ -125,20 +125,7 @@ struct AngleSpring : PotentialNode {
 RegisterNodeType<AngleSpring, 1> angle_spring_node("angle_spring");
 
 // ---------------------------------------------------------------------------------------------- dihedrals
-// Blondel & Karplus dihedral and its gradient; reference vector_math.h:704-735
-__device__ __forceinline__ float dihedral_germ(f3 r1, f3 r2, f3 r3, f3 r4, f3& d1, f3& d2, f3& d3, f3& d4) {
-    f3 F = r1 - r2, G = r2 - r3, H = r4 - r3;
-    f3 A = cross(F, G), B = cross(H, G), C = cross(B, A);
-    float iA = 1.f / mag2(A), iB = 1.f / mag2(B);
-    float G2 = mag2(G), iG = rsqrtf(G2), Gm = G2 * iG;
-    d1 = (-Gm * iA) * A;
-    d4 = (Gm * iB) * B;
-    f3 fm = (dot(F, G) * iA * iG) * A - (dot(H, G) * iB * iG) * B;
-    d2 = fm - d1;
-    d3 = -d4 - fm;
-    return atan2f(dot(C, G), dot(A, B) * Gm);
-}
-
+// (dihedral_germ: common.cuh)
 // reference bonds.cpp:519-545
 struct SpringParam4 { int a[4]; float equil, k; };
 __global__ void k_dihedral_spring(const float* __restrict__ pos, float* __restrict__ sens, float* __restrict__ pot,

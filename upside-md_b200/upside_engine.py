@@ -71,6 +71,10 @@ def lib():
     L.ub_md_set_temperature.argtypes = [ct.c_void_p, _fp]
     L.ub_md_run.argtypes = [ct.c_void_p, ct.c_long]
     L.ub_sync.argtypes = [ct.c_void_p]
+    L.ub_mc_n_samplers.argtypes = [ct.c_void_p]
+    L.ub_mc_sampler_name.argtypes = [ct.c_void_p, ct.c_int, ct.c_char_p, ct.c_int]
+    L.ub_mc_execute.argtypes = [ct.c_void_p, ct.c_uint64]
+    L.ub_mc_stats.argtypes = [ct.c_void_p, ct.c_int, ct.POINTER(ct.c_uint64), ct.POINTER(ct.c_uint64), ct.c_int]
     L.ub_recenter.argtypes = [ct.c_void_p, ct.c_int]
     L.ub_stream.restype = ct.c_void_p
     L.ub_stream.argtypes = [ct.c_void_p]
@@ -347,6 +351,28 @@ class BatchEngine(object):
 
     def sync(self):
         if self.L.ub_sync(self.e): raise _err('sync')
+
+    # Monte-Carlo moves (reference monte_carlo_sampler.cpp): the samplers of /input/pivot_moves and /input/jump_moves
+    def mc_samplers(self):
+        names = []
+        for i in range(self.L.ub_mc_n_samplers(self.e)):
+            buf = ct.create_string_buffer(64)
+            if self.L.ub_mc_sampler_name(self.e, i, buf, 64): raise _err('mc_sampler_name')
+            names.append(buf.value.decode())
+        return names
+
+    def mc_execute(self, round_num, sync=True):
+        """one Metropolis step of every sampler for every replica (MultipleMonteCarloSampler::execute); needs md_init"""
+        if self.L.ub_mc_execute(self.e, int(round_num)): raise _err('mc_execute')
+        if sync:
+            self.sync()
+
+    def mc_stats(self, sampler, reset=False):
+        """(n_success, n_attempt) per replica of sampler number `sampler`"""
+        ok, tr = np.zeros(self.n_replica, dtype='u8'), np.zeros(self.n_replica, dtype='u8')
+        p = ct.POINTER(ct.c_uint64)
+        if self.L.ub_mc_stats(self.e, int(sampler), ok.ctypes.data_as(p), tr.ctypes.data_as(p), int(reset)): raise _err('mc_stats')
+        return ok, tr
 
     def recenter(self, xy_only=False):
         if self.L.ub_recenter(self.e, int(xy_only)): raise _err('recenter')
