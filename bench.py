@@ -48,23 +48,25 @@ def workload_positions(n_replica, rank):
     return pos
 
 
-def cpu_reference_arm(steps, warmup, max_seconds=60.0):
-    """reference engine on the host cores: n_thread replicas (8 per core would only lengthen the run), bounded sample"""
+def cpu_reference_arm(steps, warmup, max_seconds=60.0, target_seconds=None):
+    """reference engine on the host cores: a bounded sample of the workload = 4 replicas per core (one OpenMP thread per
+    core, the reference's one-thread-per-system scheme, README.md:198-200); `steps` rounds, or - for the cpu_baseline leg -
+    as many rounds as fill `target_seconds` of CPU time"""
     from oracle import ref_engine
     if not ref_engine.available('fast'):
         return None
     cores = os.cpu_count() or 1
-    n_sys = cores
+    n_sys = 4 * cores
     pos = workload_positions(n_sys, 0)
     # warm-up rounds relax the clashing random starts exactly like the GPU arm's warm-up does
     w = ref_engine.md_run(CONFIG, pos, TEMPERATURE, EQUIL_ROUNDS + max(1, warmup), seed=SEED, dt=DT, n_thread=cores, flavour='fast')
     per_round = max(w['seconds'] / (EQUIL_ROUNDS + max(1, warmup)), 1e-6)
-    rounds = int(max(1, min(steps, max_seconds / per_round)))
+    rounds = int(max(1, target_seconds / per_round)) if target_seconds else int(max(1, min(steps, max_seconds / per_round)))
     r = ref_engine.md_run(CONFIG, w['pos'], TEMPERATURE, rounds, seed=SEED + 1, dt=DT, n_thread=cores, flavour='fast')
     value = n_sys * 3 * rounds / r['seconds']
     return dict(value=value, unit=UNIT, cores=cores, kind='reference', seconds=r['seconds'], rounds=rounds, n_sys=n_sys,
-                sample='%d replicas (one per host core, OpenMP) x %d rounds of config3 (100 res, ff_1), reference '
-                       'sources built -O3 -ffast-math -march=x86-64-v3 -DPARAM_7A_CUTOFF' % (n_sys, rounds),
+                sample='%d replicas (4 per host core, one OpenMP thread per core) x %d rounds = %.1f s of config3 (100 res, ff_1), '
+                       'reference sources built -O3 -ffast-math -march=x86-64-v3 -DPARAM_7A_CUTOFF' % (n_sys, rounds, r['seconds']),
                 us_per_force_eval=r['seconds'] * 1e6 / (3 * rounds))
 
 
@@ -181,7 +183,7 @@ def gpu_arm(args):
         roof = kernel_rooflines(eng, stream, torch)
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
-        cpu = cpu_reference_arm(args.steps, 3, max_seconds=20.0)
+        cpu = cpu_reference_arm(args.steps, 3, target_seconds=12.0)
     if rank == 0:
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32',
