@@ -104,19 +104,24 @@ __global__ void __launch_bounds__(CTPB) k_hbond_coverage(IGraphDev g, QuadSpline
             [&](int j, int, const float* s) { out[size_t(r) * g.s2.n + j] = s[0]; });
     }
 }
-// backward: bead side sens[j] * sum_i dV/d(bead j); site side sum_j sens[j] * dV/d(site i) (7 components, last = d/d hb)
+// backward: every edge is evaluated ONCE (rows = beads whose coverage has a non-zero sensitivity).  Bead side:
+// sens[j] * sum_i dV/d(bead j), summed per row in a fixed order.  Site side: sens[j] * dV/d(site i) (7 components, last =
+// d/d hb) goes into per-site accumulators in shared memory with atomics (a site has few partners; forces are summed with
+// float atomics elsewhere on the path as well), flushed by one thread per site.
 __global__ void __launch_bounds__(CTPB) k_hbond_coverage_deriv(IGraphDev g, QuadSplineShape q, const float* __restrict__ sens, int n_rep,
                                                                int n_rows_max) {
     extern __shared__ float4 smem4[];
     StagedGroup S1, S2;
     float* table;
     const int n_tab = g.n_type1 * g.n_type2 * g.n_param;
-    EdgeScratch E = carve_edge_scratch(carve_groups(g, smem4, S1, S2, table, n_tab), n_rows_max, 7);
+    EdgeScratch E = carve_edge_scratch(carve_groups(g, smem4, S1, S2, table, n_tab), n_rows_max, 6);
     float* sn = reinterpret_cast<float*>(E.wtot + 33);   // [n2] sens of this replica's beads
+    float* acc1 = sn + g.s2.n;                            // [n1][7] site-side sums
     stage_table(g, S1, S2, table, n_tab);
     for (int r = blockIdx.x; r < n_rep; r += gridDim.x) {
-        stage_groups(g, r, S1, S2);   // (leading barrier: previous replica's readers of sn are done)
+        stage_groups(g, r, S1, S2);   // (leading barrier: previous replica's readers of sn / acc1 are done)
         for (int j = threadIdx.x; j < g.s2.n; j += blockDim.x) sn[j] = sens[size_t(r) * g.s2.n + j];
+        for (int i = threadIdx.x; i < g.s1.n * 7; i += blockDim.x) acc1[i] = 0.f;
         __syncthreads();
         const int* cnt2 = g.cnt2 + size_t(r) * g.s2.n;
         scan_row_lengths(g.s2.n, [&](int j) { return sn[j] != 0.f ? cnt2[j] : 0; }, E.start, E.wtot);
@@ -125,6 +130,9 @@ __global__ void __launch_bounds__(CTPB) k_hbond_coverage_deriv(IGraphDev g, Quad
                 float x1[8], x2[8], d1[7];
                 unpack8(S1, i, x1); unpack8(S2, j, x2);
                 hbond_coverage_edge(table + (S1.type[i] * g.n_type2 + S2.type[j]) * g.n_param, q, x1, x2, d1, o);
+                const float sj = sn[j];
+#pragma unroll
+                for (int c = 0; c < 7; ++c) atomicAdd(&acc1[i * 7 + c], sj * d1[c]);
             },
             [&](int j, int c, const float* s) {
                 if (!c) return;
@@ -134,24 +142,16 @@ __global__ void __launch_bounds__(CTPB) k_hbond_coverage_deriv(IGraphDev g, Quad
                 a.x += sj * s[0]; a.y += sj * s[1]; a.z += sj * s[2]; a.w += sj * s[3]; b.x += sj * s[4]; b.y += sj * s[5];
                 reinterpret_cast<float4*>(dst)[0] = a; reinterpret_cast<float4*>(dst)[1] = b;
             });
+        // (for_each_edge ends with a barrier: acc1 is complete)
         const int* cnt1 = g.cnt1 + size_t(r) * g.s1.n;
-        scan_row_lengths(g.s1.n, [&](int i) { return cnt1[i]; }, E.start, E.wtot);
-        for_each_edge<7>(g.s1.n, g.nbr1 + size_t(r) * g.s1.n * g.K1, g.K1, E,
-            [&](int i, int j, float* o) {
-                float x1[8], x2[8], d2[6];
-                unpack8(S1, i, x1); unpack8(S2, j, x2);
-                hbond_coverage_edge(table + (S1.type[i] * g.n_type2 + S2.type[j]) * g.n_param, q, x1, x2, o, d2);
-                const float sj = sn[j];
-#pragma unroll
-                for (int c = 0; c < 7; ++c) o[c] *= sj;
-            },
-            [&](int i, int c, const float* s) {
-                if (!c) return;
-                float* dst = elem_sens_ptr(g.s1, r, i);
-                float4 a = reinterpret_cast<float4*>(dst)[0], b = reinterpret_cast<float4*>(dst)[1];
-                a.x += s[0]; a.y += s[1]; a.z += s[2]; a.w += s[3]; b.x += s[4]; b.y += s[5]; b.z += s[6];
-                reinterpret_cast<float4*>(dst)[0] = a; reinterpret_cast<float4*>(dst)[1] = b;
-            });
+        for (int i = threadIdx.x; i < g.s1.n; i += blockDim.x) {
+            if (!cnt1[i]) continue;
+            const float* s = acc1 + i * 7;
+            float* dst = elem_sens_ptr(g.s1, r, i);
+            float4 a = reinterpret_cast<float4*>(dst)[0], b = reinterpret_cast<float4*>(dst)[1];
+            a.x += s[0]; a.y += s[1]; a.z += s[2]; a.w += s[3]; b.x += s[4]; b.y += s[5]; b.z += s[6];
+            reinterpret_cast<float4*>(dst)[0] = a; reinterpret_cast<float4*>(dst)[1] = b;
+        }
     }
 }
 struct HBondCoverage : CoordNode {
@@ -172,7 +172,7 @@ struct HBondCoverage : CoordNode {
     }
     void finalize() override {
         ig.allocate(engine);
-        launch.init(engine, ig, 7, ig.n2, (const void*)k_hbond_coverage, (const void*)k_hbond_coverage_deriv, "hbond_coverage");
+        launch.init(engine, ig, 6, ig.n2 + 7 * ig.n1, (const void*)k_hbond_coverage, (const void*)k_hbond_coverage_deriv, "hbond_coverage");
     }
     QuadSplineShape shape() const { QuadSplineShape q; q.nka = nka; q.nk = nk; q.inv_dx = 1.f / knot_spacing; q.inv_dtheta = (nka - 3) / 2.f; return q; }
     void compute_value(cudaStream_t s, ComputeMode) override {
@@ -218,6 +218,8 @@ __global__ void __launch_bounds__(CTPB) k_env_coverage(IGraphDev g, float* __res
             [&](int i, int, const float* s) { out[size_t(r) * g.s1.n + i] = s[0]; });
     }
 }
+// backward: every edge is evaluated once (rows = CBs whose coverage has a non-zero sensitivity); CB side summed per row in a
+// fixed order, bead side (position + weight, 4 components) through shared-memory accumulators as in k_hbond_coverage_deriv
 __global__ void __launch_bounds__(CTPB) k_env_coverage_deriv(IGraphDev g, const float* __restrict__ sens, int n_rep, int n_rows_max) {
     extern __shared__ float4 smem4[];
     StagedGroup S1, S2;
@@ -225,10 +227,12 @@ __global__ void __launch_bounds__(CTPB) k_env_coverage_deriv(IGraphDev g, const 
     const int n_tab = g.n_type1 * g.n_type2 * g.n_param;
     EdgeScratch E = carve_edge_scratch(carve_groups(g, smem4, S1, S2, table, n_tab), n_rows_max, 6);
     float* sn = reinterpret_cast<float*>(E.wtot + 33);   // [n1] sens of this replica's CB coverages
+    float* acc2 = sn + g.s1.n;                            // [n2][4] bead-side sums
     stage_table(g, S1, S2, table, n_tab);
     for (int r = blockIdx.x; r < n_rep; r += gridDim.x) {
-        stage_groups(g, r, S1, S2);   // (leading barrier: previous replica's readers of sn are done)
+        stage_groups(g, r, S1, S2);   // (leading barrier: previous replica's readers of sn / acc2 are done)
         for (int i = threadIdx.x; i < g.s1.n; i += blockDim.x) sn[i] = sens[size_t(r) * g.s1.n + i];
+        for (int j = threadIdx.x; j < g.s2.n * 4; j += blockDim.x) acc2[j] = 0.f;
         __syncthreads();
         const int* cnt1 = g.cnt1 + size_t(r) * g.s1.n;
         scan_row_lengths(g.s1.n, [&](int i) { return sn[i] != 0.f ? cnt1[i] : 0; }, E.start, E.wtot);
@@ -239,6 +243,9 @@ __global__ void __launch_bounds__(CTPB) k_env_coverage_deriv(IGraphDev g, const 
                 float4 v = S2.a[j];
                 float x2[4] = {v.x, v.y, v.z, v.w};
                 environment_edge(table + (S1.type[i] * g.n_type2 + S2.type[j]) * g.n_param, x1, x2, o, d2);
+                const float si = sn[i];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) atomicAdd(&acc2[j * 4 + c], si * d2[c]);
             },
             [&](int i, int c, const float* s) {
                 if (!c) return;
@@ -249,25 +256,13 @@ __global__ void __launch_bounds__(CTPB) k_env_coverage_deriv(IGraphDev g, const 
                 reinterpret_cast<float4*>(dst)[0] = a; reinterpret_cast<float4*>(dst)[1] = b;
             });
         const int* cnt2 = g.cnt2 + size_t(r) * g.s2.n;
-        scan_row_lengths(g.s2.n, [&](int j) { return cnt2[j]; }, E.start, E.wtot);
-        for_each_edge<4>(g.s2.n, g.nbr2 + size_t(r) * g.s2.n * g.K2, g.K2, E,
-            [&](int j, int i, float* o) {
-                float x1[8], d1[6];
-                unpack8(S1, i, x1);
-                float4 v = S2.a[j];
-                float x2[4] = {v.x, v.y, v.z, v.w};
-                environment_edge(table + (S1.type[i] * g.n_type2 + S2.type[j]) * g.n_param, x1, x2, d1, o);
-                const float si = sn[i];
-#pragma unroll
-                for (int c = 0; c < 4; ++c) o[c] *= si;
-            },
-            [&](int j, int c, const float* s) {
-                if (!c) return;
-                float4* dst = reinterpret_cast<float4*>(elem_sens_ptr(g.s2, r, j));
-                float4 o = *dst;
-                o.x += s[0]; o.y += s[1]; o.z += s[2]; o.w += s[3];
-                *dst = o;
-            });
+        for (int j = threadIdx.x; j < g.s2.n; j += blockDim.x) {
+            if (!cnt2[j]) continue;
+            float4* dst = reinterpret_cast<float4*>(elem_sens_ptr(g.s2, r, j));
+            float4 o = *dst;
+            o.x += acc2[4 * j]; o.y += acc2[4 * j + 1]; o.z += acc2[4 * j + 2]; o.w += acc2[4 * j + 3];
+            *dst = o;
+        }
     }
 }
 struct EnvironmentCoverage : CoordNode {
@@ -283,7 +278,7 @@ struct EnvironmentCoverage : CoordNode {
     }
     void finalize() override {
         ig.allocate(engine);
-        launch.init(engine, ig, 6, ig.n1, (const void*)k_env_coverage, (const void*)k_env_coverage_deriv, "environment_coverage");
+        launch.init(engine, ig, 6, ig.n1 + 4 * ig.n2, (const void*)k_env_coverage, (const void*)k_env_coverage_deriv, "environment_coverage");
     }
     void compute_value(cudaStream_t s, ComputeMode) override {
         if (!n_elem) return;
