@@ -108,3 +108,35 @@ def test_clamped_spline_helpers():
     eps = 1e-2
     fd = (ue.clamped_spline_value(c, np.array([3.5 + eps], 'f4')) - ue.clamped_spline_value(c, np.array([3.5 - eps], 'f4'))) / (2 * eps)
     assert vd[0, 1] == pytest.approx(float(fd[0]), rel=1e-2)
+
+
+def test_restraint_config_writers_against_reference_potentials():
+    """config 6 (tools/make_restraint_config.py, written with config.py's restraint writers): the reference engine reads it,
+    and its restraint energies are what numpy computes from the written tables (bonds.cpp:36-47,77-88,355-372,406-424)"""
+    from oracle import ref_engine
+    if not ref_engine.available('pinned'):
+        pytest.skip('oracle/_ref not built')
+    import parity
+    cfg = parity.CONFIGS[6]
+    pot = h5lite.load(cfg)['input/potential']
+    pos = parity.initial_pos(cfg).astype('f8')
+    ref = ref_engine.RefEngine(cfg, len(pos), 'pinned')
+    ref.energy(pos.astype('f4'))
+    g = pot['atom_pos_spring']
+    d = pos[np.array(g['id'].data)] - np.array(g['x0'].data)
+    assert ref.node_potential('atom_pos_spring') == pytest.approx(float((0.5 * np.array(g['spring_const'].data) * (d ** 2).sum(1)).sum()), rel=1e-5)
+    g = pot['tension']
+    assert ref.node_potential('tension') == pytest.approx(float(-(pos[np.array(g['atom'].data)] * np.array(g['tension_coeff'].data)).sum()), rel=1e-5)
+    g = pot['z_flat_bottom']
+    dz = pos[np.array(g['atom'].data), 2] - np.array(g['z0'].data)
+    rad = np.array(g['radius'].data)
+    ex = np.where(dz > rad, dz - rad, np.where(dz < -rad, dz + rad, 0.))
+    assert ref.node_potential('z_flat_bottom') == pytest.approx(float((0.5 * np.array(g['spring_constant'].data) * ex ** 2).sum()), rel=1e-5, abs=1e-6)
+    g = pot['cavity_radial']
+    rr = np.sqrt((pos[np.array(g['id'].data)] ** 2).sum(1))
+    ex = np.maximum(rr - np.array(g['radius'].data), 0.)
+    assert ref.node_potential('cavity_radial') == pytest.approx(float((0.5 * np.array(g['spring_constant'].data) * ex ** 2).sum()), rel=1e-4, abs=1e-5)
+    # the restraint group appended unbonded springs to dist_spring
+    ds = pot['dist_spring']
+    assert (np.array(ds['bonded_atoms'].data) == 0).sum() > 0 and len(ds['id'].data) == len(ds['equil_dist'].data)
+    ref.close()
