@@ -34,7 +34,7 @@ TEMPERATURE = 0.80
 DT = 0.009
 SEED = 42
 N_RES = 100
-EQUIL_ROUNDS = 30
+EQUIL_ROUNDS = 300   # the cost of a round drifts until ~250 rounds after random_initial_config (tools/equil_probe.py)
 METRIC = 'replica-timesteps/sec, 100-residue protein batch'
 UNIT = 'replica-timesteps/s'
 

@@ -213,8 +213,9 @@ __device__ __forceinline__ void refine_rows(int r, const RefineRole& R, float cu
     }
 }
 
+// `which`: bit 0 = refine table 1, bit 1 = refine the transposed table (two groups only)
 template <int G>
-__global__ void k_refine(IGraphSide A, IGraphSide Bs, int two_groups, RefineTable T1, RefineTable T2, float cutoff2, int* error_flag) {
+__global__ void k_refine(IGraphSide A, IGraphSide Bs, int two_groups, int which, RefineTable T1, RefineTable T2, float cutoff2, int* error_flag) {
     extern __shared__ float4 sm_pos[];
     const int r = blockIdx.x;
     float4* posA = sm_pos;                                  // [A.n + 1], last = sentinel
@@ -222,13 +223,14 @@ __global__ void k_refine(IGraphSide A, IGraphSide Bs, int two_groups, RefineTabl
     // one row per thread where the block is large enough; with two groups the first A.n threads (rounded up to whole
     // warps) refine table 1 while the others refine the transposed table
     const int T = blockDim.x;
-    const int split = two_groups ? max(32, min(T - 32, ((T * A.n / (A.n + Bs.n)) + 16) & ~31)) : 0;   // threads in proportion to rows
+    const bool two_tables = two_groups && which == 3;
+    const int split = two_tables ? max(32, min(T - 32, ((T * A.n / (A.n + Bs.n)) + 16) & ~31)) : 0;   // threads in proportion to rows
     RefineRole R1{T1, A.n, 1, (int)threadIdx.x, T, posA, posB}, R2{T2, Bs.n, 0, (int)threadIdx.x, T, posB, posA};
-    const bool both = two_groups && split <= 0;      // block too small to split: every thread does both tables in turn
-    if (two_groups && split > 0) {
+    const bool both = two_tables && split <= 0;      // block too small to split: every thread does both tables in turn
+    if (two_tables && split > 0) {
         if ((int)threadIdx.x < split) R1.n_thread = split;
         else { R1 = R2; R1.t0 = threadIdx.x - split; R1.n_thread = T - split; }
-    }
+    } else if (two_groups && which == 2) R1 = R2;    // only the transposed table is wanted
     RefinePrefetch F;
     refine_prefetch(r, R1, R1.t0, F);
     const float4 far = make_float4(1e18f, 1e18f, 1e18f, 0.f);
@@ -449,6 +451,9 @@ struct IGraphHost {
     DevBuf<int> ccnt1, ccnt2, flag, rep_list, n_list;
     DevBuf<float> cpos1, cpos2;
     int Kc1 = 0, Kc2 = 0;
+    // which exact tables the owning node's kernels read (asymmetric graphs; set before allocate()): a table nobody gathers
+    // from is neither rebuilt nor refined
+    bool need1 = true, need2 = true;
     Engine* engine = nullptr;
 
     // reads index/type/id(+1/2) and interaction_param (n_type1,n_type2,n_param): interaction_graph.h:305-381

@@ -64,7 +64,7 @@ struct CoverageLaunch {
     size_t smem_fwd = 0, smem_bwd = 0;
     int grid_fwd = 1, grid_bwd = 1, n_rows_max = 0;
     void init(Engine* e, const IGraphHost& ig, int nv_bwd, int n_sens, const void* kf, const void* kb, const char* what) {
-        if (ig.K1 > EL_CAP || ig.K2 > EL_CAP) throw std::string(what) + ": neighbour capacity exceeds the edge chunk size";
+        if ((ig.need1 && ig.K1 > EL_CAP) || (ig.need2 && ig.K2 > EL_CAP)) throw std::string(what) + ": neighbour capacity exceeds the edge chunk size";
         n_rows_max = std::max(ig.n1, ig.n2);
         size_t staged = staged_bytes(ig.n1, ig.n2, ig.n_type1 * ig.n_type2 * ig.n_param);
         smem_fwd = staged + edge_scratch_bytes(n_rows_max, 1);
@@ -143,10 +143,9 @@ __global__ void __launch_bounds__(CTPB) k_hbond_coverage_deriv(IGraphDev g, Quad
                 reinterpret_cast<float4*>(dst)[0] = a; reinterpret_cast<float4*>(dst)[1] = b;
             });
         // (for_each_edge ends with a barrier: acc1 is complete)
-        const int* cnt1 = g.cnt1 + size_t(r) * g.s1.n;
         for (int i = threadIdx.x; i < g.s1.n; i += blockDim.x) {
-            if (!cnt1[i]) continue;
             const float* s = acc1 + i * 7;
+            if (s[0] == 0.f && s[1] == 0.f && s[2] == 0.f && s[6] == 0.f) continue;   // site without a partner (no table by site is kept)
             float* dst = elem_sens_ptr(g.s1, r, i);
             float4 a = reinterpret_cast<float4*>(dst)[0], b = reinterpret_cast<float4*>(dst)[1];
             a.x += s[0]; a.y += s[1]; a.z += s[2]; a.w += s[3]; b.x += s[4]; b.y += s[5]; b.z += s[6];
@@ -171,6 +170,7 @@ struct HBondCoverage : CoordNode {
         ig.cutoff = float((nk - 2 - 1e-6) / double(1.f / knot_spacing));   // hbond.cpp:250-252
     }
     void finalize() override {
+        ig.need1 = false;   // both kernels walk the rows of the beads (table 2)
         ig.allocate(engine);
         launch.init(engine, ig, 6, ig.n2 + 7 * ig.n1, (const void*)k_hbond_coverage, (const void*)k_hbond_coverage_deriv, "hbond_coverage");
     }
@@ -255,9 +255,8 @@ __global__ void __launch_bounds__(CTPB) k_env_coverage_deriv(IGraphDev g, const 
                 a.x += si * s[0]; a.y += si * s[1]; a.z += si * s[2]; a.w += si * s[3]; b.x += si * s[4]; b.y += si * s[5];
                 reinterpret_cast<float4*>(dst)[0] = a; reinterpret_cast<float4*>(dst)[1] = b;
             });
-        const int* cnt2 = g.cnt2 + size_t(r) * g.s2.n;
         for (int j = threadIdx.x; j < g.s2.n; j += blockDim.x) {
-            if (!cnt2[j]) continue;
+            if (acc2[4 * j] == 0.f && acc2[4 * j + 1] == 0.f && acc2[4 * j + 2] == 0.f && acc2[4 * j + 3] == 0.f) continue;   // bead outside every cone
             float4* dst = reinterpret_cast<float4*>(elem_sens_ptr(g.s2, r, j));
             float4 o = *dst;
             o.x += acc2[4 * j]; o.y += acc2[4 * j + 1]; o.z += acc2[4 * j + 2]; o.w += acc2[4 * j + 3];
@@ -277,6 +276,7 @@ struct EnvironmentCoverage : CoordNode {
         ig.cutoff = c;
     }
     void finalize() override {
+        ig.need2 = false;   // both kernels walk the rows of the CBs (table 1)
         ig.allocate(engine);
         launch.init(engine, ig, 6, ig.n1 + 4 * ig.n2, (const void*)k_env_coverage, (const void*)k_env_coverage_deriv, "environment_coverage");
     }

@@ -57,9 +57,13 @@ void IGraphHost::allocate(Engine* e) {
     engine = e;
     K1 = neighbor_capacity(cutoff, n2);
     K2 = symmetric ? K1 : neighbor_capacity(cutoff, n1);
-    nbr1.alloc(size_t(e->n_rep) * n1 * K1);
-    cnt1.alloc(size_t(e->n_rep) * n1);
-    if (!symmetric) {
+    if (symmetric) need1 = need2 = true;
+    if (!need1 && !need2) throw std::string("interaction graph without a neighbour table");
+    if (need1) {
+        nbr1.alloc(size_t(e->n_rep) * n1 * K1);
+        cnt1.alloc(size_t(e->n_rep) * n1);
+    }
+    if (!symmetric && need2) {
         nbr2.alloc(size_t(e->n_rep) * n2 * K2);
         cnt2.alloc(size_t(e->n_rep) * n2);
     }
@@ -72,12 +76,16 @@ void IGraphHost::allocate(Engine* e) {
         if (const char* sk = getenv("UPSIDE_B200_SKIN_SCALE")) skin = std::max(0.1f, (float)atof(sk)) * (1.0f + 0.2f * cutoff);
         Kc1 = neighbor_capacity(cutoff + skin, n2);   // multiple of eight: slices (see k_pairlist)
         Kc2 = symmetric ? Kc1 : neighbor_capacity(cutoff + skin, n1);
-        cand1.alloc(size_t(e->n_rep) * n1 * Kc1);
-        ccnt1.alloc(size_t(e->n_rep) * n1);
+        if (need1) {
+            cand1.alloc(size_t(e->n_rep) * n1 * Kc1);
+            ccnt1.alloc(size_t(e->n_rep) * n1);
+        }
         cpos1.alloc(size_t(e->n_rep) * n1 * 4);
         if (!symmetric) {
-            cand2.alloc(size_t(e->n_rep) * n2 * Kc2);
-            ccnt2.alloc(size_t(e->n_rep) * n2);
+            if (need2) {
+                cand2.alloc(size_t(e->n_rep) * n2 * Kc2);
+                ccnt2.alloc(size_t(e->n_rep) * n2);
+            }
             cpos2.alloc(size_t(e->n_rep) * n2 * 4);
         }
         flag.upload(std::vector<int>(e->n_rep, 2));   // 2 = never built
@@ -107,9 +115,10 @@ void IGraphHost::build(cudaStream_t s) {
     if (!n1 || !n2) return;
     const int B = engine->n_rep;
     if (!use_cache) {
-        k_pairlist<TILE><<<dim3((n1 + TILE - 1) / TILE, B), TILE, 0, s>>>(d.s1, d.s2, d.nbr1, d.cnt1, d.K1, d.cutoff2, d.excl,
-                                                                          symmetric, 1, d.error_flag, nullptr, nullptr, 0);
-        if (!symmetric)
+        if (need1)
+            k_pairlist<TILE><<<dim3((n1 + TILE - 1) / TILE, B), TILE, 0, s>>>(d.s1, d.s2, d.nbr1, d.cnt1, d.K1, d.cutoff2, d.excl,
+                                                                              symmetric, 1, d.error_flag, nullptr, nullptr, 0);
+        if (!symmetric && need2)
             k_pairlist<TILE><<<dim3((n2 + TILE - 1) / TILE, B), TILE, 0, s>>>(d.s2, d.s1, d.nbr2, d.cnt2, d.K2, d.cutoff2, d.excl,
                                                                               0, 0, d.error_flag, nullptr, nullptr, 0);
         return;
@@ -120,35 +129,39 @@ void IGraphHost::build(cudaStream_t s) {
     k_cache_check<<<B, 128, 0, s>>>(d.s1, d.s2, symmetric ? 0 : 1, cpos1.p, cpos2.p, max_move2, flag.p, rep_list.p, n_list.p);
     // rebuilds touch only the flagged replicas: a modest grid strides over the compacted list
     const int gy = std::min(B, 592);
-    k_pairlist<TILE><<<dim3((n1 + TILE - 1) / TILE, gy), TILE, 0, s>>>(d.s1, d.s2, cand1.p, ccnt1.p, Kc1, cc * cc, d.excl, symmetric,
-                                                                       1, d.error_flag, rep_list.p, n_list.p, 1);
-    if (!symmetric)
+    if (need1)
+        k_pairlist<TILE><<<dim3((n1 + TILE - 1) / TILE, gy), TILE, 0, s>>>(d.s1, d.s2, cand1.p, ccnt1.p, Kc1, cc * cc, d.excl, symmetric,
+                                                                           1, d.error_flag, rep_list.p, n_list.p, 1);
+    if (!symmetric && need2)
         k_pairlist<TILE><<<dim3((n2 + TILE - 1) / TILE, gy), TILE, 0, s>>>(d.s2, d.s1, cand2.p, ccnt2.p, Kc2, cc * cc, d.excl, 0, 0,
                                                                            d.error_flag, rep_list.p, n_list.p, 1);
     RefineTable T1{cand1.p, ccnt1.p, Kc1, d.nbr1, d.cnt1, d.K1};
     RefineTable T2{cand2.p, ccnt2.p, Kc2, symmetric ? nullptr : d.nbr2, symmetric ? nullptr : d.cnt2, d.K2};
     size_t smem = sizeof(float4) * size_t(symmetric ? n1 + 1 : n1 + n2 + 2);
-    const int rows = symmetric ? n1 : ((n1 + 31) & ~31) + n2;
+    const int which = symmetric ? 1 : (need1 ? 1 : 0) | (need2 ? 2 : 0);
+    const int rows = which == 3 ? ((n1 + 31) & ~31) + n2 : (which == 2 ? n2 : n1);
     const int tpb = std::min(256, std::max(64, (rows + 31) & ~31));   // smaller blocks keep more of them resident
-    k_refine<RGL><<<B, tpb, smem, s>>>(d.s1, d.s2, symmetric ? 0 : 1, T1, T2, d.cutoff2, d.error_flag);
+    k_refine<RGL><<<B, tpb, smem, s>>>(d.s1, d.s2, symmetric ? 0 : 1, which, T1, T2, d.cutoff2, d.error_flag);
     engine->mark(s, "(pairlist)");
 }
 
 bool IGraphHost::pairlist(int replica, std::vector<int>& i1, std::vector<int>& i2) {
     if (replica < 0 || replica >= engine->n_rep) throw std::string("replica out of range");
     engine->sync_and_check();
-    std::vector<unsigned short> rows(size_t(n1) * K1);
-    std::vector<int> cnt(n1);
-    UB_CUDA(cudaMemcpy(rows.data(), nbr1.p + size_t(replica) * n1 * K1, rows.size() * sizeof(unsigned short), cudaMemcpyDeviceToHost));
-    UB_CUDA(cudaMemcpy(cnt.data(), cnt1.p + size_t(replica) * n1, cnt.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    const bool t1 = need1;   // read whichever table the node keeps; the transposed one lists the same pairs by second index
+    const int n = t1 ? n1 : n2, K = t1 ? K1 : K2;
+    std::vector<unsigned short> rows(size_t(n) * K);
+    std::vector<int> cnt(n);
+    UB_CUDA(cudaMemcpy(rows.data(), (t1 ? nbr1.p : nbr2.p) + size_t(replica) * n * K, rows.size() * sizeof(unsigned short), cudaMemcpyDeviceToHost));
+    UB_CUDA(cudaMemcpy(cnt.data(), (t1 ? cnt1.p : cnt2.p) + size_t(replica) * n, cnt.size() * sizeof(int), cudaMemcpyDeviceToHost));
     i1.clear();
     i2.clear();
-    for (int i = 0; i < n1; ++i)
+    for (int i = 0; i < n; ++i)
         for (int k = 0; k < cnt[i]; ++k) {
-            int j = rows[size_t(i) * K1 + k];
+            int j = rows[size_t(i) * K + k];
             if (symmetric && !(i < j)) continue;   // the reference keeps i1<i2 only (interaction_graph.h:142-144)
-            i1.push_back(i);
-            i2.push_back(j);
+            i1.push_back(t1 ? i : j);
+            i2.push_back(t1 ? j : i);
         }
     sort_reference_order(i1, i2);
     return true;
