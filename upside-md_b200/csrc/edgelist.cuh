@@ -11,7 +11,10 @@
 
 namespace ub {
 
-constexpr int EL_CAP = 1024;   // edges evaluated per chunk (a chunk is a run of whole rows)
+#ifndef UB_EL_CAP
+#define UB_EL_CAP 1024
+#endif
+constexpr int EL_CAP = UB_EL_CAP;   // edges evaluated per chunk (a chunk is a run of whole rows)
 
 struct EdgeScratch {
     int* start;        // [n_rows_max + 1] exclusive scan of the row lengths

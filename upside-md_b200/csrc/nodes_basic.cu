@@ -184,8 +184,8 @@ RegisterNodeType<DihedralSpring, 1> dihedral_spring_node("dihedral_spring");
 // ---------------------------------------------------------------------------------------------- RamaCoord
 // reference bonds.cpp:171-249: phi,psi per residue (dummy angle -1.3963 at the termini) and its Jacobian
 struct RamaParam { int atom[5]; int dummy0, dummy1; };
-__global__ void k_rama_coord(const float* __restrict__ pos, float* __restrict__ out, float* __restrict__ jac,
-                             const RamaParam* __restrict__ prm, int n, int n_atom) {
+__global__ void k_rama_coord(const float* __restrict__ pos, float* __restrict__ out, const RamaParam* __restrict__ prm, int n,
+                             int n_atom) {
     int i = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
     if (i >= n) return;
     RamaParam p = prm[i];
@@ -193,41 +193,49 @@ __global__ void k_rama_coord(const float* __restrict__ pos, float* __restrict__ 
     f3 a[5];
 #pragma unroll
     for (int k = 0; k < 5; ++k) a[k] = ld3v(x + 4 * p.atom[k]);
-    f3 d[2][5];
-#pragma unroll
-    for (int k = 0; k < 5; ++k) d[0][k] = d[1][k] = mk3(0.f, 0.f, 0.f);
+    f3 d[4];
     float phi = -1.3963f, psi = -1.3963f;
-    if (!p.dummy0) phi = dihedral_germ(a[0], a[1], a[2], a[3], d[0][0], d[0][1], d[0][2], d[0][3]);
-    if (!p.dummy1) psi = dihedral_germ(a[1], a[2], a[3], a[4], d[1][1], d[1][2], d[1][3], d[1][4]);
-    float* o = out + (size_t(r) * n + i) * 2;
-    o[0] = phi;
-    o[1] = psi;
-    float* j = jac + (size_t(r) * n + i) * 30;
-#pragma unroll
-    for (int q = 0; q < 2; ++q)
-#pragma unroll
-        for (int k = 0; k < 5; ++k) st3(j + (q * 5 + k) * 3, d[q][k]);
+    if (!p.dummy0) phi = dihedral_germ(a[0], a[1], a[2], a[3], d[0], d[1], d[2], d[3]);
+    if (!p.dummy1) psi = dihedral_germ(a[1], a[2], a[3], a[4], d[0], d[1], d[2], d[3]);
+    reinterpret_cast<float2*>(out)[size_t(r) * n + i] = make_float2(phi, psi);
 }
-__global__ void k_rama_coord_deriv(float* __restrict__ pos_sens, const float* __restrict__ sens,
-                                   const float* __restrict__ jac, const RamaParam* __restrict__ prm, int n, int n_atom) {
+// the Jacobian (2 x 5 x 3, bonds.cpp:222-247) is recomputed from the positions: ~200 flops cost less than storing and
+// re-reading 120 bytes per residue with a 120-byte stride between threads
+__global__ void k_rama_coord_deriv(const float* __restrict__ pos, float* __restrict__ pos_sens, const float* __restrict__ sens,
+                                   const RamaParam* __restrict__ prm, int n, int n_atom) {
     int i = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
     if (i >= n) return;
     RamaParam p = prm[i];
-    const float* sn = sens + (size_t(r) * n + i) * 2;
-    float s0 = sn[0], s1 = sn[1];
-    const float* j = jac + (size_t(r) * n + i) * 30;
+    const float2 sn = reinterpret_cast<const float2*>(sens)[size_t(r) * n + i];
+    const float* x = pos + size_t(r) * n_atom * 4;
+    f3 a[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) a[k] = ld3v(x + 4 * p.atom[k]);
+    f3 v[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) v[k] = mk3(0.f, 0.f, 0.f);
+    if (!p.dummy0) {
+        f3 d[4];
+        dihedral_germ(a[0], a[1], a[2], a[3], d[0], d[1], d[2], d[3]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] += sn.x * d[k];
+    }
+    if (!p.dummy1) {
+        f3 d[4];
+        dihedral_germ(a[1], a[2], a[3], a[4], d[0], d[1], d[2], d[3]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k + 1] += sn.y * d[k];
+    }
     float* ps = pos_sens + size_t(r) * n_atom * 4;
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
-        f3 v = s0 * ld3(j + k * 3) + s1 * ld3(j + (5 + k) * 3);
         bool used = (k < 4 && !p.dummy0) || (k > 0 && !p.dummy1);
-        if (used) atomic_add3(ps + 4 * p.atom[k], v);
+        if (used) atomic_add3(ps + 4 * p.atom[k], v[k]);
     }
 }
 struct RamaCoord : CoordNode {
     CoordNode& pos;
     DevBuf<RamaParam> prm;
-    DevBuf<float> jac;
     RamaCoord(Engine&, const h5l::Node& g, CoordNode& pos_) : CoordNode((int)h5_dims(g, "id", 2)[0], 2), pos(pos_) {
         h5_check_size(g, "id", {(uint64_t)n_elem, 5});
         auto id = h5_read<int>(g, "id");
@@ -242,12 +250,11 @@ struct RamaCoord : CoordNode {
         }
         prm.upload(h);
     }
-    void finalize() override { jac.alloc(size_t(engine->n_rep) * n_elem * 30); }
     void compute_value(cudaStream_t s, ComputeMode) override {
-        k_rama_coord<<<grid_for(n_elem, engine->n_rep), TPB, 0, s>>>(pos.output, output, jac.p, prm.p, n_elem, pos.n_elem);
+        k_rama_coord<<<grid_for(n_elem, engine->n_rep), TPB, 0, s>>>(pos.output, output, prm.p, n_elem, pos.n_elem);
     }
     void propagate_deriv(cudaStream_t s) override {
-        k_rama_coord_deriv<<<grid_for(n_elem, engine->n_rep), TPB, 0, s>>>(pos.sens, sens, jac.p, prm.p, n_elem, pos.n_elem);
+        k_rama_coord_deriv<<<grid_for(n_elem, engine->n_rep), TPB, 0, s>>>(pos.output, pos.sens, sens, prm.p, n_elem, pos.n_elem);
     }
 };
 RegisterNodeType<RamaCoord, 1> rama_coord_node("rama_coord");
@@ -646,17 +653,25 @@ __global__ void k_placement(const float* __restrict__ affine, const float* __res
         const float* c = data + size_t(layer[i]) * sig.n_dim;
         for (int d = 0; d < sig.n_dim; ++d) val[d] = __ldg(c + d);
     }
-    float* o = out + (size_t(r) * n + i) * wp;
+    float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     int off = 0;
     for (int b = 0; b < sig.n_block; ++b) {
         if (sig.type[b] == P_SCALAR) { o[off] = val[off]; off += 1; }
         else {
             f3 v = rot_apply(U, mk3(val[off], val[off + 1], val[off + 2]));
             if (sig.type[b] == P_POINT) v += t;
-            st3(o + off, v);
+            o[off] = v.x; o[off + 1] = v.y; o[off + 2] = v.z;
             off += 3;
         }
     }
+    // rows are padded to 1/2/4/8 floats (padding written as zero): 16-byte stores
+    float* dst = out + (size_t(r) * n + i) * wp;
+    if (wp == 8) {
+        reinterpret_cast<float4*>(dst)[0] = make_float4(o[0], o[1], o[2], o[3]);
+        reinterpret_cast<float4*>(dst)[1] = make_float4(o[4], o[5], o[6], o[7]);
+    } else if (wp == 4) reinterpret_cast<float4*>(dst)[0] = make_float4(o[0], o[1], o[2], o[3]);
+    else if (wp == 2) reinterpret_cast<float2*>(dst)[0] = make_float2(o[0], o[1]);
+    else dst[0] = o[0];
 }
 template <bool RAMA>
 __global__ void k_placement_deriv(const float* __restrict__ affine, float* __restrict__ affine_sens,
@@ -667,8 +682,15 @@ __global__ void k_placement_deriv(const float* __restrict__ affine, float* __res
                                   const int* __restrict__ layer, PlaceSig sig, int n, int wp, int n_aff, int n_rama,
                                   int nx, int ny) {
     int i = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
-    if (i >= n) return;
-    int ar = affine_residue[i];
+    const bool active = i < n;
+    const unsigned lane = threadIdx.x & 31u;
+    // elements placed on the same residue frame are neighbours in every configuration upside_config.py writes: their
+    // force and torque are summed across the lanes of a warp first (segmented suffix sums), one atomic per run of <= 8
+    const int ar = active ? affine_residue[i] : -1 - (int)lane;
+    bool spatial = false;
+    for (int b = 0; b < sig.n_block; ++b) spatial |= sig.type[b] != P_SCALAR;
+    f3 com = mk3(0.f, 0.f, 0.f), torque = mk3(0.f, 0.f, 0.f);
+    if (active) {
     const float* aff = affine + (size_t(r) * n_aff + ar) * 8;
     float4 a0 = reinterpret_cast<const float4*>(aff)[0], a1 = reinterpret_cast<const float4*>(aff)[1];
     f3 t = mk3(a0.x, a0.y, a0.z);
@@ -678,7 +700,6 @@ __global__ void k_placement_deriv(const float* __restrict__ affine, float* __res
     const float* x = out + (size_t(r) * n + i) * wp;
     const float* sn = sens + (size_t(r) * n + i) * wp;
     float ref_sens[7];
-    f3 com = mk3(0.f, 0.f, 0.f), torque = mk3(0.f, 0.f, 0.f);
     int off = 0;
     for (int b = 0; b < sig.n_block; ++b) {
         if (sig.type[b] == P_SCALAR) { ref_sens[off] = sn[off]; off += 1; }
@@ -704,9 +725,24 @@ __global__ void k_placement_deriv(const float* __restrict__ affine, float* __res
         float* pd = param_deriv + size_t(layer[i]) * sig.n_dim;
         for (int d = 0; d < sig.n_dim; ++d) atomicAdd(pd + d, ref_sens[d]);
     }
-    float* as = affine_sens + (size_t(r) * n_aff + ar) * 8;
-    atomic_add3(as, com);
-    atomic_add3(as + 3, torque);
+    }
+    if (!spatial) return;   // scalar placements move no frame (uniform over the grid)
+    const int ar_prev = __shfl_up_sync(UB_FULL_MASK, ar, 1);
+    const unsigned heads = __ballot_sync(UB_FULL_MASK, lane == 0 || ar_prev != ar);
+    const int seg_start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
+    float v[6] = {com.x, com.y, com.z, torque.x, torque.y, torque.z};
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+        const int start_o = __shfl_down_sync(UB_FULL_MASK, seg_start, o);
+        const bool take = lane + o < 32 && start_o == seg_start;   // same run, whatever the order of the elements
+#pragma unroll
+        for (int c = 0; c < 6; ++c) { const float w = __shfl_down_sync(UB_FULL_MASK, v[c], o); if (take) v[c] += w; }
+    }
+    if (active && ((lane - seg_start) & 7) == 0) {
+        float* as = affine_sens + (size_t(r) * n_aff + ar) * 8;
+        atomic_add3(as, mk3(v[0], v[1], v[2]));
+        atomic_add3(as + 3, mk3(v[3], v[4], v[5]));
+    }
 }
 
 template <bool RAMA> struct PlacementNode : CoordNode {

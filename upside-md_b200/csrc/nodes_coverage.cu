@@ -12,7 +12,10 @@
 namespace ub {
 namespace {
 
-constexpr int CTPB = 256;
+#ifndef UB_CTPB
+#define UB_CTPB 256
+#endif
+constexpr int CTPB = UB_CTPB;
 
 struct StagedGroup {
     float4* a;   // x,y,z,w0

@@ -782,7 +782,17 @@ __device__ void bp_solve_generic(const RotamerDev& P, int want_pot, int r, float
 // chain per sweep to one shared-memory round trip per four incident pairs.  The sweep-end barrier doubles as the
 // convergence vote (__syncthreads_or).  Replicas that do not fit the shared-memory budget (or configurations with state
 // counts other than 1/3/6) are appended to slow_list and solved by k_rot_bp.
-constexpr int BP2_TPB = 384;
+#ifndef UB_BP2_TPB
+#define UB_BP2_TPB 384
+#endif
+#ifndef UB_BP2_WANT10
+#define UB_BP2_WANT10 38   // pair capacity the fast kernel must offer, per residue, x10
+#endif
+#ifndef UB_BP2_OCC
+#define UB_BP2_OCC 3
+#endif
+constexpr int BP2_TPB = UB_BP2_TPB;
+constexpr int BP2_OCC = UB_BP2_OCC;
 
 struct Bp2Lay {
     int nRp;     // padded residue count of the component-major belief arrays (== 4 mod 32: conflict-free node update)
@@ -888,7 +898,7 @@ __device__ __forceinline__ float bp2_node(int A, const float* __restrict__ prob,
     return dev;
 }
 
-__global__ void __launch_bounds__(BP2_TPB, 3) k_rot_bp2(RotamerDev P, Bp2Lay L, int want_pot) {
+__global__ void __launch_bounds__(BP2_TPB, BP2_OCC) k_rot_bp2(RotamerDev P, Bp2Lay L, int want_pot) {
     extern __shared__ float smem[];
     const int r = blockIdx.x, tid = threadIdx.x;
     const int nR = P.n_res, nRp = L.nRp, SP = L.SP;
@@ -1290,8 +1300,8 @@ struct RotamerSidechain : PotentialNode {
         int sm_total = 0;
         UB_CUDA(cudaDeviceGetAttribute(&sm_total, cudaDevAttrMaxSharedMemoryPerMultiprocessor, engine->device));
         auto pad4 = [](int v) { return ((v + 27) / 32) * 32 + 4; };   // smallest value >= v that is 4 mod 32
-        const int want_pairs = std::min<long>(max_pairs, std::max<long>(32, (long)std::ceil(3.8 * n_res)));
-        for (int occ = 3; occ >= 1; --occ) {
+        const int want_pairs = std::min<long>(max_pairs, std::max<long>(32, (long)std::ceil(0.1 * UB_BP2_WANT10 * n_res)));
+        for (int occ = BP2_OCC; occ >= 1; --occ) {
             size_t budget = std::min<size_t>(device_smem, size_t(sm_total) / occ - 1024);
             Bp2Lay L;
             L.nRp = pad4(n_res);
