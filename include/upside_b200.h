@@ -49,6 +49,10 @@ int ub_get_node_potential(UbEngine* e, const char* node, float* out /* n_replica
 int ub_get_value_by_name(UbEngine* e, const char* node, const char* log_name, int replica, int n, float* out, int* n_written);
 int ub_get_param(UbEngine* e, const char* node, int n, float* out, int* n_param);
 int ub_set_param(UbEngine* e, const char* node, int n, const float* param);
+/* dV/d(parameter) of `node` from the state of the last evaluation with derivatives (reference get_param_deriv of a
+ * PARAM_DERIV build, src/engine_c_library.cpp:93-108, src/interaction_graph.h:404-415); replica < 0 sums over the
+ * batch; out == NULL only reports the size (0 = the node has no parameter derivative) */
+int ub_get_param_deriv(UbEngine* e, const char* node, int replica, int n, float* out, int* n_param);
 
 /* pair list a node built in the last evaluation, in the reference's emission order
  * (PairlistComputation::find_edges, src/interaction_graph.h:201-257); *n_edge receives the full count */

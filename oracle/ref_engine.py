@@ -37,6 +37,7 @@ def load(flavour='pinned'):
     L.get_sens.argtypes = [ct.c_int, fp, ct.c_void_p, ct.c_char_p]
     L.get_param.argtypes = [ct.c_int, fp, ct.c_void_p, ct.c_char_p]
     L.set_param.argtypes = [ct.c_int, fp, ct.c_void_p, ct.c_char_p]
+    L.get_param_deriv.argtypes = [ct.c_int, fp, ct.c_void_p, ct.c_char_p]
     L.get_value_by_name.argtypes = [ct.c_int, fp, ct.c_void_p, ct.c_char_p, ct.c_char_p]
     L.ref_pairlist.argtypes = [ct.c_void_p, ct.c_char_p, ip, ip, ct.c_int]
     L.ref_get_computation.restype = ct.c_void_p
@@ -129,6 +130,13 @@ class RefEngine:
         if self.L.ref_node_potential(self.e, node.encode(), ct.byref(out)):
             raise RuntimeError(node + ' is not a potential node')
         return out.value
+
+    def get_param_deriv(self, node, n):
+        """reference get_param_deriv (PARAM_DERIV build, engine_c_library.cpp:93-108) after a deriv() call"""
+        a = np.zeros(n, dtype='f4')
+        if self.L.get_param_deriv(a.size, _fp(a), self.e, node.encode()):
+            raise RuntimeError('get_param_deriv failed for ' + node)
+        return a
 
     def get_value_by_name(self, node, name, n):
         a = np.zeros(n, dtype='f4')

@@ -229,3 +229,43 @@ def test_full_batch_invariants():
     ke = be.kinetic_energy() / (1.5 * 0.8)
     assert 0.5 < np.median(ke) < 4.0
     be.close()
+
+
+@pytest.mark.skipif(not ref_engine.available('pinned'), reason='oracle/_ref not shipped')
+@pytest.mark.parametrize('cid', [1, 3])
+def test_param_deriv_matches_oracle(cid):
+    """get_param_deriv (reference PARAM_DERIV build: interaction_graph.h:404-415, bead_interaction.h:86-129,
+    hbond.cpp:278-283,447-449, environment.cpp:62-65,375-390, placement.cpp:138-161) after an evaluation with
+    derivatives, node by node, through the single-system C ABI and through the batched one"""
+    cfg = parity.CONFIGS[cid]
+    pos = parity.test_positions(cfg, 3)[1:]
+    n_atom = pos.shape[1]
+    ref = ref_engine.RefEngine(cfg, n_atom)
+    up = ue.Upside(cfg)
+    be = ue.BatchEngine(cfg, len(pos))
+    be.evaluate(pos)
+    names = [n for n, _ in ref.node_names()]
+    checked = 0
+    for node in names:
+        size = be.get_param(node).size
+        got_batch = [be.get_param_deriv(node, r) for r in range(len(pos))]
+        if not got_batch[0].size:
+            continue
+        assert got_batch[0].size == size, node
+        for r in range(len(pos)):
+            ref.deriv(pos[r])                      # every query starts from a fresh backward pass of the reference
+            want = ref.get_param_deriv(node, size)
+            scale = max(1.0, float(np.abs(want).max()))
+            assert np.abs(got_batch[r] - want).max() <= 2e-3 * scale, (node, r, np.abs(got_batch[r] - want).max(), scale)
+            if r == 0:
+                up.deriv(pos[r])
+                one = up.get_param_deriv((size,), node)
+                assert np.abs(one - want).max() <= 2e-3 * scale, (node, 'C ABI')
+        total = be.get_param_deriv(node, -1)
+        assert np.abs(total - np.sum(got_batch, axis=0)).max() <= 1e-3 * max(1.0, float(np.abs(total).max())), node
+        checked += 1
+    # rotamer pair table, both coverage tables, the environment spline, E_hb and the three fixed placements
+    assert checked >= 7, checked
+    assert np.abs(be.get_param_deriv('rotamer', 0)).max() > 0
+    be.close()
+    ref.close()

@@ -182,6 +182,17 @@ int ub_get_param(UbEngine* e, const char* node, int n, float* out, int* n_param)
     return 0;
     UB_CATCH
 }
+int ub_get_param_deriv(UbEngine* e, const char* node, int replica, int n, float* out, int* n_param) {
+    UB_TRY
+    auto v = node_of(e, node).get_param_deriv(replica);
+    if (n_param) *n_param = (int)v.size();
+    if (out) {
+        if ((int)v.size() != n) throw std::string("wrong number of parameters (parameter derivatives are not implemented for this node)");
+        std::copy(v.begin(), v.end(), out);
+    }
+    return 0;
+    UB_CATCH
+}
 int ub_set_param(UbEngine* e, const char* node, int n, const float* param) {
     UB_TRY
     e->eng->sync_and_check();
@@ -371,7 +382,7 @@ int get_param(int n_param, float* param, DerivEngine* engine, const char* node_n
 }
 int get_param_deriv(int n_param, float* deriv, DerivEngine* engine, const char* node_name) {
     UB_TRY
-    auto v = node_of(&engine->u, node_name).get_param_deriv();
+    auto v = node_of(&engine->u, node_name).get_param_deriv(0);
     if ((int)v.size() != n_param) throw std::string("wrong number of parameters (parameter derivatives are not implemented for this node)");
     std::copy(v.begin(), v.end(), deriv);
     return 0;

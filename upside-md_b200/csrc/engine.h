@@ -78,7 +78,9 @@ struct DerivComputation {
     virtual void finalize() {}
     virtual std::vector<float> get_param() const { return {}; }
     virtual void set_param(const std::vector<float>&) {}
-    virtual std::vector<float> get_param_deriv() { return {}; }
+    // dV/d(parameter) from the state the last evaluation with derivatives left behind (reference PARAM_DERIV builds);
+    // replica < 0 sums over the batch.  Empty = the node has no parameter derivative.
+    virtual std::vector<float> get_param_deriv(int replica = 0) { return {}; }
     virtual std::vector<float> get_value_by_name(int replica, const char* log_name) {
         throw std::string("No values implemented");
     }

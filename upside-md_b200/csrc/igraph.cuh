@@ -353,6 +353,43 @@ __device__ __forceinline__ float quadspline_edge(const float* __restrict__ p, co
     return wv + angular_weight * nv;
 }
 
+// d(quadspline)/d(parameter) (reference quadspline_param_deriv, bead_interaction.h:86-129): the value is linear in the
+// coefficients of each of its four splines, so the derivative has 16 non-zero entries - the four basis weights of the
+// knot interval of each spline times the other factors.  idx = position inside the type pair's parameter row.
+__device__ __forceinline__ void quadspline_param_deriv(const float* __restrict__ p, const QuadSplineShape& q, const float* x1,
+                                                       const float* x2, int* idx, float* val) {
+    f3 displace = mk3(x2[0] - x1[0], x2[1] - x1[1], x2[2] - x1[2]);
+    f3 rvec1 = mk3(x1[3], x1[4], x1[5]), rvec2 = mk3(x2[3], x2[4], x2[5]);
+    float dist2 = mag2(displace);
+    float inv_dist = rsqrtf(dist2);
+    float dist_coord = dist2 * (inv_dist * q.inv_dx);
+    f3 u = inv_dist * displace;
+    float cos1 = dot(rvec1, u), cos2 = -dot(rvec2, u);
+    float wa1[4], wa2[4], wr[4], d[4], a1v, a2v, nv, unused;
+    float x = (cos1 + 1.f) * q.inv_dtheta + 1.f;
+    const int b1 = max(1, min((int)x, q.nka - 3));
+    bspline_weights(x - (float)b1, wa1, d);
+    bspline_apply(wa1, d, p[b1 - 1], p[b1], p[b1 + 1], p[b1 + 2], a1v, unused);
+    const float* p2 = p + q.nka;
+    x = (cos2 + 1.f) * q.inv_dtheta + 1.f;
+    const int b2 = max(1, min((int)x, q.nka - 3));
+    bspline_weights(x - (float)b2, wa2, d);
+    bspline_apply(wa2, d, p2[b2 - 1], p2[b2], p2[b2 + 1], p2[b2 + 2], a2v, unused);
+    int rs;   // first coefficient of the radial interval (clamped_deBoor_coeff_deriv, spline.h:375-392)
+    if (dist_coord <= 1.f) { rs = 0; wr[0] = 1.f / 6.f; wr[1] = 2.f / 3.f; wr[2] = 1.f / 6.f; wr[3] = 0.f; }
+    else if (dist_coord >= (float)(q.nk - 2)) { rs = q.nk - 4; wr[0] = 0.f; wr[1] = 1.f / 6.f; wr[2] = 2.f / 3.f; wr[3] = 1.f / 6.f; }
+    else { const int b = (int)dist_coord; rs = b - 1; bspline_weights(dist_coord - (float)b, wr, d); }
+    const float* narrow = p + 2 * q.nka + q.nk;
+    nv = wr[0] * narrow[rs] + wr[1] * narrow[rs + 1] + wr[2] * narrow[rs + 2] + wr[3] * narrow[rs + 3];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        idx[i] = b1 - 1 + i;                       val[i] = a2v * nv * wa1[i];
+        idx[4 + i] = q.nka + b2 - 1 + i;           val[4 + i] = a1v * nv * wa2[i];
+        idx[8 + i] = 2 * q.nka + rs + i;           val[8 + i] = wr[i];
+        idx[12 + i] = 2 * q.nka + q.nk + rs + i;   val[12 + i] = a1v * a2v * wr[i];
+    }
+}
+
 // HBondCoverageInteraction (hbond.cpp:241-286): quadspline scaled by (1-hb)^2, hb = x1[6]; d1 has 7 components
 __device__ __forceinline__ float hbond_coverage_edge(const float* __restrict__ p, const QuadSplineShape& q, const float* x1,
                                                      const float* x2, float* d1, float* d2) {

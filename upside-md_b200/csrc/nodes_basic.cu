@@ -13,6 +13,13 @@ namespace {
 constexpr int TPB = 128;
 inline dim3 grid_for(int n_elem, int n_rep) { return dim3((n_elem + TPB - 1) / TPB, n_rep); }
 
+// host copy of replicas [r0,r1) of a node's output or sens rows (padded rows, as on the device); accessors only
+static std::vector<float> download_rows(const CoordNode& n, const float* base, int r0, int r1) {
+    std::vector<float> h(size_t(r1 - r0) * n.stride());
+    if (!h.empty()) UB_CUDA(cudaMemcpy(h.data(), base + size_t(r0) * n.stride(), h.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    return h;
+}
+
 // block partial sum -> one atomicAdd per block into pot[replica]
 __device__ __forceinline__ void accumulate_potential(float v, float* pot) {
     __shared__ float sc[32];
@@ -804,6 +811,38 @@ template <bool RAMA> struct PlacementNode : CoordNode {
             RAMA ? rama->n_elem : 0, nx, ny);
     }
     std::vector<float> get_param() const override { return h_data; }
+    // placement.cpp:138-161: sensitivity of every element rotated back into the reference frame, summed per layer
+    // (the Rama-dependent placements return nothing, :95-97)
+    std::vector<float> get_param_deriv(int replica) override {
+        if (RAMA) return {};
+        if (replica >= engine->n_rep) throw std::string("replica out of range");
+        engine->sync_and_check();
+        const int r0 = replica < 0 ? 0 : replica, r1 = replica < 0 ? engine->n_rep : replica + 1;
+        auto sn = download_rows(*this, sens, r0, r1);
+        auto af = download_rows(alignment, alignment.output, r0, r1);
+        auto ar = affine_residue.download();
+        auto li = layer.download();
+        std::vector<float> deriv(h_data.size(), 0.f);
+        for (int r = 0; r < r1 - r0; ++r)
+            for (int i = 0; i < n_elem; ++i) {
+                const float* a = &af[(size_t(r) * alignment.n_elem + ar[i]) * 8];
+                const float q0 = a[3], q1 = a[4], q2 = a[5], q3 = a[6];
+                const float U[9] = {q0 * q0 + q1 * q1 - q2 * q2 - q3 * q3, 2.f * (q1 * q2 - q0 * q3), 2.f * (q1 * q3 + q0 * q2),
+                                    2.f * (q1 * q2 + q0 * q3), q0 * q0 - q1 * q1 + q2 * q2 - q3 * q3, 2.f * (q2 * q3 - q0 * q1),
+                                    2.f * (q1 * q3 - q0 * q2), 2.f * (q2 * q3 + q0 * q1), q0 * q0 - q1 * q1 - q2 * q2 + q3 * q3};
+                const float* s = &sn[(size_t(r) * n_elem + i) * wp];
+                float* d = &deriv[size_t(li[i]) * sig.n_dim];
+                int off = 0;
+                for (int b = 0; b < sig.n_block; ++b) {
+                    if (sig.type[b] == P_SCALAR) { d[off] += s[off]; off += 1; }
+                    else {   // U^T s
+                        for (int c = 0; c < 3; ++c) d[off + c] += U[c] * s[off] + U[3 + c] * s[off + 1] + U[6 + c] * s[off + 2];
+                        off += 3;
+                    }
+                }
+            }
+        return deriv;
+    }
     void set_param(const std::vector<float>& p) override {
         if (RAMA) return;
         if (p.size() != h_data.size()) throw std::string("wrong param size");
@@ -922,6 +961,32 @@ struct NonlinearCoupling : PotentialNode {
             mode == PotentialAndDerivMode);
     }
     std::vector<float> get_param() const override { return h_coeff; }
+    // environment.cpp:375-390: d/d(coeff) = the four basis weights of each residue's knot interval (clamped spline)
+    std::vector<float> get_param_deriv(int replica) override {
+        if (replica >= engine->n_rep) throw std::string("replica out of range");
+        engine->sync_and_check();
+        const int r0 = replica < 0 ? 0 : replica, r1 = replica < 0 ? engine->n_rep : replica + 1;
+        auto x = download_rows(input, input.output, r0, r1);
+        auto t = types.download();
+        std::vector<float> deriv(h_coeff.size(), 0.f);
+        for (int r = 0; r < r1 - r0; ++r)
+            for (int ne = 0; ne < input.n_elem; ++ne) {
+                const float c = (x[(size_t(r) * input.n_elem + ne) * input.wp] - offset) * inv_dx;
+                int bin;
+                float w[4];
+                if (c <= 1.f) { bin = 0; w[0] = 1.f / 6.f; w[1] = 2.f / 3.f; w[2] = 1.f / 6.f; w[3] = 0.f; }
+                else if (c >= float(n_coeff - 2)) { bin = n_coeff - 4; w[0] = 0.f; w[1] = 1.f / 6.f; w[2] = 2.f / 3.f; w[3] = 1.f / 6.f; }
+                else {
+                    const int b = (int)c;
+                    const float y = c - b, z = 1.f - y;
+                    bin = b - 1;
+                    w[0] = z * z * z / 6.f; w[3] = y * y * y / 6.f;
+                    w[1] = (3.f * y * y * y - 6.f * y * y + 4.f) / 6.f; w[2] = (3.f * z * z * z - 6.f * z * z + 4.f) / 6.f;
+                }
+                for (int i = 0; i < 4; ++i) deriv[size_t(t[ne]) * n_coeff + bin + i] += w[i];
+            }
+        return deriv;
+    }
     void set_param(const std::vector<float>& p) override {
         if (p.size() != h_coeff.size()) throw std::string("attempting to change size of coeff vector on set_param");
         h_coeff = p;
@@ -963,6 +1028,14 @@ struct HBondEnergy : PotentialNode {
                                                                    n, Ep, mode == PotentialAndDerivMode);
     }
     std::vector<float> get_param() const override { return {Ep}; }
+    std::vector<float> get_param_deriv(int replica) override {   // hbond.cpp:447-449: dE/dE_hb = number of H-bonds
+        if (replica >= engine->n_rep) throw std::string("replica out of range");
+        engine->sync_and_check();
+        auto v = n_hbond.download();
+        float tot = 0.f;
+        for (int r = 0; r < engine->n_rep; ++r) if (replica < 0 || r == replica) tot += v[r];
+        return {tot};
+    }
     void set_param(const std::vector<float>& p) override {
         if (p.size() != 1u) throw "expected 1 param to hbond_energy but got " + std::to_string(p.size());
         Ep = p[0];

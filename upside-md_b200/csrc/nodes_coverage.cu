@@ -156,6 +156,29 @@ __global__ void __launch_bounds__(CTPB) k_hbond_coverage_deriv(IGraphDev g, Quad
         }
     }
 }
+// parameter derivative (interaction_graph.h:404-415 with hbond.cpp:278-283): sum over edges of
+// sens[bead] * (1-hb)^2 * d(quadspline)/d(param); off the hot path, one thread per bead row, atomics into the table
+__global__ void k_hbond_coverage_param_deriv(IGraphDev g, QuadSplineShape q, const float* __restrict__ sens, int r0, int r1,
+                                             float* __restrict__ out) {
+    const int r = r0 + blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= r1 || j >= g.s2.n) return;
+    const float sj = sens[size_t(r) * g.s2.n + j];
+    const int c = g.cnt2[size_t(r) * g.s2.n + j];
+    if (!c || sj == 0.f) return;
+    float x2[8];
+    load8(elem_ptr(g.s2, r, j), x2);
+    const unsigned short* row = g.nbr2 + (size_t(r) * g.s2.n + j) * g.K2;
+    for (int k = 0; k < c; ++k) {
+        const int i = row[k];
+        float x1[8], val[16];
+        int idx[16];
+        load8(elem_ptr(g.s1, r, i), x1);
+        const int tp = g.s1.type[i] * g.n_type2 + g.s2.type[j];
+        quadspline_param_deriv(g.param + size_t(tp) * g.n_param, q, x1, x2, idx, val);
+        const float w = sj * (1.f - x1[6]) * (1.f - x1[6]);
+        for (int m = 0; m < 16; ++m) atomicAdd(out + size_t(tp) * g.n_param + idx[m], w * val[m]);
+    }
+}
 struct HBondCoverage : CoordNode {
     IGraphHost ig;
     int nka = 15, nk = 12;
@@ -190,6 +213,19 @@ struct HBondCoverage : CoordNode {
     bool get_pairlist(int replica, std::vector<int>& i1, std::vector<int>& i2) override { return ig.pairlist(replica, i1, i2); }
     std::vector<float> get_param() const override { return ig.h_param; }
     void set_param(const std::vector<float>& p) override { ig.set_param(p); }
+    std::vector<float> get_param_deriv(int replica) override {
+        if (replica >= engine->n_rep) throw std::string("replica out of range");
+        engine->sync_and_check();
+        DevBuf<float> acc;
+        acc.upload(std::vector<float>(ig.h_param.size(), 0.f));
+        const int r0 = replica < 0 ? 0 : replica, r1 = replica < 0 ? engine->n_rep : replica + 1;
+        for (int a = r0; n_elem && a < r1; a += 32768) {
+            const int b = std::min(r1, a + 32768);
+            k_hbond_coverage_param_deriv<<<dim3((ig.n2 + 127) / 128, b - a), 128>>>(ig.dev(), shape(), sens, a, b, acc.p);
+        }
+        UB_CUDA(cudaDeviceSynchronize());
+        return acc.download();
+    }
     std::vector<float> get_value_by_name(int replica, const char* nm) override {
         if (std::string(nm) == "count_edges_by_type") return ig.count_edges_by_type(replica);
         throw std::string("Value ") + nm + " not implemented";
@@ -295,6 +331,8 @@ struct EnvironmentCoverage : CoordNode {
     bool get_pairlist(int replica, std::vector<int>& i1, std::vector<int>& i2) override { return ig.pairlist(replica, i1, i2); }
     std::vector<float> get_param() const override { return ig.h_param; }
     void set_param(const std::vector<float>& p) override { ig.set_param(p); }   // a cutoff change needs a new engine
+    // the reference leaves this derivative unimplemented and returns zeros (environment.cpp:62-65)
+    std::vector<float> get_param_deriv(int) override { return std::vector<float>(ig.h_param.size(), 0.f); }
 };
 RegisterNodeType<EnvironmentCoverage, 2> environment_coverage_node("environment_coverage");
 

@@ -1136,6 +1136,30 @@ __global__ void __launch_bounds__(BP2_TPB, BP2_OCC) k_rot_bp2(RotamerDev P, Bp2L
     }
 }
 
+// parameter derivative (interaction_graph.h:404-415 with bead_interaction.h:204-207): sum over bead pairs (i<j, the
+// reference's edge orientation) of the backward weight ss[e] (pair marginal / node marginal / 1) times
+// d(quadspline)/d(param) of the ordered type pair; off the hot path, one thread per CSR row, atomics into the table
+__global__ void k_rot_param_deriv(RotamerDev P, int r0, int r1, float* __restrict__ out) {
+    const int r = r0 + blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= r1 || i >= P.n_bead) return;
+    const int* rowstart = P.rowstart + size_t(r) * (P.n_bead + 1);
+    const unsigned short* dj = P.dj + size_t(r) * P.cap_e;
+    const float* ss = P.ss + size_t(r) * P.cap_e;
+    float x1[8];
+    load8(elem_ptr(P.g.s1, r, i), x1);
+    for (int e = rowstart[i]; e < rowstart[i + 1]; ++e) {
+        const int j = dj[e];
+        if (j <= i) continue;
+        float x2[8], val[16];
+        int idx[16];
+        load8(elem_ptr(P.g.s1, r, j), x2);
+        const int tp = P.g.s1.type[i] * P.g.n_type2 + P.g.s1.type[j];
+        quadspline_param_deriv(P.g.param + size_t(tp) * P.g.n_param, P.q, x1, x2, idx, val);
+        const float w = ss[e];
+        for (int m = 0; m < 16; ++m) atomicAdd(out + size_t(tp) * P.g.n_param + idx[m], w * val[m]);
+    }
+}
+
 struct RotamerSidechain : PotentialNode {
     std::vector<CoordNode*> prob_nodes;
     IGraphHost ig;
@@ -1372,6 +1396,19 @@ struct RotamerSidechain : PotentialNode {
     bool get_pairlist(int replica, std::vector<int>& i1, std::vector<int>& i2) override { return ig.pairlist(replica, i1, i2); }
     std::vector<float> get_param() const override { return ig.h_param; }
     void set_param(const std::vector<float>& p) override { ig.set_param(p); upload_table(); }
+    std::vector<float> get_param_deriv(int replica) override {
+        if (replica >= engine->n_rep) throw std::string("replica out of range");
+        engine->sync_and_check();
+        DevBuf<float> acc;
+        acc.upload(std::vector<float>(ig.h_param.size(), 0.f));
+        const int first = replica < 0 ? 0 : replica, last = replica < 0 ? engine->n_rep : replica + 1;
+        for (int r0 = first; ig.n1 && r0 < last; r0 += 32768) {
+            const int r1 = std::min(last, r0 + 32768);
+            k_rot_param_deriv<<<dim3((ig.n1 + 127) / 128, r1 - r0), 128>>>(dev(), r0, r1, acc.p);
+        }
+        UB_CUDA(cudaDeviceSynchronize());
+        return acc.download();
+    }
 
     std::vector<float> get_value_by_name(int replica, const char* log_name) override {
         std::string nm(log_name);

@@ -66,6 +66,7 @@ def lib():
     L.ub_get_value_by_name.argtypes = [ct.c_void_p, ct.c_char_p, ct.c_char_p, ct.c_int, ct.c_int, _fp, _ip]
     L.ub_get_param.argtypes = [ct.c_void_p, ct.c_char_p, ct.c_int, _fp, _ip]
     L.ub_set_param.argtypes = [ct.c_void_p, ct.c_char_p, ct.c_int, _fp]
+    L.ub_get_param_deriv.argtypes = [ct.c_void_p, ct.c_char_p, ct.c_int, ct.c_int, _fp, _ip]
     L.ub_get_pairlist.argtypes = [ct.c_void_p, ct.c_char_p, ct.c_int, ct.c_int, _ip, _ip, _ip]
     L.ub_md_init.argtypes = [ct.c_void_p, ct.c_uint32, _fp, ct.c_float, ct.c_float, ct.c_int]
     L.ub_md_set_temperature.argtypes = [ct.c_void_p, _fp]
@@ -293,6 +294,15 @@ class BatchEngine(object):
         if self.L.ub_get_param(self.e, node.encode(), 0, None, ct.byref(n)): raise _err('get_param')
         a = np.zeros(n.value, dtype='f4')
         if self.L.ub_get_param(self.e, node.encode(), a.size, _f(a), ct.byref(n)): raise _err('get_param')
+        return a
+
+    def get_param_deriv(self, node, replica=0):
+        """dV/d(parameter) of `node` for one replica (replica < 0: summed over the batch) from the state the last
+        evaluate(want_deriv=True) left behind; empty if the node has no parameter derivative"""
+        n = ct.c_int()
+        if self.L.ub_get_param_deriv(self.e, node.encode(), replica, 0, None, ct.byref(n)): raise _err('get_param_deriv')
+        a = np.zeros(n.value, dtype='f4')
+        if n.value and self.L.ub_get_param_deriv(self.e, node.encode(), replica, a.size, _f(a), ct.byref(n)): raise _err('get_param_deriv')
         return a
 
     def set_param(self, node, param):
