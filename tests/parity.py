@@ -147,7 +147,7 @@ def compare_engines(cfg, pos, verbose=True):
         n_node = int(ref.get_value_by_name('rotamer', 'n_node', 1)[0])
         n_prob = len(h5lite.load(cfg)['input/potential/rotamer'].attrs['arguments']) - 1
         rep['accessors'] = {}
-        for nm, n in (('rotamer_1body_energy', n_node * n_prob), ('node_energy', n_node * 6)):
+        for nm, n in (('rotamer_1body_energy', n_node * n_prob), ('node_energy', n_node * 6), ('rotamer_free_energy', n_node)):
             a, b = be.get_value_by_name('rotamer', nm, r), ref.get_value_by_name('rotamer', nm, n)
             rep['accessors'][nm] = (a.shape == b.shape, float(np.abs(a - b).max()) if a.shape == b.shape else np.inf,
                                     float(np.abs(b[b < 1e4]).max()))

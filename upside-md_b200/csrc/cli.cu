@@ -139,6 +139,7 @@ bool tree_equal(const h5l::Node& a, const h5l::Node& b) {
 }
 
 struct Group {   // configuration files that share one batched engine
+    vector<ub::NodeLogger> loggers;   // node loggers of the requested --log-level
     std::unique_ptr<ub::Engine> engine;
     vector<int> systems;   // slot r of the engine = system systems[r]
     const h5l::Node* potential = nullptr;
@@ -155,6 +156,9 @@ struct System {
     vector<double> kinetic, potential, time, temperature_log;
     vector<int> replica_index, cumulative_swaps;
     std::map<string, vector<int>> mc_stats;   // "<sampler>_stats": (n_success, n_attempt) since the previous frame
+    // node loggers of --log-level detailed (state_logger.h:56-66): name -> (per-frame shape, int64?, samples)
+    struct Series { vector<uint64_t> dims; bool integer = false; vector<float> data; };
+    std::map<string, Series> node_series;
     size_t n_frame = 0;
 };
 
@@ -174,6 +178,12 @@ void write_output(System& sys, const string& invocation, bool have_replex, const
     put("time", h5l::make_array(sys.time, {nf}));
     put("temperature", h5l::make_array(sys.temperature_log, {nf, 1}));
     for (auto& kv : sys.mc_stats) put(kv.first.c_str(), h5l::make_array(kv.second, {nf, 2}));   // monte_carlo_sampler.h:31-36
+    for (auto& kv : sys.node_series) {
+        vector<uint64_t> dims{nf};
+        dims.insert(dims.end(), kv.second.dims.begin(), kv.second.dims.end());
+        if (kv.second.integer) put(kv.first.c_str(), h5l::make_array(vector<long>(kv.second.data.begin(), kv.second.data.end()), dims));
+        else put(kv.first.c_str(), h5l::make_array(kv.second.data, dims));
+    }
     if (have_replex) {
         put("replica_index", h5l::make_array(sys.replica_index, {nf, 1}));
         const auto& ps = plan->participating_swaps[ns];
@@ -234,6 +244,9 @@ int run(int argc, const char* const* argv, int verbose) {
     const int mc_interval = args.mc_interval > 0. ? std::max(1, int(args.mc_interval / (3 * dt))) : 0;   // main.cpp:409-411
     if (!args.log_level.empty() && args.log_level != "basic" && args.log_level != "detailed" && args.log_level != "extensive")
         throw string("Illegal value for --log-level");
+    // main.cpp:474-479.  The extensive-only loggers (placement_pos, virtual, environment_coverage) are not offered: with
+    // several placement nodes the reference itself cannot create them (duplicate dataset name).
+    const int log_level = args.log_level == "detailed" ? 1 : (args.log_level == "extensive" ? 2 : 0);
 
     // ---- load the configurations and group identical ones into batched engines --------------------------------------------
     // (errors while setting the systems up return 2, as the reference does: main.cpp:562-573)
@@ -267,6 +280,14 @@ int run(int argc, const char* const* argv, int verbose) {
     for (auto& g : groups) {
         g.engine = ub::initialize_engine_from_hdf5(g.n_atom, *g.potential, (int)g.systems.size(), 0);
         for (const auto& p : set_param_map) g.engine->get(p.first).set_param(p.second);
+        if (log_level > 0)
+            for (auto& n : g.engine->nodes) {
+                const size_t before = g.loggers.size();
+                n.computation->add_loggers(log_level, g.loggers);
+                for (size_t a = before; a < g.loggers.size(); ++a)
+                    for (size_t b = 0; b < a; ++b)   // the reference's H5Logger cannot create a second dataset of the same name
+                        if (g.loggers[a].name == g.loggers[b].name) throw "while adding '" + n.name + "', logger " + g.loggers[a].name + " exists already";
+            }
         vector<float> all_pos;
         vector<float> T;
         vector<uint32_t> seeds;
@@ -424,6 +445,13 @@ int run(int argc, const char* const* argv, int verbose) {
                 sys.potential.push_back(pot[r]);
                 sys.time.push_back(3 * double(dt) * nr);
                 sys.temperature_log.push_back(sys.temperature);
+                for (auto& lg : g.loggers) {
+                    auto& series = sys.node_series[lg.name];
+                    series.dims = lg.dims;
+                    series.integer = lg.integer;
+                    auto v = lg.sample(r);
+                    series.data.insert(series.data.end(), v.begin(), v.end());
+                }
                 if (replex) {
                     sys.replica_index.push_back(replex->replica_indices[ns]);
                     for (auto& ps : replex->participating_swaps[ns]) {

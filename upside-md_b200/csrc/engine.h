@@ -65,6 +65,15 @@ template <typename T> struct DevBuf {
 };
 
 // ---- nodes ----------------------------------------------------------------------------------------------
+// A named per-frame series a node offers to the /output writer of upside_main (reference H5Logger::add_logger,
+// state_logger.h:107-141; registered in the node constructors when logging(level) holds).
+struct NodeLogger {
+    std::string name;
+    std::vector<uint64_t> dims;                              // shape of one frame
+    bool integer = false;                                    // written as int64 (rotamer_bad_solves_cumulative)
+    std::function<std::vector<float>(int replica)> sample;   // called after the frame's evaluation
+};
+
 struct DerivComputation {
     const bool potential_term;
     Engine* engine = nullptr;
@@ -84,6 +93,8 @@ struct DerivComputation {
     virtual std::vector<float> get_value_by_name(int replica, const char* log_name) {
         throw std::string("No values implemented");
     }
+    // loggers of this node at `level` (1 = detailed, 2 = extensive; state_logger.h:56-66)
+    virtual void add_loggers(int level, std::vector<NodeLogger>& out) {}
     // pair list of `replica` built by the last evaluation, in the reference's emission order; false if none
     virtual bool get_pairlist(int replica, std::vector<int>& i1, std::vector<int>& i2) { return false; }
 };
@@ -93,6 +104,12 @@ struct CoordNode : DerivComputation {
     float* output = nullptr;   // [B][n_elem][wp]  (assigned by the engine)
     float* sens = nullptr;     // [B][n_elem][wp]
     size_t stride() const { return size_t(n_elem) * wp; }
+    // host copy of one replica's padded rows of `base` (= output or sens); accessors and loggers only
+    std::vector<float> host_rows(const float* base, int replica) const {
+        std::vector<float> h(stride());
+        if (!h.empty()) UB_CUDA(cudaMemcpy(h.data(), base + size_t(replica) * stride(), h.size() * sizeof(float), cudaMemcpyDeviceToHost));
+        return h;
+    }
     CoordNode(int n_elem_, int elem_width_)
         : DerivComputation(false), n_elem(n_elem_), elem_width(elem_width_), wp(ub_padded_width(elem_width_)) {}
 };

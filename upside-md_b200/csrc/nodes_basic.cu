@@ -54,6 +54,8 @@ struct DistSpring : PotentialNode {
     CoordNode& pos;
     int n_elem;
     DevBuf<SpringParam2> prm;
+    std::vector<SpringParam2> h_prm;
+    std::vector<int> bonded_atoms;
     DistSpring(Engine&, const h5l::Node& g, CoordNode& pos_) : pos(pos_) {
         n_elem = (int)h5_dims(g, "id", 2)[0];
         h5_check_size(g, "id", {(uint64_t)n_elem, 2});
@@ -69,6 +71,25 @@ struct DistSpring : PotentialNode {
             if (h[i].a0 < 0 || h[i].a0 >= pos.n_elem || h[i].a1 < 0 || h[i].a1 >= pos.n_elem) throw std::string("atom index out of range");
         }
         prm.upload(h);
+        h_prm = h;
+        bonded_atoms = h5_read<int>(g, "bonded_atoms");
+    }
+    // bonds.cpp:280-295: energy of the springs that are not covalent bonds
+    void add_loggers(int level, std::vector<NodeLogger>& out) override {
+        if (level < 1) return;
+        out.push_back({"nonbonded_spring_energy", {1}, false, [this](int r) {
+            auto x = pos.host_rows(pos.output, r);
+            float pot = 0.f;
+            for (int nt = 0; nt < n_elem; ++nt) {
+                if (bonded_atoms[nt]) continue;
+                const SpringParam2& p = h_prm[nt];
+                const float* a = &x[size_t(p.a0) * pos.wp];
+                const float* b = &x[size_t(p.a1) * pos.wp];
+                float d = std::sqrt((a[0] - b[0]) * (a[0] - b[0]) + (a[1] - b[1]) * (a[1] - b[1]) + (a[2] - b[2]) * (a[2] - b[2]));
+                pot += 0.5f * p.k * (d - p.equil) * (d - p.equil);
+            }
+            return std::vector<float>{pot};
+        }});
     }
     void compute_value(cudaStream_t s, ComputeMode mode) override {
         if (!n_elem) return;
@@ -260,6 +281,15 @@ struct RamaCoord : CoordNode {
     void compute_value(cudaStream_t s, ComputeMode) override {
         k_rama_coord<<<grid_for(n_elem, engine->n_rep), TPB, 0, s>>>(pos.output, output, prm.p, n_elem, pos.n_elem);
     }
+    void add_loggers(int level, std::vector<NodeLogger>& out) override {   // bonds.cpp:199-202
+        if (level < 1) return;
+        out.push_back({"rama", {(uint64_t)n_elem, 2}, false, [this](int r) {
+            auto o = host_rows(output, r);
+            std::vector<float> v(size_t(n_elem) * 2);
+            for (int i = 0; i < n_elem; ++i) { v[2 * i] = o[size_t(i) * wp]; v[2 * i + 1] = o[size_t(i) * wp + 1]; }
+            return v;
+        }});
+    }
     void propagate_deriv(cudaStream_t s) override {
         k_rama_coord_deriv<<<grid_for(n_elem, engine->n_rep), TPB, 0, s>>>(pos.output, pos.sens, sens, prm.p, n_elem, pos.n_elem);
     }
@@ -327,7 +357,9 @@ struct RamaMapPot : PotentialNode {
     int n_residue, n_layer, nx;
     DevBuf<int> residue, map_id;
     DevBuf<float> coeff, residue_pot;
+    bool log_pot = true;   // attribute log_pot = 0: never log the per-residue potential (rama_map_pot.cpp:22,34)
     RamaMapPot(Engine&, const h5l::Node& g, CoordNode& rama_) : rama(rama_) {
+        if (g.attrs.count("log_pot")) log_pot = h5_attr<int>(g, ".", "log_pot") != 0;
         check_elem_width(rama, 2);
         n_residue = (int)h5_dims(g, "residue_id", 1)[0];
         auto d = h5_dims(g, "rama_pot", 3);
@@ -352,6 +384,14 @@ struct RamaMapPot : PotentialNode {
         k_rama_map_pot<<<grid_for(n_residue, engine->n_rep), TPB, 0, s>>>(rama.output, rama.sens, potential, residue_pot.p,
                                                                            residue.p, map_id.p, coeff.p, n_residue,
                                                                            rama.n_elem, nx, mode == PotentialAndDerivMode);
+    }
+    void add_loggers(int level, std::vector<NodeLogger>& out) override {   // rama_map_pot.cpp:50-54
+        if (level < 1 || !log_pot) return;
+        out.push_back({"rama_map_potential", {(uint64_t)n_residue}, false, [this](int r) {
+            std::vector<float> v(n_residue);
+            if (n_residue) UB_CUDA(cudaMemcpy(v.data(), residue_pot.p + size_t(r) * n_residue, v.size() * sizeof(float), cudaMemcpyDeviceToHost));
+            return v;
+        }});
     }
     void set_param(const std::vector<float>& p) override {
         if (p.size() != size_t(n_layer) * nx * nx) throw std::string("wrong number of parameters");
@@ -961,6 +1001,32 @@ struct NonlinearCoupling : PotentialNode {
             mode == PotentialAndDerivMode);
     }
     std::vector<float> get_param() const override { return h_coeff; }
+    // clamped cubic B-spline: first coefficient and the four basis weights at coordinate c (spline.h:318-336,375-392)
+    void basis(float c, int& bin, float* w) const {
+        if (c <= 1.f) { bin = 0; w[0] = 1.f / 6.f; w[1] = 2.f / 3.f; w[2] = 1.f / 6.f; w[3] = 0.f; return; }
+        if (c >= float(n_coeff - 2)) { bin = n_coeff - 4; w[0] = 0.f; w[1] = 1.f / 6.f; w[2] = 2.f / 3.f; w[3] = 1.f / 6.f; return; }
+        const int b = (int)c;
+        const float y = c - b, z = 1.f - y;
+        bin = b - 1;
+        w[0] = z * z * z / 6.f; w[3] = y * y * y / 6.f;
+        w[1] = (3.f * y * y * y - 6.f * y * y + 4.f) / 6.f; w[2] = (3.f * z * z * z - 6.f * z * z + 4.f) / 6.f;
+    }
+    void add_loggers(int level, std::vector<NodeLogger>& out) override {   // environment.cpp:348-355: energy per residue
+        if (level < 1) return;
+        out.push_back({"nonlinear_coupling", {(uint64_t)input.n_elem}, false, [this](int r) {
+            auto x = input.host_rows(input.output, r);
+            auto t = types.download();
+            std::vector<float> v(input.n_elem);
+            for (int ne = 0; ne < input.n_elem; ++ne) {
+                int bin;
+                float w[4];
+                basis((x[size_t(ne) * input.wp] - offset) * inv_dx, bin, w);
+                const float* c = &h_coeff[size_t(t[ne]) * n_coeff + bin];
+                v[ne] = w[0] * c[0] + w[1] * c[1] + w[2] * c[2] + w[3] * c[3];
+            }
+            return v;
+        }});
+    }
     // environment.cpp:375-390: d/d(coeff) = the four basis weights of each residue's knot interval (clamped spline)
     std::vector<float> get_param_deriv(int replica) override {
         if (replica >= engine->n_rep) throw std::string("replica out of range");
@@ -974,15 +1040,7 @@ struct NonlinearCoupling : PotentialNode {
                 const float c = (x[(size_t(r) * input.n_elem + ne) * input.wp] - offset) * inv_dx;
                 int bin;
                 float w[4];
-                if (c <= 1.f) { bin = 0; w[0] = 1.f / 6.f; w[1] = 2.f / 3.f; w[2] = 1.f / 6.f; w[3] = 0.f; }
-                else if (c >= float(n_coeff - 2)) { bin = n_coeff - 4; w[0] = 0.f; w[1] = 1.f / 6.f; w[2] = 2.f / 3.f; w[3] = 1.f / 6.f; }
-                else {
-                    const int b = (int)c;
-                    const float y = c - b, z = 1.f - y;
-                    bin = b - 1;
-                    w[0] = z * z * z / 6.f; w[3] = y * y * y / 6.f;
-                    w[1] = (3.f * y * y * y - 6.f * y * y + 4.f) / 6.f; w[2] = (3.f * z * z * z - 6.f * z * z + 4.f) / 6.f;
-                }
+                basis(c, bin, w);
                 for (int i = 0; i < 4; ++i) deriv[size_t(t[ne]) * n_coeff + bin + i] += w[i];
             }
         return deriv;

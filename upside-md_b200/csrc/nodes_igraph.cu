@@ -286,6 +286,15 @@ struct ProteinHBond : CoordNode {
     bool get_pairlist(int replica, std::vector<int>& i1, std::vector<int>& i2) override { return ig.pairlist(replica, i1, i2); }
     std::vector<float> get_param() const override { return ig.h_param; }
     void set_param(const std::vector<float>& p) override { ig.set_param(p); }
+    void add_loggers(int level, std::vector<NodeLogger>& out) override {   // hbond.cpp:306-311: H-bond fraction per site
+        if (level < 1) return;
+        out.push_back({"hbond", {(uint64_t)n_virtual}, false, [this](int r) {
+            auto o = host_rows(output, r);
+            std::vector<float> v(n_virtual);
+            for (int i = 0; i < n_virtual; ++i) v[i] = o[size_t(i) * wp + 6];
+            return v;
+        }});
+    }
 };
 RegisterNodeType<ProteinHBond, 1> protein_hbond_node("protein_hbond");
 

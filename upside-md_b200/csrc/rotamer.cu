@@ -76,6 +76,10 @@ struct RotamerDev {
     int* n_bad;               // [B] solves that hit max_iter without converging (n_bad_solve, rotamer.cpp:604,785)
     int* slow_list;           // [B] replicas the fast BP kernel declined
     int* n_slow;              // [1] (reset by k_rot_prep)
+    // per-residue free energy (residue_free_energies, rotamer.cpp:868-902): node term + half of every incident pair term;
+    // only filled while *fe_flag != 0 (logging runs and the rotamer_free_energy accessor)
+    float* res_fe;            // [B][n_res]
+    const int* fe_flag;       // [1]
     int n_rep;
     float* potential;
     int* error_flag;
@@ -209,6 +213,7 @@ __global__ void __launch_bounds__(PREP_TPB) k_rot_prep(RotamerDev P) {
     const int n_pair = estart[nR];
     if (tid == 0) { P.stats[size_t(r) * 4 + 1] = n_pair; P.e11[r] = 0.f; }
     if (tid == 0 && r == 0) *P.n_slow = 0;
+    if (*P.fe_flag) for (int A = tid; A < nR; A += PREP_TPB) P.res_fe[size_t(r) * nR + A] = 0.f;
     int* rowstart = P.rowstart + size_t(r) * (nb + 1);
     if (n_pair > P.max_pairs || rs[nb] > P.cap_e) {   // uniform across the block: report, and leave an empty graph behind
         if (tid == 0) { atomicExch(P.error_flag, n_pair > P.max_pairs ? 2 : 3); P.stats[size_t(r) * 4 + 1] = 0; }
@@ -399,6 +404,7 @@ __global__ void __launch_bounds__(EDGE_TPB, 3) k_rot_energy(RotamerDev P, int wa
     const PairTab T{table, rowoff};
     const int nb = P.n_bead;
     stage_table(P, table, rowoff);
+    const bool fe_on = want_pot && *P.fe_flag;
     for (int r = blockIdx.y; r < n_rep; r += gridDim.y) {
         __syncthreads();   // previous replica's readers are done with `beads`
         stage_beads(P, r, beads);
@@ -436,7 +442,13 @@ __global__ void __launch_bounds__(EDGE_TPB, 3) k_rot_energy(RotamerDev P, int wa
                     else if (cd < 0 && !code_is_fold(cd)) continue;   // (single, multi): handled from the partner's row
                     const float V = pair_term<false, NKA, NK>(P, T, bi, beads[js[u]], nullptr, nullptr);
                     if (cd >= 0) { if (P.multi_bead_states) atomicAdd(&pmat[cd], V); else pmat[cd] = V; }
-                    else if (cd == CODE_SS) e11 += V;
+                    else if (cd == CODE_SS) {
+                        e11 += V;
+                        if (fe_on) {   // edges11: half to each residue (rotamer.cpp:877-881)
+                            atomicAdd(&P.res_fe[size_t(r) * P.n_res + (bi.res_rot >> 3)], 0.5f * V);
+                            atomicAdd(&P.res_fe[size_t(r) * P.n_res + (beads[js[u]].res_rot >> 3)], 0.5f * V);
+                        }
+                    }
                     else fold += V;
                 }
             }
@@ -635,6 +647,7 @@ __global__ void __launch_bounds__(BP_TPB) k_rot_bp(RotamerDev P, int want_pot, i
 __device__ void bp_solve_generic(const RotamerDev& P, int want_pot, int r, float* smem) {
     const int tid = threadIdx.x;
     const int nR = P.n_res, SP = P.smem_pairs;
+    const bool fe_on = want_pot && *P.fe_flag;
     const int n_pair = P.stats[size_t(r) * 4 + 1];
     float* prob = smem;                         // [nR][6]
     float* bel = prob + nR * MAXR;              // [nR][6]
@@ -741,6 +754,7 @@ __device__ void bp_solve_generic(const RotamerDev& P, int want_pot, int r, float
             float e = offs[A];
             for (int a = 0; a < nA; ++a) e += b[a] * __logf((1e-10f + b[a]) / (1e-10f + prob[A * MAXR + a]));
             en += e;
+            if (fe_on) atomicAdd(&P.res_fe[size_t(r) * nR + A], e);
         }
     }
     __syncthreads();
@@ -755,15 +769,17 @@ __device__ void bp_solve_generic(const RotamerDev& P, int want_pot, int r, float
         float* out = g_pmat + size_t(e) * 36;
         float s = 0.f;
         for (int a = 0; a < nA; ++a) for (int b = 0; b < nB; ++b) s += Pm[at(lp, e, a * 6 + b)] * bc1[a] * bc2[b];
-        float is = 1.f / s;
+        float is = 1.f / s, en_pair = 0.f;
         for (int a = 0; a < MAXR; ++a)
             for (int b = 0; b < MAXR; ++b) {
                 float pr = Pm[at(lp, e, a * 6 + b)];
                 float mg = (a < nA && b < nB) ? pr * bc1[a] * bc2[b] * is : 0.f;
                 if (want_pot && a < nA && b < nB)
-                    en += mg * __logf((1e-10f + mg) / (1e-10f + pr * bel[A * MAXR + a] * bel[Bq * MAXR + b]));
+                    en_pair += mg * __logf((1e-10f + mg) / (1e-10f + pr * bel[A * MAXR + a] * bel[Bq * MAXR + b]));
                 out[a * 6 + b] = mg;
             }
+        en += en_pair;
+        if (fe_on) { atomicAdd(&P.res_fe[size_t(r) * nR + A], 0.5f * en_pair); atomicAdd(&P.res_fe[size_t(r) * nR + Bq], 0.5f * en_pair); }
     }
     __syncthreads();   // this CTA's global writes of the pair marginals are visible to all its threads
     emit_entry_weights(P, r, BP_TPB, [&](int cd) { return g_pmat[cd]; }, [&](int node) { return bel[node]; });
@@ -902,6 +918,7 @@ __global__ void __launch_bounds__(BP2_TPB, BP2_OCC) k_rot_bp2(RotamerDev P, Bp2L
     extern __shared__ float smem[];
     const int r = blockIdx.x, tid = threadIdx.x;
     const int nR = P.n_res, nRp = L.nRp, SP = L.SP;
+    const bool fe_on = want_pot && *P.fe_flag;
     const int n_pair = P.stats[size_t(r) * 4 + 1];
     float* prob = smem;                          // [6][nRp]
     float* bel = prob + 6 * nRp;                 // [6][nRp]
@@ -1108,14 +1125,18 @@ __global__ void __launch_bounds__(BP2_TPB, BP2_OCC) k_rot_bp2(RotamerDev P, Bp2L
             float e = offs[A];
             for (int k = 0; k < nA; ++k) e += b[k] * __logf((1e-10f + b[k]) / (1e-10f + prob[k * nRp + A]));
             en += e;
+            if (fe_on) atomicAdd(&P.res_fe[size_t(r) * nR + A], e);
         }
     }
     __syncthreads();
     for (int p = tid; p < n_pair; p += BP2_TPB) {
         const int F = fs[2 * p] & 0x7fff, S = fs[2 * p + 1];
-        if (p < n66) en += bp2_pair_marginal<6, 6>(bel, nRp, F, S, msg, SP, p, P66, n66, p, want_pot);
-        else if (p < n66 + n36) en += bp2_pair_marginal<3, 6>(bel, nRp, F, S, msg, SP, p, P36, n36, p - n66, want_pot);
-        else en += bp2_pair_marginal<3, 3>(bel, nRp, F, S, msg, SP, p, P33, n33, p - n66 - n36, want_pot);
+        float en_pair;
+        if (p < n66) en_pair = bp2_pair_marginal<6, 6>(bel, nRp, F, S, msg, SP, p, P66, n66, p, want_pot);
+        else if (p < n66 + n36) en_pair = bp2_pair_marginal<3, 6>(bel, nRp, F, S, msg, SP, p, P36, n36, p - n66, want_pot);
+        else en_pair = bp2_pair_marginal<3, 3>(bel, nRp, F, S, msg, SP, p, P33, n33, p - n66 - n36, want_pot);
+        en += en_pair;
+        if (fe_on) { atomicAdd(&P.res_fe[size_t(r) * nR + F], 0.5f * en_pair); atomicAdd(&P.res_fe[size_t(r) * nR + S], 0.5f * en_pair); }
     }
     __syncthreads();
     // backward-pass weight of every bead-pair entry, read from the marginals while they are in shared memory
@@ -1176,7 +1197,9 @@ struct RotamerSidechain : PotentialNode {
     size_t smem_prep = 0, smem_edge = 0, smem_bp = 0, smem_bp2 = 0;
     Bp2Lay lay2{0, 0, 0};
     bool fast_bp = false;
-    DevBuf<int> slow_list, n_slow, n_bad;
+    DevBuf<int> slow_list, n_slow, n_bad, fe_flag;
+    DevBuf<float> res_fe;
+    bool fe_always = false;   // a logger wants the per-residue free energies at every evaluation
 
     RotamerSidechain(Engine&, const h5l::Node& g, const ArgList& args)
         : prob_nodes(args.begin() + 1, args.end()), ig(h5_child(g, "pair_interaction"), true, EXCL_ROTAMER, 6, 6, args[0], nullptr) {
@@ -1293,6 +1316,8 @@ struct RotamerSidechain : PotentialNode {
         slow_list.alloc(B);
         n_bad.upload(std::vector<int>(B, 0));
         n_slow.alloc(1);
+        fe_flag.upload(std::vector<int>(1, 0));
+        res_fe.alloc(B * n_res);
         pmat.alloc(B * max_pairs * 36);
         pair_ab.alloc(B * max_pairs * 2);
         inc.alloc(B * 2 * max_pairs);
@@ -1365,6 +1390,7 @@ struct RotamerSidechain : PotentialNode {
         P.enode = enode.p; P.fold = fold.p; P.e11 = e11.p;
         P.pmat = pmat.p; P.pair_ab = pair_ab.p; P.inc = inc.p; P.istart = istart.p; P.node_marg = node_marg.p; P.stats = stats.p;
         P.potential = potential; P.error_flag = engine->error_flag.p;
+        P.res_fe = res_fe.p; P.fe_flag = fe_flag.p;
         P.slow_list = slow_list.p; P.n_slow = n_slow.p; P.n_bad = n_bad.p; P.n_rep = engine->n_rep;
         return P;
     }
@@ -1410,6 +1436,24 @@ struct RotamerSidechain : PotentialNode {
         return acc.download();
     }
 
+    void set_fe_flag(int v) { UB_CUDA(cudaMemcpy(fe_flag.p, &v, sizeof(int), cudaMemcpyHostToDevice)); }
+    // rotamer.cpp:657-672: cumulative bad solves, free energy per residue, marginal-weighted 1-body energy per residue
+    // and probability node.  The free energies are accumulated by the kernels themselves from now on (fe_flag).
+    void add_loggers(int level, std::vector<NodeLogger>& out) override {
+        if (level < 1) return;
+        fe_always = true;
+        set_fe_flag(1);
+        out.push_back({"rotamer_bad_solves_cumulative", {1}, true, [this](int r) { return get_value_by_name(r, "read n_bad_solve"); }});
+        out.push_back({"rotamer_free_energy", {(uint64_t)n_res}, false, [this](int r) { return get_value_by_name(r, "rotamer_free_energy"); }});
+        const int n_prob = (int)prob_nodes.size();
+        for (int p = 0; p < n_prob; ++p)
+            out.push_back({"rotamer_1body_energy" + std::to_string(p), {(uint64_t)n_res}, false, [this, p, n_prob](int r) {
+                auto all = get_value_by_name(r, "rotamer_1body_energy");
+                std::vector<float> v(n_res);
+                for (int i = 0; i < n_res; ++i) v[i] = all[size_t(i) * n_prob + p];
+                return v;
+            }});
+    }
     std::vector<float> get_value_by_name(int replica, const char* log_name) override {
         std::string nm(log_name);
         engine->sync_and_check();
@@ -1441,6 +1485,15 @@ struct RotamerSidechain : PotentialNode {
             UB_CUDA(cudaMemcpy(v.data(), p, n * sizeof(float), cudaMemcpyDeviceToHost));
             return v;
         };
+        if (nm == "rotamer_free_energy") {   // residue_free_energies (:868-902): filled by the kernels while fe_flag is set
+            if (!fe_always) {
+                set_fe_flag(1);
+                engine->compute(PotentialAndDerivMode);
+                engine->sync_and_check();
+                set_fe_flag(0);
+            }
+            return download(res_fe.p + size_t(replica) * n_res, n_res);
+        }
         if (nm == "rotamer_1body_energy") {   // marginal-weighted 1-body energy per residue and probability node (:680-691,904-927)
             std::vector<float> nmg = download(node_marg.p + size_t(replica) * n_res * MAXR, size_t(n_res) * MAXR);
             const int n_prob = (int)prob_nodes.size();
