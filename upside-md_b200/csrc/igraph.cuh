@@ -183,8 +183,13 @@ __device__ __forceinline__ void refine_rows(int r, const RefineRole& R, float cu
         const int c = F.c;
         const uint4* cs = reinterpret_cast<const uint4*>(T.cand + size_t(r) * T.Kc * nA) + i;
         unsigned short* row = T.nbr + (size_t(r) * nA + i) * T.K;   // 16-byte aligned (K is a multiple of 8)
-        int n = 0;
-        const int n_slice = (c + 7) >> 3, last = T.K - 1;
+        // the row base stays in one register pair (a store address is then one IMAD.WIDE) and the stores are st.global, which
+        // the compiler may move across the shared-memory position loads
+        unsigned long long rowp = (unsigned long long)__cvta_generic_to_global(row);
+        asm volatile("" : "+l"(rowp));
+        unsigned n = 0;
+        const int n_slice = (c + 7) >> 3;
+        const unsigned last = T.K - 1;
         // slices are fetched four at a time (independent 16-byte loads: one memory round trip per 32 candidates)
         for (int s0 = 0; s0 < n_slice; s0 += 4) {
             uint4 v[4];
@@ -203,19 +208,24 @@ __device__ __forceinline__ void refine_rows(int r, const RefineRole& R, float cu
                     const float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
                     const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
                     const bool hit = d2 < cutoff2;
-                    if (hit) row[min(n, last)] = (unsigned short)j;   // predicated store; an overflowing row is reported below
-                    n += hit;
+                    if (hit) {   // predicated store; an overflowing row is reported below
+                        asm volatile("st.global.u16 [%0], %1;" :: "l"(rowp + 2ull * min(n, last)), "h"((unsigned short)j));
+                        ++n;
+                    }
                 }
             }
         }
-        if (n > T.K) { atomicExch(error_flag, 1); n = T.K; }
-        T.cnt[size_t(r) * nA + i] = n;
+        if (n > (unsigned)T.K) { atomicExch(error_flag, 1); n = T.K; }
+        T.cnt[size_t(r) * nA + i] = (int)n;
     }
 }
 
 // `which`: bit 0 = refine table 1, bit 1 = refine the transposed table (two groups only)
+#ifndef UB_REFINE_OCC
+#define UB_REFINE_OCC 3
+#endif
 template <int G>
-__global__ void k_refine(IGraphSide A, IGraphSide Bs, int two_groups, int which, RefineTable T1, RefineTable T2, float cutoff2, int* error_flag) {
+__global__ void __launch_bounds__(256, UB_REFINE_OCC) k_refine(IGraphSide A, IGraphSide Bs, int two_groups, int which, RefineTable T1, RefineTable T2, float cutoff2, int* error_flag) {
     extern __shared__ float4 sm_pos[];
     const int r = blockIdx.x;
     float4* posA = sm_pos;                                  // [A.n + 1], last = sentinel
