@@ -60,6 +60,34 @@ __device__ __forceinline__ void scan_row_lengths(int n, LenF len, int* start, in
     __syncthreads();
 }
 
+// the same scan, in place: start[0..n) holds the row lengths on entry (written by any threads, visible after a barrier
+// the caller has already passed); no global memory is touched
+__device__ __forceinline__ void scan_row_lengths_inplace(int n, int* start, int* wtot) {
+    const int T = blockDim.x, t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const int per = (n + T - 1) / T;
+    const int r0 = min(n, t * per), r1 = min(n, r0 + per);
+    int s = 0;
+    for (int r = r0; r < r1; ++r) s += start[r];
+    int incl = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(UB_FULL_MASK, incl, o); if (lane >= o) incl += v; }
+    if (lane == 31) wtot[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+        int nw = (T + 31) >> 5;
+        int v = lane < nw ? wtot[lane] : 0, iv = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int u = __shfl_up_sync(UB_FULL_MASK, iv, o); if (lane >= o) iv += u; }
+        wtot[lane] = iv - v;
+        if (lane == 31) wtot[32] = iv;
+    }
+    __syncthreads();
+    int run = wtot[w] + incl - s;
+    for (int r = r0; r < r1; ++r) { const int len = start[r]; start[r] = run; run += len; }
+    if (t == 0) start[n] = wtot[32];
+    __syncthreads();
+}
+
 // Evaluate `edge(row, partner, out[NV])` once per edge of rows [0,n) and hand every row the sum over its edges:
 // `row_done(row, n_edges_of_row, sum[NV])` is called by exactly one thread per row (also for empty rows).
 // nbr/K: the replica's ELL table for these rows; start: scan_row_lengths of the lengths to use (a caller may zero rows).

@@ -21,6 +21,7 @@ struct StagedGroup {
     float4* a;   // x,y,z,w0
     float4* b;   // w1..w4
     int* type;
+    int* loc;    // element -> row of the parent node's output (replica independent, staged once)
 };
 
 // carve `n1`+`n2` staged elements and `n_tab` table floats out of dynamic shared memory; returns the first free byte
@@ -31,44 +32,81 @@ __device__ __forceinline__ void* carve_groups(const IGraphDev& g, float4* smem, 
     table = reinterpret_cast<float*>(S2.b + g.s2.n);
     S1.type = reinterpret_cast<int*>(table + ((n_tab + 3) & ~3));
     S2.type = S1.type + g.s1.n;
-    return S1.type + ((g.s1.n + g.s2.n + 3) & ~3);
+    S1.loc = S2.type + g.s2.n;
+    S2.loc = S1.loc + g.s1.n;
+    return S1.type + ((2 * (g.s1.n + g.s2.n) + 3) & ~3);
 }
 // parameter table and element types do not depend on the replica: staged once per (persistent) CTA
 __device__ __forceinline__ void stage_table(const IGraphDev& g, const StagedGroup& S1, const StagedGroup& S2, float* table, int n_tab) {
     for (int i = threadIdx.x; i < n_tab; i += blockDim.x) table[i] = g.param[i];
-    for (int i = threadIdx.x; i < g.s1.n; i += blockDim.x) S1.type[i] = g.s1.type[i];
-    for (int i = threadIdx.x; i < g.s2.n; i += blockDim.x) S2.type[i] = g.s2.type[i];
+    for (int i = threadIdx.x; i < g.s1.n; i += blockDim.x) { S1.type[i] = g.s1.type[i]; S1.loc[i] = g.s1.loc[i]; }
+    for (int i = threadIdx.x; i < g.s2.n; i += blockDim.x) { S2.type[i] = g.s2.type[i]; S2.loc[i] = g.s2.loc[i]; }
+    __syncthreads();
 }
 // both barriers included: the previous replica's readers are done before the overwrite, the data is visible after
+// the trailing barrier is the caller's (it usually has more to put into shared memory first)
 __device__ __forceinline__ void stage_groups(const IGraphDev& g, int r, const StagedGroup& S1, const StagedGroup& S2) {
     __syncthreads();
     for (int i = threadIdx.x; i < g.s1.n; i += blockDim.x) {
-        const float* p = elem_ptr(g.s1, r, i);
+        const float* p = g.s1.out + (size_t(r) * g.s1.n_node + S1.loc[i]) * g.s1.wp;
         S1.a[i] = reinterpret_cast<const float4*>(p)[0];
         S1.b[i] = g.s1.wp >= 8 ? reinterpret_cast<const float4*>(p)[1] : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     for (int i = threadIdx.x; i < g.s2.n; i += blockDim.x) {
-        const float* p = elem_ptr(g.s2, r, i);
+        const float* p = g.s2.out + (size_t(r) * g.s2.n_node + S2.loc[i]) * g.s2.wp;
         S2.a[i] = reinterpret_cast<const float4*>(p)[0];
         S2.b[i] = g.s2.wp >= 8 ? reinterpret_cast<const float4*>(p)[1] : make_float4(0.f, 0.f, 0.f, 0.f);
     }
+}
+// Per-replica prologue shared by the four kernels.  The row lengths (and, backward, the rows' sensitivities) are fetched
+// into registers BEFORE the barrier that frees the staging area, so that their latency overlaps the staging loads instead
+// of following them; the lengths go to E.start for the in-place scan.  RPT = rows per thread (ceil(n_rows / CTPB)).
+template <int RPT, bool BWD>
+__device__ __forceinline__ void replica_prologue(const IGraphDev& g, int r, const StagedGroup& S1, const StagedGroup& S2, int n_rows,
+                                                 const int* __restrict__ cnt, const float* __restrict__ sens, float* sn,
+                                                 float* acc, int n_acc, const EdgeScratch& E) {
+    int plen[RPT];
+    float psn[RPT];
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) {
+        const int j = threadIdx.x + k * CTPB;
+        plen[k] = j < n_rows ? cnt[size_t(r) * n_rows + j] : 0;
+        psn[k] = (BWD && j < n_rows) ? sens[size_t(r) * n_rows + j] : 1.f;
+    }
+    stage_groups(g, r, S1, S2);   // (leading barrier: the previous replica's readers of sn / acc / E.start are done)
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) {
+        const int j = threadIdx.x + k * CTPB;
+        if (j < n_rows) {
+            if (BWD) sn[j] = psn[k];
+            E.start[j] = psn[k] != 0.f ? plen[k] : 0;   // rows without sensitivity contribute nothing
+        }
+    }
+    if (BWD) for (int i = threadIdx.x; i < n_acc; i += CTPB) acc[i] = 0.f;
     __syncthreads();
+    scan_row_lengths_inplace(n_rows, E.start, E.wtot);
 }
 __device__ __forceinline__ void unpack8(const StagedGroup& S, int i, float* x) {
     float4 a = S.a[i], b = S.b[i];
     x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
 }
 inline size_t staged_bytes(int n1, int n2, int n_tab) {
-    return size_t(n1 + n2) * 2 * sizeof(float4) + sizeof(float) * ((n_tab + 3) & ~3) + sizeof(int) * size_t((n1 + n2 + 3) & ~3);
+    return size_t(n1 + n2) * 2 * sizeof(float4) + sizeof(float) * ((n_tab + 3) & ~3) + sizeof(int) * size_t((2 * (n1 + n2) + 3) & ~3);
 }
 
 // shared-memory sizes and persistent grids (as many CTAs as stay resident, striding over the replicas)
 struct CoverageLaunch {
     size_t smem_fwd = 0, smem_bwd = 0;
-    int grid_fwd = 1, grid_bwd = 1, n_rows_max = 0;
+    int grid_fwd = 1, grid_bwd = 1, n_rows_max = 0, rpt = 2;   // rpt: rows per thread of the prologue, 2 / 4 / 8
+    static int rows_per_thread(const IGraphHost& ig, const char* what) {
+        const int n_rows = ig.need1 ? ig.n1 : ig.n2;
+        if (n_rows > 8 * CTPB) throw std::string(what) + ": more than " + std::to_string(8 * CTPB) + " rows per replica";
+        return n_rows <= 2 * CTPB ? 2 : (n_rows <= 4 * CTPB ? 4 : 8);
+    }
     void init(Engine* e, const IGraphHost& ig, int nv_bwd, int n_sens, const void* kf, const void* kb, const char* what) {
         if ((ig.need1 && ig.K1 > EL_CAP) || (ig.need2 && ig.K2 > EL_CAP)) throw std::string(what) + ": neighbour capacity exceeds the edge chunk size";
         n_rows_max = std::max(ig.n1, ig.n2);
+        rpt = rows_per_thread(ig, what);
         size_t staged = staged_bytes(ig.n1, ig.n2, ig.n_type1 * ig.n_type2 * ig.n_param);
         smem_fwd = staged + edge_scratch_bytes(n_rows_max, 1);
         smem_bwd = staged + edge_scratch_bytes(n_rows_max, nv_bwd) + sizeof(float) * n_sens;
@@ -87,6 +125,7 @@ struct CoverageLaunch {
 
 // ================================================================================================ HBondCoverage
 // forward: per bead (group 2) the coverage of every H/O site (group 1) in range
+template <int RPT>
 __global__ void __launch_bounds__(CTPB) k_hbond_coverage(IGraphDev g, QuadSplineShape q, float* __restrict__ out, int n_rep, int n_rows_max) {
     extern __shared__ float4 smem4[];
     StagedGroup S1, S2;
@@ -95,9 +134,7 @@ __global__ void __launch_bounds__(CTPB) k_hbond_coverage(IGraphDev g, QuadSpline
     EdgeScratch E = carve_edge_scratch(carve_groups(g, smem4, S1, S2, table, n_tab), n_rows_max, 1);
     stage_table(g, S1, S2, table, n_tab);
     for (int r = blockIdx.x; r < n_rep; r += gridDim.x) {
-        stage_groups(g, r, S1, S2);
-        const int* cnt = g.cnt2 + size_t(r) * g.s2.n;
-        scan_row_lengths(g.s2.n, [&](int j) { return cnt[j]; }, E.start, E.wtot);
+        replica_prologue<RPT, false>(g, r, S1, S2, g.s2.n, g.cnt2, nullptr, nullptr, nullptr, 0, E);
         for_each_edge<1>(g.s2.n, g.nbr2 + size_t(r) * g.s2.n * g.K2, g.K2, E,
             [&](int j, int i, float* o) {
                 float x1[8], x2[8], d1[7], d2[6];
@@ -111,6 +148,7 @@ __global__ void __launch_bounds__(CTPB) k_hbond_coverage(IGraphDev g, QuadSpline
 // sens[j] * sum_i dV/d(bead j), summed per row in a fixed order.  Site side: sens[j] * dV/d(site i) (7 components, last =
 // d/d hb) goes into per-site accumulators in shared memory with atomics (a site has few partners; forces are summed with
 // float atomics elsewhere on the path as well), flushed by one thread per site.
+template <int RPT>
 __global__ void __launch_bounds__(CTPB) k_hbond_coverage_deriv(IGraphDev g, QuadSplineShape q, const float* __restrict__ sens, int n_rep,
                                                                int n_rows_max) {
     extern __shared__ float4 smem4[];
@@ -122,12 +160,7 @@ __global__ void __launch_bounds__(CTPB) k_hbond_coverage_deriv(IGraphDev g, Quad
     float* acc1 = sn + g.s2.n;                            // [n1][7] site-side sums
     stage_table(g, S1, S2, table, n_tab);
     for (int r = blockIdx.x; r < n_rep; r += gridDim.x) {
-        stage_groups(g, r, S1, S2);   // (leading barrier: previous replica's readers of sn / acc1 are done)
-        for (int j = threadIdx.x; j < g.s2.n; j += blockDim.x) sn[j] = sens[size_t(r) * g.s2.n + j];
-        for (int i = threadIdx.x; i < g.s1.n * 7; i += blockDim.x) acc1[i] = 0.f;
-        __syncthreads();
-        const int* cnt2 = g.cnt2 + size_t(r) * g.s2.n;
-        scan_row_lengths(g.s2.n, [&](int j) { return sn[j] != 0.f ? cnt2[j] : 0; }, E.start, E.wtot);
+        replica_prologue<RPT, true>(g, r, S1, S2, g.s2.n, g.cnt2, sens, sn, acc1, g.s1.n * 7, E);
         for_each_edge<6>(g.s2.n, g.nbr2 + size_t(r) * g.s2.n * g.K2, g.K2, E,
             [&](int j, int i, float* o) {
                 float x1[8], x2[8], d1[7];
@@ -139,20 +172,19 @@ __global__ void __launch_bounds__(CTPB) k_hbond_coverage_deriv(IGraphDev g, Quad
             },
             [&](int j, int c, const float* s) {
                 if (!c) return;
-                float* dst = elem_sens_ptr(g.s2, r, j);
+                // reductions without a return value (RED): the thread does not wait for the row to come back from L2
+                float* dst = g.s2.sens + (size_t(r) * g.s2.n_node + S2.loc[j]) * g.s2.wp;
                 const float sj = sn[j];
-                float4 a = reinterpret_cast<float4*>(dst)[0], b = reinterpret_cast<float4*>(dst)[1];
-                a.x += sj * s[0]; a.y += sj * s[1]; a.z += sj * s[2]; a.w += sj * s[3]; b.x += sj * s[4]; b.y += sj * s[5];
-                reinterpret_cast<float4*>(dst)[0] = a; reinterpret_cast<float4*>(dst)[1] = b;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) atomicAdd(dst + k, sj * s[k]);
             });
         // (for_each_edge ends with a barrier: acc1 is complete)
         for (int i = threadIdx.x; i < g.s1.n; i += blockDim.x) {
             const float* s = acc1 + i * 7;
             if (s[0] == 0.f && s[1] == 0.f && s[2] == 0.f && s[6] == 0.f) continue;   // site without a partner (no table by site is kept)
-            float* dst = elem_sens_ptr(g.s1, r, i);
-            float4 a = reinterpret_cast<float4*>(dst)[0], b = reinterpret_cast<float4*>(dst)[1];
-            a.x += s[0]; a.y += s[1]; a.z += s[2]; a.w += s[3]; b.x += s[4]; b.y += s[5]; b.z += s[6];
-            reinterpret_cast<float4*>(dst)[0] = a; reinterpret_cast<float4*>(dst)[1] = b;
+            float* dst = g.s1.sens + (size_t(r) * g.s1.n_node + S1.loc[i]) * g.s1.wp;
+#pragma unroll
+            for (int k = 0; k < 7; ++k) atomicAdd(dst + k, s[k]);
         }
     }
 }
@@ -198,17 +230,22 @@ struct HBondCoverage : CoordNode {
     void finalize() override {
         ig.need1 = false;   // both kernels walk the rows of the beads (table 2)
         ig.allocate(engine);
-        launch.init(engine, ig, 6, ig.n2 + 7 * ig.n1, (const void*)k_hbond_coverage, (const void*)k_hbond_coverage_deriv, "hbond_coverage");
+        const int rpt = CoverageLaunch::rows_per_thread(ig, "hbond_coverage");
+        kf = rpt == 2 ? k_hbond_coverage<2> : (rpt == 4 ? k_hbond_coverage<4> : k_hbond_coverage<8>);
+        kb = rpt == 2 ? k_hbond_coverage_deriv<2> : (rpt == 4 ? k_hbond_coverage_deriv<4> : k_hbond_coverage_deriv<8>);
+        launch.init(engine, ig, 6, ig.n2 + 7 * ig.n1, (const void*)kf, (const void*)kb, "hbond_coverage");
     }
+    void (*kf)(IGraphDev, QuadSplineShape, float*, int, int) = nullptr;
+    void (*kb)(IGraphDev, QuadSplineShape, const float*, int, int) = nullptr;
     QuadSplineShape shape() const { QuadSplineShape q; q.nka = nka; q.nk = nk; q.inv_dx = 1.f / knot_spacing; q.inv_dtheta = (nka - 3) / 2.f; return q; }
     void compute_value(cudaStream_t s, ComputeMode) override {
         if (!n_elem) return;
         ig.build(s);
-        k_hbond_coverage<<<launch.grid_fwd, CTPB, launch.smem_fwd, s>>>(ig.dev(), shape(), output, engine->n_rep, launch.n_rows_max);
+        kf<<<launch.grid_fwd, CTPB, launch.smem_fwd, s>>>(ig.dev(), shape(), output, engine->n_rep, launch.n_rows_max);
     }
     void propagate_deriv(cudaStream_t s) override {
         if (!n_elem) return;
-        k_hbond_coverage_deriv<<<launch.grid_bwd, CTPB, launch.smem_bwd, s>>>(ig.dev(), shape(), sens, engine->n_rep, launch.n_rows_max);
+        kb<<<launch.grid_bwd, CTPB, launch.smem_bwd, s>>>(ig.dev(), shape(), sens, engine->n_rep, launch.n_rows_max);
     }
     bool get_pairlist(int replica, std::vector<int>& i1, std::vector<int>& i2) override { return ig.pairlist(replica, i1, i2); }
     std::vector<float> get_param() const override { return ig.h_param; }
@@ -235,6 +272,7 @@ RegisterNodeType<HBondCoverage, 2> coverage_node("hbond_coverage");
 
 // ================================================================================================ EnvironmentCoverage
 // forward: per CB (group 1) the weighted count of side-chain beads (group 2) in its cone
+template <int RPT>
 __global__ void __launch_bounds__(CTPB) k_env_coverage(IGraphDev g, float* __restrict__ out, int n_rep, int n_rows_max) {
     extern __shared__ float4 smem4[];
     StagedGroup S1, S2;
@@ -243,9 +281,7 @@ __global__ void __launch_bounds__(CTPB) k_env_coverage(IGraphDev g, float* __res
     EdgeScratch E = carve_edge_scratch(carve_groups(g, smem4, S1, S2, table, n_tab), n_rows_max, 1);
     stage_table(g, S1, S2, table, n_tab);
     for (int r = blockIdx.x; r < n_rep; r += gridDim.x) {
-        stage_groups(g, r, S1, S2);
-        const int* cnt = g.cnt1 + size_t(r) * g.s1.n;
-        scan_row_lengths(g.s1.n, [&](int i) { return cnt[i]; }, E.start, E.wtot);
+        replica_prologue<RPT, false>(g, r, S1, S2, g.s1.n, g.cnt1, nullptr, nullptr, nullptr, 0, E);
         for_each_edge<1>(g.s1.n, g.nbr1 + size_t(r) * g.s1.n * g.K1, g.K1, E,
             [&](int i, int j, float* o) {
                 float x1[8], d1[6], d2[4];
@@ -259,6 +295,7 @@ __global__ void __launch_bounds__(CTPB) k_env_coverage(IGraphDev g, float* __res
 }
 // backward: every edge is evaluated once (rows = CBs whose coverage has a non-zero sensitivity); CB side summed per row in a
 // fixed order, bead side (position + weight, 4 components) through shared-memory accumulators as in k_hbond_coverage_deriv
+template <int RPT>
 __global__ void __launch_bounds__(CTPB) k_env_coverage_deriv(IGraphDev g, const float* __restrict__ sens, int n_rep, int n_rows_max) {
     extern __shared__ float4 smem4[];
     StagedGroup S1, S2;
@@ -269,12 +306,7 @@ __global__ void __launch_bounds__(CTPB) k_env_coverage_deriv(IGraphDev g, const 
     float* acc2 = sn + g.s1.n;                            // [n2][4] bead-side sums
     stage_table(g, S1, S2, table, n_tab);
     for (int r = blockIdx.x; r < n_rep; r += gridDim.x) {
-        stage_groups(g, r, S1, S2);   // (leading barrier: previous replica's readers of sn / acc2 are done)
-        for (int i = threadIdx.x; i < g.s1.n; i += blockDim.x) sn[i] = sens[size_t(r) * g.s1.n + i];
-        for (int j = threadIdx.x; j < g.s2.n * 4; j += blockDim.x) acc2[j] = 0.f;
-        __syncthreads();
-        const int* cnt1 = g.cnt1 + size_t(r) * g.s1.n;
-        scan_row_lengths(g.s1.n, [&](int i) { return sn[i] != 0.f ? cnt1[i] : 0; }, E.start, E.wtot);
+        replica_prologue<RPT, true>(g, r, S1, S2, g.s1.n, g.cnt1, sens, sn, acc2, g.s2.n * 4, E);
         for_each_edge<6>(g.s1.n, g.nbr1 + size_t(r) * g.s1.n * g.K1, g.K1, E,
             [&](int i, int j, float* o) {
                 float x1[8], d2[4];
@@ -288,18 +320,16 @@ __global__ void __launch_bounds__(CTPB) k_env_coverage_deriv(IGraphDev g, const 
             },
             [&](int i, int c, const float* s) {
                 if (!c) return;
-                float* dst = elem_sens_ptr(g.s1, r, i);
+                float* dst = g.s1.sens + (size_t(r) * g.s1.n_node + S1.loc[i]) * g.s1.wp;
                 const float si = sn[i];
-                float4 a = reinterpret_cast<float4*>(dst)[0], b = reinterpret_cast<float4*>(dst)[1];
-                a.x += si * s[0]; a.y += si * s[1]; a.z += si * s[2]; a.w += si * s[3]; b.x += si * s[4]; b.y += si * s[5];
-                reinterpret_cast<float4*>(dst)[0] = a; reinterpret_cast<float4*>(dst)[1] = b;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) atomicAdd(dst + k, si * s[k]);
             });
         for (int j = threadIdx.x; j < g.s2.n; j += blockDim.x) {
             if (acc2[4 * j] == 0.f && acc2[4 * j + 1] == 0.f && acc2[4 * j + 2] == 0.f && acc2[4 * j + 3] == 0.f) continue;   // bead outside every cone
-            float4* dst = reinterpret_cast<float4*>(elem_sens_ptr(g.s2, r, j));
-            float4 o = *dst;
-            o.x += acc2[4 * j]; o.y += acc2[4 * j + 1]; o.z += acc2[4 * j + 2]; o.w += acc2[4 * j + 3];
-            *dst = o;
+            float* dst = g.s2.sens + (size_t(r) * g.s2.n_node + S2.loc[j]) * g.s2.wp;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) atomicAdd(dst + k, acc2[4 * j + k]);
         }
     }
 }
@@ -317,16 +347,21 @@ struct EnvironmentCoverage : CoordNode {
     void finalize() override {
         ig.need2 = false;   // both kernels walk the rows of the CBs (table 1)
         ig.allocate(engine);
-        launch.init(engine, ig, 6, ig.n1 + 4 * ig.n2, (const void*)k_env_coverage, (const void*)k_env_coverage_deriv, "environment_coverage");
+        const int rpt = CoverageLaunch::rows_per_thread(ig, "environment_coverage");
+        kf = rpt == 2 ? k_env_coverage<2> : (rpt == 4 ? k_env_coverage<4> : k_env_coverage<8>);
+        kb = rpt == 2 ? k_env_coverage_deriv<2> : (rpt == 4 ? k_env_coverage_deriv<4> : k_env_coverage_deriv<8>);
+        launch.init(engine, ig, 6, ig.n1 + 4 * ig.n2, (const void*)kf, (const void*)kb, "environment_coverage");
     }
+    void (*kf)(IGraphDev, float*, int, int) = nullptr;
+    void (*kb)(IGraphDev, const float*, int, int) = nullptr;
     void compute_value(cudaStream_t s, ComputeMode) override {
         if (!n_elem) return;
         ig.build(s);
-        k_env_coverage<<<launch.grid_fwd, CTPB, launch.smem_fwd, s>>>(ig.dev(), output, engine->n_rep, launch.n_rows_max);
+        kf<<<launch.grid_fwd, CTPB, launch.smem_fwd, s>>>(ig.dev(), output, engine->n_rep, launch.n_rows_max);
     }
     void propagate_deriv(cudaStream_t s) override {
         if (!n_elem) return;
-        k_env_coverage_deriv<<<launch.grid_bwd, CTPB, launch.smem_bwd, s>>>(ig.dev(), sens, engine->n_rep, launch.n_rows_max);
+        kb<<<launch.grid_bwd, CTPB, launch.smem_bwd, s>>>(ig.dev(), sens, engine->n_rep, launch.n_rows_max);
     }
     bool get_pairlist(int replica, std::vector<int>& i1, std::vector<int>& i2) override { return ig.pairlist(replica, i1, i2); }
     std::vector<float> get_param() const override { return ig.h_param; }
