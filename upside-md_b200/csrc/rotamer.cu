@@ -148,6 +148,7 @@ __global__ void __launch_bounds__(PREP_TPB) k_rot_prep(RotamerDev P) {
         const int c = cnt[i], me = rr[i];
         const bool mA = me & 1;
         int lo = 0, nfl = 0, nev = 0;
+        int last_res = -1;   // partners ascend and the beads of a residue are neighbours: one adjacency update per run
         for (int k0 = 0; k0 < c; k0 += 8) {
             const uint4 v = row4[k0 >> 3];
             const unsigned w[4] = {v.x, v.y, v.z, v.w};
@@ -157,9 +158,10 @@ __global__ void __launch_bounds__(PREP_TPB) k_rot_prep(RotamerDev P) {
                 const int j = (u & 1) ? int(w[u >> 1] >> 16) : int(w[u >> 1] & 0xffffu);
                 const int other = rr[j];
                 const bool mB = other & 1, below = j < i;
-                if (mA && mB) {
+                if (mA && mB && (other >> 4) != last_res) {
                     // both directions, so that the adjacency stays symmetric even if a row was truncated by a capacity
                     // overflow (reported through error_flag): every index derived below relies on that symmetry
+                    last_res = other >> 4;
                     atomicOr(&bitmap[(me >> 4) * nW + (other >> 9)], 1u << ((other >> 4) & 31));
                     atomicOr(&bitmap[(other >> 4) * nW + (me >> 9)], 1u << ((me >> 4) & 31));
                 }
@@ -262,6 +264,7 @@ __global__ void __launch_bounds__(PREP_TPB) k_rot_prep(RotamerDev P) {
         const int c = cnt[i], base = rs[i], me = rr[i], A = me >> 4, ra = (me >> 1) & 7;
         const bool mA = me & 1;
         int run_f = lo_s[i], run_o = 0;   // next slot of a folding / other partner below the bead
+        int last_res = -1, last_slot36 = 0;   // the pair slot is looked up once per run of beads of the same partner residue
         for (int k0 = 0; k0 < c; k0 += 8) {
             const uint4 v = row4[k0 >> 3];
             const unsigned w[4] = {v.x, v.y, v.z, v.w};
@@ -273,7 +276,10 @@ __global__ void __launch_bounds__(PREP_TPB) k_rot_prep(RotamerDev P) {
                 const int other = rr[j], Bq = other >> 4, rb = (other >> 1) & 7;
                 const bool mB = other & 1, below = j < i;
                 int cd;
-                if (mA && mB) cd = A < Bq ? slot_of(A, Bq) * 36 + ra * 6 + rb : slot_of(Bq, A) * 36 + rb * 6 + ra;
+                if (mA && mB) {
+                    if (Bq != last_res) { last_res = Bq; last_slot36 = 36 * (A < Bq ? slot_of(A, Bq) : slot_of(Bq, A)); }
+                    cd = last_slot36 + (A < Bq ? ra * 6 + rb : rb * 6 + ra);
+                }
                 else if (mA) cd = code_node(A * MAXR + ra, true);
                 else if (mB) cd = code_node(Bq * MAXR + rb, false);
                 else cd = CODE_SS;
