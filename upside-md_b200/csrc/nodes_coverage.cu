@@ -16,6 +16,9 @@ namespace {
 #define UB_CTPB 256
 #endif
 constexpr int CTPB = UB_CTPB;
+#ifndef UB_COV_RED
+#define UB_COV_RED 1   // partner-side derivatives of the backward kernels: 1 = 16-byte global reductions, 0 = shared-memory accumulators
+#endif
 
 struct StagedGroup {
     float4* a;   // x,y,z,w0
@@ -160,15 +163,23 @@ __global__ void __launch_bounds__(CTPB) k_hbond_coverage_deriv(IGraphDev g, Quad
     float* acc1 = sn + g.s2.n;                            // [n1][7] site-side sums
     stage_table(g, S1, S2, table, n_tab);
     for (int r = blockIdx.x; r < n_rep; r += gridDim.x) {
-        replica_prologue<RPT, true>(g, r, S1, S2, g.s2.n, g.cnt2, sens, sn, acc1, g.s1.n * 7, E);
+        replica_prologue<RPT, true>(g, r, S1, S2, g.s2.n, g.cnt2, sens, sn, acc1, UB_COV_RED ? 0 : g.s1.n * 7, E);
         for_each_edge<6>(g.s2.n, g.nbr2 + size_t(r) * g.s2.n * g.K2, g.K2, E,
             [&](int j, int i, float* o) {
                 float x1[8], x2[8], d1[7];
                 unpack8(S1, i, x1); unpack8(S2, j, x2);
                 hbond_coverage_edge(table + (S1.type[i] * g.n_type2 + S2.type[j]) * g.n_param, q, x1, x2, d1, o);
                 const float sj = sn[j];
+#if UB_COV_RED
+                // two 16-byte reductions straight into the site's sens row (REDG.ADD.F32x4): a shared-memory float atomicAdd
+                // would be a compare-and-swap loop on sm_100a (ATOMS.CAST.SPIN)
+                float4* d = reinterpret_cast<float4*>(g.s1.sens + (size_t(r) * g.s1.n_node + S1.loc[i]) * g.s1.wp);
+                atomicAdd(d, make_float4(sj * d1[0], sj * d1[1], sj * d1[2], sj * d1[3]));
+                atomicAdd(d + 1, make_float4(sj * d1[4], sj * d1[5], sj * d1[6], 0.f));
+#else
 #pragma unroll
                 for (int c = 0; c < 7; ++c) atomicAdd(&acc1[i * 7 + c], sj * d1[c]);
+#endif
             },
             [&](int j, int c, const float* s) {
                 if (!c) return;
@@ -178,6 +189,7 @@ __global__ void __launch_bounds__(CTPB) k_hbond_coverage_deriv(IGraphDev g, Quad
 #pragma unroll
                 for (int k = 0; k < 6; ++k) atomicAdd(dst + k, sj * s[k]);
             });
+#if !UB_COV_RED
         // (for_each_edge ends with a barrier: acc1 is complete)
         for (int i = threadIdx.x; i < g.s1.n; i += blockDim.x) {
             const float* s = acc1 + i * 7;
@@ -186,6 +198,7 @@ __global__ void __launch_bounds__(CTPB) k_hbond_coverage_deriv(IGraphDev g, Quad
 #pragma unroll
             for (int k = 0; k < 7; ++k) atomicAdd(dst + k, s[k]);
         }
+#endif
     }
 }
 // parameter derivative (interaction_graph.h:404-415 with hbond.cpp:278-283): sum over edges of
@@ -233,7 +246,7 @@ struct HBondCoverage : CoordNode {
         const int rpt = CoverageLaunch::rows_per_thread(ig, "hbond_coverage");
         kf = rpt == 2 ? k_hbond_coverage<2> : (rpt == 4 ? k_hbond_coverage<4> : k_hbond_coverage<8>);
         kb = rpt == 2 ? k_hbond_coverage_deriv<2> : (rpt == 4 ? k_hbond_coverage_deriv<4> : k_hbond_coverage_deriv<8>);
-        launch.init(engine, ig, 6, ig.n2 + 7 * ig.n1, (const void*)kf, (const void*)kb, "hbond_coverage");
+        launch.init(engine, ig, 6, ig.n2 + (UB_COV_RED ? 0 : 7 * ig.n1), (const void*)kf, (const void*)kb, "hbond_coverage");
     }
     void (*kf)(IGraphDev, QuadSplineShape, float*, int, int) = nullptr;
     void (*kb)(IGraphDev, QuadSplineShape, const float*, int, int) = nullptr;
@@ -306,7 +319,7 @@ __global__ void __launch_bounds__(CTPB) k_env_coverage_deriv(IGraphDev g, const 
     float* acc2 = sn + g.s1.n;                            // [n2][4] bead-side sums
     stage_table(g, S1, S2, table, n_tab);
     for (int r = blockIdx.x; r < n_rep; r += gridDim.x) {
-        replica_prologue<RPT, true>(g, r, S1, S2, g.s1.n, g.cnt1, sens, sn, acc2, g.s2.n * 4, E);
+        replica_prologue<RPT, true>(g, r, S1, S2, g.s1.n, g.cnt1, sens, sn, acc2, UB_COV_RED ? 0 : g.s2.n * 4, E);
         for_each_edge<6>(g.s1.n, g.nbr1 + size_t(r) * g.s1.n * g.K1, g.K1, E,
             [&](int i, int j, float* o) {
                 float x1[8], d2[4];
@@ -315,8 +328,13 @@ __global__ void __launch_bounds__(CTPB) k_env_coverage_deriv(IGraphDev g, const 
                 float x2[4] = {v.x, v.y, v.z, v.w};
                 environment_edge(table + (S1.type[i] * g.n_type2 + S2.type[j]) * g.n_param, x1, x2, o, d2);
                 const float si = sn[i];
+#if UB_COV_RED
+                atomicAdd(reinterpret_cast<float4*>(g.s2.sens + (size_t(r) * g.s2.n_node + S2.loc[j]) * g.s2.wp),
+                          make_float4(si * d2[0], si * d2[1], si * d2[2], si * d2[3]));   // one REDG.ADD.F32x4 per edge
+#else
 #pragma unroll
                 for (int c = 0; c < 4; ++c) atomicAdd(&acc2[j * 4 + c], si * d2[c]);
+#endif
             },
             [&](int i, int c, const float* s) {
                 if (!c) return;
@@ -325,12 +343,14 @@ __global__ void __launch_bounds__(CTPB) k_env_coverage_deriv(IGraphDev g, const 
 #pragma unroll
                 for (int k = 0; k < 6; ++k) atomicAdd(dst + k, si * s[k]);
             });
+#if !UB_COV_RED
         for (int j = threadIdx.x; j < g.s2.n; j += blockDim.x) {
             if (acc2[4 * j] == 0.f && acc2[4 * j + 1] == 0.f && acc2[4 * j + 2] == 0.f && acc2[4 * j + 3] == 0.f) continue;   // bead outside every cone
             float* dst = g.s2.sens + (size_t(r) * g.s2.n_node + S2.loc[j]) * g.s2.wp;
 #pragma unroll
             for (int k = 0; k < 4; ++k) atomicAdd(dst + k, acc2[4 * j + k]);
         }
+#endif
     }
 }
 struct EnvironmentCoverage : CoordNode {
@@ -350,7 +370,7 @@ struct EnvironmentCoverage : CoordNode {
         const int rpt = CoverageLaunch::rows_per_thread(ig, "environment_coverage");
         kf = rpt == 2 ? k_env_coverage<2> : (rpt == 4 ? k_env_coverage<4> : k_env_coverage<8>);
         kb = rpt == 2 ? k_env_coverage_deriv<2> : (rpt == 4 ? k_env_coverage_deriv<4> : k_env_coverage_deriv<8>);
-        launch.init(engine, ig, 6, ig.n1 + 4 * ig.n2, (const void*)kf, (const void*)kb, "environment_coverage");
+        launch.init(engine, ig, 6, ig.n1 + (UB_COV_RED ? 0 : 4 * ig.n2), (const void*)kf, (const void*)kb, "environment_coverage");
     }
     void (*kf)(IGraphDev, float*, int, int) = nullptr;
     void (*kb)(IGraphDev, const float*, int, int) = nullptr;

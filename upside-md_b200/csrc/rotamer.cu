@@ -467,6 +467,9 @@ __global__ void __launch_bounds__(EDGE_TPB, 3) k_rot_energy(RotamerDev P, int wa
     }
 }
 
+// (Evaluating every pair once and adding the partner's half into shared-memory accumulators was measured at 663-679 us per
+// launch against 358 us for this gather form: sm_100a has no native shared-memory float add, atomicAdd compiles to an
+// ATOMS.CAST.SPIN compare-and-swap loop.)
 template <int NKA, int NK>
 __global__ void __launch_bounds__(EDGE_TPB, 3) k_rot_deriv(RotamerDev P, int n_rep) {
     extern __shared__ float4 smem4[];
