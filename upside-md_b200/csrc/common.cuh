@@ -35,6 +35,11 @@ __device__ __forceinline__ void add3(float* p, f3 a) { p[0] += a.x; p[1] += a.y;
 __device__ __forceinline__ void atomic_add3(float* p, f3 a) {
     atomicAdd(p + 0, a.x); atomicAdd(p + 1, a.y); atomicAdd(p + 2, a.z);
 }
+// the same into a 16-byte aligned row whose fourth float is padding (or tolerates +0): ONE 16-byte reduction
+// (REDG.ADD.F32x4, sm_90+) instead of three 4-byte ones
+__device__ __forceinline__ void atomic_add3v(float* p16, f3 a) {
+    atomicAdd(reinterpret_cast<float4*>(p16), make_float4(a.x, a.y, a.z, 0.f));
+}
 
 // quaternion (a,b,c,d) -> row-major rotation matrix; reference affine.h:99-108
 __device__ __forceinline__ void quat_to_rot(float* U, const float* q) {

@@ -44,8 +44,8 @@ __global__ void k_dist_spring(const float* __restrict__ pos, float* __restrict__
         f3 deriv = (p.k * (1.f - p.equil * inv)) * disp;
         float dm = d2 * inv - p.equil;
         e = 0.5f * p.k * dm * dm;
-        atomic_add3(s + 4 * p.a0, deriv);
-        atomic_add3(s + 4 * p.a1, -deriv);
+        atomic_add3v(s + 4 * p.a0, deriv);
+        atomic_add3v(s + 4 * p.a1, -deriv);
     }
     if (want_pot) accumulate_potential(e, pot);
 }
@@ -118,9 +118,9 @@ __global__ void k_angle_spring(const float* __restrict__ pos, float* __restrict_
         float pre = p.k * (dp - p.equil);
         f3 d1 = (pre * i1) * (h2 - dp * h1);
         f3 d2 = (pre * i2) * (h1 - dp * h2);
-        atomic_add3(s + 4 * p.a0, d1);
-        atomic_add3(s + 4 * p.a1, d2);
-        atomic_add3(s + 4 * p.a2, -(d1 + d2));
+        atomic_add3v(s + 4 * p.a0, d1);
+        atomic_add3v(s + 4 * p.a1, d2);
+        atomic_add3v(s + 4 * p.a2, -(d1 + d2));
         e = 0.5f * p.k * (dp - p.equil) * (dp - p.equil);
     }
     if (want_pot) accumulate_potential(e, pot);
@@ -173,7 +173,7 @@ __global__ void k_dihedral_spring(const float* __restrict__ pos, float* __restri
         disp = (disp < -PI) ? disp + 2.f * PI : disp;
         float sc = p.k * disp;
 #pragma unroll
-        for (int a = 0; a < 4; ++a) atomic_add3(s + 4 * p.a[a], sc * d[a]);
+        for (int a = 0; a < 4; ++a) atomic_add3v(s + 4 * p.a[a], sc * d[a]);
         e = 0.5f * p.k * disp * disp;
     }
     if (want_pot) accumulate_potential(e, pot);
@@ -258,7 +258,7 @@ __global__ void k_rama_coord_deriv(const float* __restrict__ pos, float* __restr
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
         bool used = (k < 4 && !p.dummy0) || (k > 0 && !p.dummy1);
-        if (used) atomic_add3(ps + 4 * p.atom[k], v[k]);
+        if (used) atomic_add3v(ps + 4 * p.atom[k], v[k]);
     }
 }
 struct RamaCoord : CoordNode {
@@ -549,7 +549,7 @@ __global__ void k_affine_alignment_deriv(float* __restrict__ pos_sens, const flo
                 for (int b = 0; b < 4; ++b) acc += dF[a][b] * W[a][b];
             d[j] = acc;
         }
-        atomic_add3(ps + 4 * p.atom[na], (1.f / 3.f) * s3 + mk3(d[0], d[1], d[2]));
+        atomic_add3v(ps + 4 * p.atom[na], (1.f / 3.f) * s3 + mk3(d[0], d[1], d[2]));
     }
 }
 struct AffineAlignment : CoordNode {
@@ -626,9 +626,9 @@ __global__ void k_infer_ho_deriv(const float* __restrict__ pos, float* __restric
     f3 s_prev = (-pi) * (dot(prev, s_disp) * prev - s_disp);
     f3 s_next = (-ni) * (dot(next, s_disp) * next - s_disp);
     float* ps = pos_sens + size_t(r) * n_atom * 4;
-    atomic_add3(ps + 4 * p.atom[0], s_prev);
-    atomic_add3(ps + 4 * p.atom[1], s_pos - s_prev - s_next);
-    atomic_add3(ps + 4 * p.atom[2], s_next);
+    atomic_add3v(ps + 4 * p.atom[0], s_prev);
+    atomic_add3v(ps + 4 * p.atom[1], s_pos - s_prev - s_next);
+    atomic_add3v(ps + 4 * p.atom[2], s_next);
 }
 struct InferHO : CoordNode {
     CoordNode& pos;
@@ -787,8 +787,8 @@ __global__ void k_placement_deriv(const float* __restrict__ affine, float* __res
     }
     if (active && ((lane - seg_start) & 7) == 0) {
         float* as = affine_sens + (size_t(r) * n_aff + ar) * 8;
-        atomic_add3(as, mk3(v[0], v[1], v[2]));
-        atomic_add3(as + 3, mk3(v[3], v[4], v[5]));
+        atomicAdd(reinterpret_cast<float4*>(as), make_float4(v[0], v[1], v[2], v[3]));   // force, torque: two 16-byte reductions
+        atomicAdd(reinterpret_cast<float4*>(as) + 1, make_float4(v[4], v[5], 0.f, 0.f));
     }
 }
 
@@ -924,7 +924,7 @@ __global__ void k_weighted_pos_deriv(float* __restrict__ pos_sens, float* __rest
     if (i >= n) return;
     float4 s = reinterpret_cast<const float4*>(sens)[size_t(r) * n + i];
     float w = out[(size_t(r) * n + i) * 4 + 3];
-    atomic_add3(pos_sens + (size_t(r) * n_pos + ipos[i]) * wp_pos, mk3(s.x, s.y, s.z));
+    atomic_add3v(pos_sens + (size_t(r) * n_pos + ipos[i]) * wp_pos, mk3(s.x, s.y, s.z));
     atomicAdd(energy_sens + (size_t(r) * n_en + iw[i]) * wp_en, -w * s.w);
 }
 struct WeightedPos : CoordNode {
