@@ -186,8 +186,8 @@ __global__ void __launch_bounds__(CTPB) k_hbond_coverage_deriv(IGraphDev g, Quad
                 // reductions without a return value (RED): the thread does not wait for the row to come back from L2
                 float* dst = g.s2.sens + (size_t(r) * g.s2.n_node + S2.loc[j]) * g.s2.wp;
                 const float sj = sn[j];
-#pragma unroll
-                for (int k = 0; k < 6; ++k) atomicAdd(dst + k, sj * s[k]);
+                atomicAdd(reinterpret_cast<float4*>(dst), make_float4(sj * s[0], sj * s[1], sj * s[2], sj * s[3]));
+                atomicAdd(reinterpret_cast<float4*>(dst) + 1, make_float4(sj * s[4], sj * s[5], 0.f, 0.f));
             });
 #if !UB_COV_RED
         // (for_each_edge ends with a barrier: acc1 is complete)
@@ -340,8 +340,8 @@ __global__ void __launch_bounds__(CTPB) k_env_coverage_deriv(IGraphDev g, const 
                 if (!c) return;
                 float* dst = g.s1.sens + (size_t(r) * g.s1.n_node + S1.loc[i]) * g.s1.wp;
                 const float si = sn[i];
-#pragma unroll
-                for (int k = 0; k < 6; ++k) atomicAdd(dst + k, si * s[k]);
+                atomicAdd(reinterpret_cast<float4*>(dst), make_float4(si * s[0], si * s[1], si * s[2], si * s[3]));
+                atomicAdd(reinterpret_cast<float4*>(dst) + 1, make_float4(si * s[4], si * s[5], 0.f, 0.f));
             });
 #if !UB_COV_RED
         for (int j = threadIdx.x; j < g.s2.n; j += blockDim.x) {

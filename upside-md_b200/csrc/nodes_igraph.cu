@@ -186,80 +186,71 @@ void IGraphHost::set_param(const std::vector<float>& p) {
 namespace {
 
 constexpr int TPB = 128;
-constexpr int G = 8;   // lanes cooperating on one element's neighbour row
-inline dim3 group_grid(int n_elem, int n_rep) { return dim3((n_elem * G + TPB - 1) / TPB, n_rep); }
 
 // ================================================================================================ ProteinHBond
+// forward: one thread per virtual site (a site has at most a few partners inside 3.5 A) sums its edge values in row order
 __global__ void k_protein_hbond(IGraphDev g, const float* __restrict__ infer, float* __restrict__ out, int n_donor, int n_virtual) {
-    int r = blockIdx.y;
-    int e = (blockIdx.x * blockDim.x + threadIdx.x) / G, lane = threadIdx.x % G;
-    bool active = e < n_virtual;
+    const int r = blockIdx.y, e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_virtual) return;
+    const bool donor = e < n_donor;
+    const int me = donor ? e : e - n_donor;
+    const IGraphSide& mine = donor ? g.s1 : g.s2;
+    const IGraphSide& other = donor ? g.s2 : g.s1;
+    const int cnt = donor ? g.cnt1[size_t(r) * g.s1.n + me] : g.cnt2[size_t(r) * g.s2.n + me];
+    const float* src = infer + (size_t(r) * n_virtual + e) * 8;
+    const float4 a = reinterpret_cast<const float4*>(src)[0], b = reinterpret_cast<const float4*>(src)[1];
     float acc = 0.f;
-    float xs[8];
-    if (active) {
-        bool donor = e < n_donor;
-        int me = donor ? e : e - n_donor;
-        const IGraphSide& mine = donor ? g.s1 : g.s2;
-        const IGraphSide& other = donor ? g.s2 : g.s1;
+    if (cnt) {
+        float xs[8];
         load8(elem_ptr(mine, r, me), xs);
         const unsigned short* row = donor ? g.nbr1 + (size_t(r) * g.s1.n + me) * g.K1 : g.nbr2 + (size_t(r) * g.s2.n + me) * g.K2;
-        int cnt = donor ? g.cnt1[size_t(r) * g.s1.n + me] : g.cnt2[size_t(r) * g.s2.n + me];
-        for (int k = lane; k < cnt; k += G) {
-            int o = row[k];
+        for (int k = 0; k < cnt; ++k) {
             float xo[8], d1[6], d2[6];
-            load8(elem_ptr(other, r, o), xo);
+            load8(elem_ptr(other, r, row[k]), xo);
             acc += donor ? protein_hbond_edge(g.param, xs, xo, d1, d2) : protein_hbond_edge(g.param, xo, xs, d1, d2);
         }
     }
-    acc = group_sum<G>(acc);
-    if (active && lane == 0) {
-        const float* src = infer + (size_t(r) * n_virtual + e) * 8;
-        float* o = out + (size_t(r) * n_virtual + e) * 8;
-        float4 a = reinterpret_cast<const float4*>(src)[0], b = reinterpret_cast<const float4*>(src)[1];
-        reinterpret_cast<float4*>(o)[0] = a;
-        reinterpret_cast<float4*>(o)[1] = make_float4(b.x, b.y, 1.f - expf(-acc), 0.f);
-    }
+    float* o = out + (size_t(r) * n_virtual + e) * 8;
+    reinterpret_cast<float4*>(o)[0] = a;
+    reinterpret_cast<float4*>(o)[1] = make_float4(b.x, b.y, 1.f - expf(-acc), 0.f);
 }
+// backward: one thread per virtual site.  Every site passes the six copied components of its sens row through; a donor
+// also walks its row and evaluates each H-bond edge ONCE: its own half of the derivative stays in registers, the
+// acceptor's half goes straight to the acceptor's sens row as two 16-byte reductions (REDG.ADD.F32x4).
 __global__ void k_protein_hbond_deriv(IGraphDev g, const float* __restrict__ out, const float* __restrict__ sens, int n_donor,
                                       int n_virtual) {
-    int r = blockIdx.y;
-    int e = (blockIdx.x * blockDim.x + threadIdx.x) / G, lane = threadIdx.x % G;
-    bool active = e < n_virtual;
-    float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    bool donor = e < n_donor;
-    int me = donor ? e : e - n_donor;
-    if (active) {
-        const IGraphSide& mine = donor ? g.s1 : g.s2;
-        const IGraphSide& other = donor ? g.s2 : g.s1;
-        float xs[8];
-        load8(elem_ptr(mine, r, me), xs);
-        const float* o_me = out + (size_t(r) * n_virtual + e) * 8;
-        const float* s_me = sens + (size_t(r) * n_virtual + e) * 8;
-        float ss_me = s_me[6] * (1.f - o_me[6]);
-        const unsigned short* row = donor ? g.nbr1 + (size_t(r) * g.s1.n + me) * g.K1 : g.nbr2 + (size_t(r) * g.s2.n + me) * g.K2;
-        int cnt = donor ? g.cnt1[size_t(r) * g.s1.n + me] : g.cnt2[size_t(r) * g.s2.n + me];
-        for (int k = lane; k < cnt; k += G) {
-            int o = row[k];
-            int eo = donor ? n_donor + o : o;
-            float ss_o = sens[(size_t(r) * n_virtual + eo) * 8 + 6] * (1.f - out[(size_t(r) * n_virtual + eo) * 8 + 6]);
-            float es = ss_me + ss_o;
-            float xo[8], d1[6], d2[6];
-            load8(elem_ptr(other, r, o), xo);
-            if (donor) protein_hbond_edge(g.param, xs, xo, d1, d2); else protein_hbond_edge(g.param, xo, xs, d1, d2);
-            const float* d = donor ? d1 : d2;
+    const int r = blockIdx.y, e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_virtual) return;
+    const bool donor = e < n_donor;
+    const int me = donor ? e : e - n_donor;
+    const float4* s_me = reinterpret_cast<const float4*>(sens + (size_t(r) * n_virtual + e) * 8);
+    const float4 sa = s_me[0], sb = s_me[1];
+    float acc[6] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y};   // pass-through of the six copied components
+    if (donor) {
+        const int cnt = g.cnt1[size_t(r) * g.s1.n + me];
+        if (cnt) {
+            float xs[8];
+            load8(elem_ptr(g.s1, r, me), xs);
+            const float ss_me = sb.z * (1.f - out[(size_t(r) * n_virtual + e) * 8 + 6]);
+            const unsigned short* row = g.nbr1 + (size_t(r) * g.s1.n + me) * g.K1;
+            for (int k = 0; k < cnt; ++k) {
+                const int o = row[k], eo = n_donor + o;
+                const float ss_o = sens[(size_t(r) * n_virtual + eo) * 8 + 6] * (1.f - out[(size_t(r) * n_virtual + eo) * 8 + 6]);
+                const float es = ss_me + ss_o;
+                float xo[8], d1[6], d2[6];
+                load8(elem_ptr(g.s2, r, o), xo);
+                protein_hbond_edge(g.param, xs, xo, d1, d2);
 #pragma unroll
-            for (int c = 0; c < 6; ++c) acc[c] += es * d[c];
+                for (int c = 0; c < 6; ++c) acc[c] += es * d1[c];
+                float4* d = reinterpret_cast<float4*>(elem_sens_ptr(g.s2, r, o));
+                atomicAdd(d, make_float4(es * d2[0], es * d2[1], es * d2[2], es * d2[3]));
+                atomicAdd(d + 1, make_float4(es * d2[4], es * d2[5], 0.f, 0.f));
+            }
         }
     }
-#pragma unroll
-    for (int c = 0; c < 6; ++c) acc[c] = group_sum<G>(acc[c]);
-    if (active && lane == 0) {
-        const IGraphSide& mine = donor ? g.s1 : g.s2;
-        const float* s_me = sens + (size_t(r) * n_virtual + e) * 8;
-        float* dst = elem_sens_ptr(mine, r, me);
-#pragma unroll
-        for (int c = 0; c < 6; ++c) dst[c] += acc[c] + s_me[c];   // + pass-through of the six copied components
-    }
+    float4* dst = reinterpret_cast<float4*>(elem_sens_ptr(donor ? g.s1 : g.s2, r, me));
+    atomicAdd(dst, make_float4(acc[0], acc[1], acc[2], acc[3]));
+    atomicAdd(dst + 1, make_float4(acc[4], acc[5], 0.f, 0.f));
 }
 struct ProteinHBond : CoordNode {
     CoordNode& infer;
@@ -277,11 +268,11 @@ struct ProteinHBond : CoordNode {
     void compute_value(cudaStream_t s, ComputeMode) override {
         if (!n_virtual) return;
         ig.build(s);
-        k_protein_hbond<<<group_grid(n_virtual, engine->n_rep), TPB, 0, s>>>(ig.dev(), infer.output, output, n_donor, n_virtual);
+        k_protein_hbond<<<dim3((n_virtual + TPB - 1) / TPB, engine->n_rep), TPB, 0, s>>>(ig.dev(), infer.output, output, n_donor, n_virtual);
     }
     void propagate_deriv(cudaStream_t s) override {
         if (!n_virtual) return;
-        k_protein_hbond_deriv<<<group_grid(n_virtual, engine->n_rep), TPB, 0, s>>>(ig.dev(), output, sens, n_donor, n_virtual);
+        k_protein_hbond_deriv<<<dim3((n_virtual + TPB - 1) / TPB, engine->n_rep), TPB, 0, s>>>(ig.dev(), output, sens, n_donor, n_virtual);
     }
     bool get_pairlist(int replica, std::vector<int>& i1, std::vector<int>& i2) override { return ig.pairlist(replica, i1, i2); }
     std::vector<float> get_param() const override { return ig.h_param; }
