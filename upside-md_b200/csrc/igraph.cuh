@@ -264,6 +264,11 @@ __global__ void __launch_bounds__(256, UB_REFINE_OCC) k_refine(IGraphSide A, IGr
     }
 }
 
+// (A warp-cooperative refinement without staging - WarpEdges over the candidate rows, positions gathered from global memory -
+// was measured for the sparse asymmetric tables and lost: 803 us against 730 us per evaluation for all pair lists.  A
+// candidate costs five global loads there (index, two element rows behind their `loc` indirection) against one shared-memory
+// gather here, and candidates outnumber elements ten to one.)
+
 // ---- row scheduling ---------------------------------------------------------------------------------------
 // Counting sort of n rows by descending key (row length, clipped to 255) into order[0..n).  Lane groups that take
 // consecutive entries of `order` then walk rows of similar length, so a warp's groups finish together.  Results do not

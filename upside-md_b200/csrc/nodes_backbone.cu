@@ -1,6 +1,7 @@
 // backbone_pairs (reference backbone_steric.cpp:38-147) and membrane_potential (membrane_potential.cpp:105-152).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "igraph.cuh"
 #include "spline_fit.h"
@@ -83,6 +84,108 @@ __global__ void k_backbone_pairs(IGraphSide S, const unsigned short* __restrict_
         if (threadIdx.x == 0) atomicAdd(pot + r, en);
     }
 }
+// Fused hot-path form: one CTA per replica places the backbone atoms of every residue in shared memory, tests all residue
+// pairs (i < j, |id_i - id_j| >= 2) against the frame-origin cutoff and compacts the survivors into a shared-memory list
+// (integer atomics), then runs one thread per listed pair: the 4x4 atom pairs are evaluated ONCE, force and torque go to
+// both residues' affine sens rows as 16-byte reductions.  Pairs beyond the origin cutoff cannot contain an atom pair in
+// range, so the result does not depend on the list; the reference-ordered list for the accessor is built on demand.
+constexpr int BB_TPB = 128;
+__global__ void __launch_bounds__(BB_TPB) k_backbone_fused(IGraphSide S, const float* __restrict__ ref_pos, const int* __restrict__ n_atom,
+                                                            float origin_cutoff2, int cap, float* __restrict__ pot, int want_pot,
+                                                            int* __restrict__ error_flag) {
+    extern __shared__ float4 bb_smem[];
+    __shared__ long long sc[BB_TPB / 32];
+    __shared__ int n_list;
+    const int r = blockIdx.x, n = S.n, tid = threadIdx.x;
+    float4* atoms = bb_smem;            // [n][4]
+    float4* org = atoms + 4 * n;        // [n] frame origin, w = id
+    unsigned* list = reinterpret_cast<unsigned*>(org + n);   // [cap] i << 16 | j
+    if (tid == 0) n_list = 0;
+    for (int i = tid; i < n; i += BB_TPB) {
+        const float* aff = S.out + (size_t(r) * S.n_node + S.loc[i]) * S.wp;
+        const float4 a0 = reinterpret_cast<const float4*>(aff)[0], a1 = reinterpret_cast<const float4*>(aff)[1];
+        const f3 t = mk3(a0.x, a0.y, a0.z);
+        float q[4] = {a0.w, a1.x, a1.y, a1.z}, U[9];
+        quat_to_rot(U, q);
+        for (int a = 0; a < 4; ++a) {
+            const f3 x = rot_apply(U, ld3(ref_pos + (i * 4 + a) * 3)) + t;
+            atoms[4 * i + a] = make_float4(x.x, x.y, x.z, 0.f);
+        }
+        org[i] = make_float4(t.x, t.y, t.z, __int_as_float(S.id[i]));
+    }
+    __syncthreads();
+    {   // phase 1: a warp per row i, its lanes over the partners j > i
+        const int lane = tid & 31, w = tid >> 5;
+        for (int i = w; i < n; i += BB_TPB / 32) {
+            const float4 oi = org[i];
+            for (int j = i + 1 + lane; j < n; j += 32) {
+                const float4 oj = org[j];
+                const float dx = oi.x - oj.x, dy = oi.y - oj.y, dz = oi.z - oj.z;
+                const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+                if (d2 < origin_cutoff2 && acceptable_id_pair(EXCL_SEQ1, __float_as_int(oi.w), __float_as_int(oj.w))) {
+                    const int slot = atomicAdd(&n_list, 1);
+                    if (slot < cap) list[slot] = unsigned(i) << 16 | unsigned(j);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (n_list > cap && tid == 0) atomicExch(error_flag, 1);
+    const int m = min(n_list, cap);
+    const float cutoff2 = 3.f * 3.f + 0.1f * 3.f;
+    const float sharp = 1.f / (3.0f * 0.10f);
+    // the list order varies from run to run (slots come from an atomic counter): the energy is summed in 2^-32 fixed point,
+    // where addition is associative, so identical replicas still give bit-identical energies
+    long long en_fx = 0;
+    for (int e = tid; e < m; e += BB_TPB) {   // phase 2: one thread per residue pair
+        const int i = list[e] >> 16, j = list[e] & 0xffffu;
+        const int na_i = n_atom[i], na_j = n_atom[j];
+        const float4 oi = org[i], oj = org[j];
+        f3 fi = mk3(0.f, 0.f, 0.f), ti = fi, tj = fi;
+        float en = 0.f;
+        bool any = false;
+        for (int b = 0; b < na_j; ++b) {
+            const float4 vj = atoms[4 * j + b];
+            const f3 xj = mk3(vj.x, vj.y, vj.z);
+            for (int a = 0; a < na_i; ++a) {
+                const float4 vi = atoms[4 * i + a];
+                const f3 xi = mk3(vi.x, vi.y, vi.z);
+                const f3 rv = xi - xj;
+                const float r2 = mag2(rv);
+                if (r2 > cutoff2) continue;
+                float val, der;
+                compact_sigmoid(r2 - 9.f, sharp, val, der);
+                const f3 g = (2.f * 4.f * der) * rv;   // force on atom a of residue i; -g on atom b of residue j
+                fi += g;
+                ti += cross(xi - mk3(oi.x, oi.y, oi.z), g);
+                tj -= cross(xj - mk3(oj.x, oj.y, oj.z), g);
+                en += 4.f * val;
+                any = true;
+            }
+        }
+        if (any) {
+            en_fx += __float2ll_rn(en * 4294967296.f);
+            float4* si = reinterpret_cast<float4*>(S.sens + (size_t(r) * S.n_node + S.loc[i]) * S.wp);
+            float4* sj = reinterpret_cast<float4*>(S.sens + (size_t(r) * S.n_node + S.loc[j]) * S.wp);
+            atomicAdd(si, make_float4(fi.x, fi.y, fi.z, ti.x));
+            atomicAdd(si + 1, make_float4(ti.y, ti.z, 0.f, 0.f));
+            atomicAdd(sj, make_float4(-fi.x, -fi.y, -fi.z, tj.x));
+            atomicAdd(sj + 1, make_float4(tj.y, tj.z, 0.f, 0.f));
+        }
+    }
+    if (want_pot) {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) en_fx += __shfl_down_sync(UB_FULL_MASK, en_fx, o);
+        if ((tid & 31) == 0) sc[tid >> 5] = en_fx;
+        __syncthreads();
+        if (tid == 0) {
+            long long tot = 0;
+            for (int w = 0; w < BB_TPB / 32; ++w) tot += sc[w];
+            atomicAdd(pot + r, float(double(tot) * (1.0 / 4294967296.0)));
+        }
+    }
+}
+
 struct BackbonePairs : PotentialNode {
     CoordNode& alignment;
     int n_residue, K = 0;
@@ -113,12 +216,22 @@ struct BackbonePairs : PotentialNode {
         dist_cutoff = 2 * max_dev + sqrtf(3.f * 3.f + 0.1f * 3.f);
         d_residue.upload(residue); d_id.upload(id); d_n_atom.upload(n_atom); d_ref.upload(ref);
     }
+    int list_cap = 0;
+    size_t smem_fused = 0;
+    bool fused = false;
     void finalize() override {
         double k = 8. + 0.55 * double(dist_cutoff) * dist_cutoff * dist_cutoff / 4.;   // residues, not beads
         K = std::max(1, (int)std::min<double>(n_residue, std::ceil(k)));
         nbr.alloc(size_t(engine->n_rep) * n_residue * K);
         cnt.alloc(size_t(engine->n_rep) * n_residue);
         atoms.alloc(size_t(engine->n_rep) * n_residue * 16);
+        // fused kernel: atoms + origins + the pair list (every pair once) of one replica in shared memory
+        list_cap = std::max(64, (n_residue * K + 1) / 2);
+        smem_fused = sizeof(float4) * 5 * size_t(n_residue) + sizeof(unsigned) * size_t(list_cap);
+        int lim = 0;
+        UB_CUDA(cudaDeviceGetAttribute(&lim, cudaDevAttrMaxSharedMemoryPerBlockOptin, engine->device));
+        fused = n_residue < 65536 && smem_fused <= (size_t)lim && !getenv("UPSIDE_B200_BACKBONE_GATHER");
+        if (fused) UB_CUDA(cudaFuncSetAttribute(k_backbone_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fused));
     }
     IGraphSide side() const {
         return IGraphSide{alignment.output, alignment.sens, alignment.n_elem, alignment.wp, d_residue.p, nullptr, d_id.p, n_residue};
@@ -126,6 +239,11 @@ struct BackbonePairs : PotentialNode {
     void compute_value(cudaStream_t s, ComputeMode mode) override {
         if (!n_residue) return;
         IGraphSide S = side();
+        if (fused) {
+            k_backbone_fused<<<engine->n_rep, BB_TPB, smem_fused, s>>>(S, d_ref.p, d_n_atom.p, dist_cutoff * dist_cutoff, list_cap, potential,
+                                                                       mode == PotentialAndDerivMode, engine->error_flag.p);
+            return;
+        }
         constexpr int TILE = 128;
         k_pairlist<TILE><<<dim3((n_residue + TILE - 1) / TILE, engine->n_rep), TILE, 0, s>>>(
             S, S, nbr.p, cnt.p, K, dist_cutoff * dist_cutoff, EXCL_SEQ1, 1, 1, engine->error_flag.p, nullptr, nullptr, 0);
@@ -136,6 +254,12 @@ struct BackbonePairs : PotentialNode {
     }
     bool get_pairlist(int replica, std::vector<int>& i1, std::vector<int>& i2) override {
         engine->sync_and_check();
+        if (fused) {   // the hot path keeps no list in global memory: build the reference's list for the accessor
+            constexpr int TILE = 128;
+            k_pairlist<TILE><<<dim3((n_residue + TILE - 1) / TILE, engine->n_rep), TILE>>>(
+                side(), side(), nbr.p, cnt.p, K, dist_cutoff * dist_cutoff, EXCL_SEQ1, 1, 1, engine->error_flag.p, nullptr, nullptr, 0);
+            engine->sync_and_check();
+        }
         std::vector<unsigned short> rows(size_t(n_residue) * K);
         std::vector<int> c(n_residue);
         UB_CUDA(cudaMemcpy(rows.data(), nbr.p + size_t(replica) * n_residue * K, rows.size() * 2, cudaMemcpyDeviceToHost));

@@ -137,7 +137,8 @@ __global__ void __launch_bounds__(PREP_TPB) k_rot_prep(RotamerDev P) {
         int loc = P.g.s1.loc[i];
         for (int p = 0; p < P.n_prob; ++p) e += P.prob_out[p][(size_t(r) * P.prob_n[p] + loc) * P.prob_wp[p]];
         int A = P.bead_res[i], ra = P.bead_rot[i];
-        atomicAdd(&en[A * MAXR + ra], e);   // one contributor per state unless several beads share a state
+        // one contributor per state unless several beads share a state (a shared-memory float atomicAdd is a CAS loop)
+        if (P.multi_bead_states) atomicAdd(&en[A * MAXR + ra], e); else en[A * MAXR + ra] = e;
         rr[i] = (A << 4) | (ra << 1) | (P.res_nrot[A] > 1 ? 1 : 0);
     }
     __syncthreads();
@@ -694,7 +695,7 @@ __device__ void bp_solve_generic(const RotamerDev& P, int want_pot, int r, float
     __syncthreads();
     for (int i = tid; i < P.n_bead; i += BP_TPB) {
         float f = P.fold[size_t(r) * P.n_bead + i];
-        if (f != 0.f) atomicAdd(&bel[P.bead_res[i] * MAXR + P.bead_rot[i]], f);
+        if (f != 0.f) { float* b = &bel[P.bead_res[i] * MAXR + P.bead_rot[i]]; if (P.multi_bead_states) atomicAdd(b, f); else *b += f; }
     }
     __syncthreads();
     for (int i = tid; i < nR * MAXR; i += BP_TPB) {
@@ -1018,7 +1019,7 @@ __global__ void __launch_bounds__(BP2_TPB, BP2_OCC) k_rot_bp2(RotamerDev P, Bp2L
     __syncthreads();
     for (int i = tid; i < P.n_bead; i += BP2_TPB) {
         float f = P.fold[size_t(r) * P.n_bead + i];
-        if (f != 0.f) atomicAdd(&bel[P.bead_rot[i] * nRp + P.bead_res[i]], f);
+        if (f != 0.f) { float* b = &bel[P.bead_rot[i] * nRp + P.bead_res[i]]; if (P.multi_bead_states) atomicAdd(b, f); else *b += f; }
     }
     __syncthreads();
     for (int i = tid; i < 6 * nR; i += BP2_TPB) {
