@@ -181,6 +181,22 @@ def gpu_arm(args):
     launches = eng.launches_per_eval()
     if rank == 0:
         roof = kernel_rooflines(eng, stream, torch)
+    # force-evaluation latency of BASELINE config 2 (76 residues, ONE replica) through the reference's own C ABI
+    # (evaluate_deriv of include/engine_c_library.h: host positions in, host derivatives out, synchronous)
+    latency = None
+    if rank == 0:
+        cfg2 = os.path.join(ROOT, 'configs', 'config2_76res.up')
+        up = ue.Upside(cfg2)
+        p2 = np.ascontiguousarray(up.initial_pos, dtype='f4')
+        for _ in range(20):
+            up.deriv(p2)
+        t0 = time.perf_counter()
+        n_lat = 200
+        for _ in range(n_lat):
+            up.deriv(p2)
+        latency = dict(us_per_force_eval=(time.perf_counter() - t0) * 1e6 / n_lat, workload='config2: 76-residue chain, 1 replica, '
+                       'evaluate_deriv through the single-system C ABI (host buffers, synchronous)', evaluations=n_lat)
+        del up
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
         cpu = cpu_reference_arm(args.steps, 3, target_seconds=12.0)
@@ -194,7 +210,7 @@ def gpu_arm(args):
                                 equilibration='%d untimed rounds from random_initial_config before warm-up' % EQUIL_ROUNDS),
                     us_per_force_eval=ms * 1e3 / (3 * args.steps), clocks=sampler.summary(),
                     e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=bytes_io, d2h_bytes_per_step=bytes_io, steps=e2e_steps),
-                    gpu_launches=int((launches * 3 + 3 + 2) * args.steps), roofline=roof,
+                    gpu_launches=int((launches * 3 + 3 + 2) * args.steps), roofline=roof, single_replica_latency=latency,
                     cpu_baseline=({k: cpu[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')} if cpu else None))
         emit(line)
     eng.close()
