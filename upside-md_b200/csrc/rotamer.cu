@@ -1,16 +1,20 @@
 // RotamerSidechain on the B200 (reference src/rotamer.cpp).  Four kernels per evaluation, all batched over replicas:
 //
 //   k_rot_prep    one CTA per replica: residue adjacency bitmap (shared memory) from the bead ELL rows -> a slot for
-//                 every residue pair by prefix popcount, incidence lists, a per-neighbour-entry "code" saying where the
-//                 pair energy goes / where its sensitivity comes from, 1-body node energies.
-//   k_rot_energy  throughput-shaped: beads + the B-spline table staged in shared memory, 8 lanes walk each bead's row,
-//                 pair energies -> residue-pair matrices; partners with a single rotamer state are folded into the
-//                 bead's node energy (fill_holders, rotamer.cpp:793-852).
-//   k_rot_bp      one CTA per replica, state resident in shared memory (pair matrices, messages, beliefs): damped
-//                 loopy belief propagation (solve_for_marginals :1005-1061, update_beliefs :453-522,
-//                 standardize_belief_update :258-273), marginals (:275-281,403-429), Bethe free energy (:292-302,431-451).
-//   k_rot_deriv   throughput-shaped: per bead, sum over partners of marginal * dV/d(bead) with the pair term recomputed
-//                 (propagate_derivatives :956-985), node marginals into the 1-body sens.
+//                 every residue pair by prefix popcount, incidence lists, and the bead pairs as CSR rows (partner + a
+//                 "code" saying where the pair energy goes / which marginal weights its derivative), rows sorted by
+//                 length for the thread-per-row consumers, 1-body node energies.
+//   k_rot_energy  throughput-shaped, persistent: the B-spline table staged once per CTA and shared by the two replicas a CTA
+//                 serves at a time, beads staged per replica; ONE THREAD PER CSR ROW walks the partners above the bead,
+//                 pair energies -> residue-pair matrices; partners with a single rotamer state are folded into the bead's
+//                 node energy (fill_holders, rotamer.cpp:793-852).
+//   k_rot_bp2     one CTA per replica, state resident in shared memory (pair matrices, messages, beliefs): damped loopy
+//                 belief propagation (solve_for_marginals :1005-1061, update_beliefs :453-522, standardize_belief_update
+//                 :258-273), marginals (:275-281,403-429), Bethe free energy (:292-302,431-451), and the backward weight of
+//                 every CSR entry; k_rot_bp is the general path for replicas that do not fit.
+//   k_rot_deriv   same shape as k_rot_energy: per bead, sum over ALL partners of weight * dV/d(bead) with the pair term
+//                 recomputed (propagate_derivatives :956-985) - gather form, fixed order, no atomics; node marginals into
+//                 the 1-body sens.
 //
 // Bead ids encode (residue k << 8 | n_rot << 4 | rot) (upside_config.py:976-983).  Differences of formulation, not of
 // result: residue pairs get slots from an adjacency bitmap instead of the reference's open-addressed EdgeLocator
@@ -26,7 +30,15 @@ namespace {
 
 constexpr int MAXR = 6;            // most rotamer states per residue (UPPER_ROT-1 in the reference)
 constexpr int PREP_TPB = 256;
-constexpr int EDGE_TPB = 256;
+#ifndef UB_EDGE_MAXT
+#define UB_EDGE_MAXT 448   // two replicas per CTA (2 x 224 threads at 100 residues) ...
+#endif
+#ifndef UB_EDGE_OCC
+#define UB_EDGE_OCC 2     // ... and two CTAs per SM: 28 warps per SM instead of 21 with one table copy per replica (measured -11 %)
+#endif
+constexpr int EDGE_TPB = 256;            // most threads on the rows of ONE replica
+constexpr int EDGE_MAXT = UB_EDGE_MAXT;  // most threads of an edge-kernel CTA (several replicas share one staged table)
+constexpr int EDGE_OCC = UB_EDGE_OCC;
 constexpr int BP_TPB = 384;
 constexpr int MAX_PROB_NODES = 4;
 constexpr int CODE_SS = INT_MIN;   // (single, single)
@@ -319,8 +331,8 @@ __device__ __forceinline__ void stage_table(const RotamerDev& P, float* table, i
         rowoff[i] = (row * P.g.n_param) << 1 | (swap ? 1 : 0);
     }
 }
-__device__ __forceinline__ void stage_beads(const RotamerDev& P, int r, BeadRec* beads) {
-    for (int i = threadIdx.x; i < P.n_bead; i += blockDim.x) {
+__device__ __forceinline__ void stage_beads(const RotamerDev& P, int r, BeadRec* beads, int t_in, int tpr) {
+    for (int i = t_in; i < P.n_bead; i += tpr) {
         const float* p = elem_ptr(P.g.s1, r, i);
         float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
         BeadRec br;
@@ -403,19 +415,23 @@ constexpr int PF = 4;   // row entries fetched per step: the index/code/weight l
 // reduced across lanes and every sum has a fixed order.  CTAs are persistent over replicas (blockIdx.y strides); with a
 // small batch the rows of a replica are split over gridDim.x CTAs.
 template <int NKA, int NK>
-__global__ void __launch_bounds__(EDGE_TPB, 3) k_rot_energy(RotamerDev P, int want_pot, int n_rep) {
+__global__ void __launch_bounds__(EDGE_MAXT, EDGE_OCC) k_rot_energy(RotamerDev P, int want_pot, int n_rep, int tpr) {
     extern __shared__ float4 smem4[];
-    BeadRec* beads = reinterpret_cast<BeadRec*>(smem4);
-    float* table = reinterpret_cast<float*>(beads + P.n_bead);
+    // a CTA serves G = blockDim.x / tpr replicas at a time: one staged table, G bead arrays, `tpr` threads (whole warps) each
+    const int G = blockDim.x / tpr, g = threadIdx.x / tpr, t_in = threadIdx.x - g * tpr;
+    BeadRec* beads = reinterpret_cast<BeadRec*>(smem4) + size_t(g) * P.n_bead;
+    float* table = reinterpret_cast<float*>(reinterpret_cast<BeadRec*>(smem4) + size_t(G) * P.n_bead);
     int* rowoff = reinterpret_cast<int*>(table + (((P.n_type * (P.n_type + 1) / 2) * P.g.n_param + 3) & ~3));
     const PairTab T{table, rowoff};
     const int nb = P.n_bead;
     stage_table(P, table, rowoff);
     const bool fe_on = want_pot && *P.fe_flag;
-    for (int r = blockIdx.y; r < n_rep; r += gridDim.y) {
+    for (int rb = blockIdx.y * G; rb < n_rep; rb += gridDim.y * G) {
+        const int r = rb + g;
         __syncthreads();   // previous replica's readers are done with `beads`
-        stage_beads(P, r, beads);
+        if (r < n_rep) stage_beads(P, r, beads, t_in, tpr);
         __syncthreads();
+        if (r >= n_rep) continue;
         const int* rowstart = P.rowstart + size_t(r) * (nb + 1);
         const unsigned short* dj = P.dj + size_t(r) * P.cap_e;
         const int* code = P.code + size_t(r) * P.cap_e;
@@ -424,9 +440,9 @@ __global__ void __launch_bounds__(EDGE_TPB, 3) k_rot_energy(RotamerDev P, int wa
         float* pmat = P.pmat + size_t(r) * P.max_pairs * 36;
         float e11 = 0.f;
         // boustrophedon over the length-sorted rows: a thread's long row of one pass is followed by a short one in the next
-        for (int t0 = 0, pass = 0; t0 < nb; t0 += gridDim.x * blockDim.x, ++pass) {
-            const int tl = blockIdx.x * blockDim.x + threadIdx.x;
-            const int t = t0 + ((pass & 1) ? gridDim.x * blockDim.x - 1 - tl : tl);
+        for (int t0 = 0, pass = 0; t0 < nb; t0 += gridDim.x * tpr, ++pass) {
+            const int tl = blockIdx.x * tpr + t_in;
+            const int t = t0 + ((pass & 1) ? gridDim.x * tpr - 1 - tl : tl);
             if (t >= nb) continue;
             const int i = order[t];
             const BeadRec bi = beads[i];
@@ -472,27 +488,30 @@ __global__ void __launch_bounds__(EDGE_TPB, 3) k_rot_energy(RotamerDev P, int wa
 // launch against 358 us for this gather form: sm_100a has no native shared-memory float add, atomicAdd compiles to an
 // ATOMS.CAST.SPIN compare-and-swap loop.)
 template <int NKA, int NK>
-__global__ void __launch_bounds__(EDGE_TPB, 3) k_rot_deriv(RotamerDev P, int n_rep) {
+__global__ void __launch_bounds__(EDGE_MAXT, EDGE_OCC) k_rot_deriv(RotamerDev P, int n_rep, int tpr) {
     extern __shared__ float4 smem4[];
-    BeadRec* beads = reinterpret_cast<BeadRec*>(smem4);
-    float* table = reinterpret_cast<float*>(beads + P.n_bead);
+    const int G = blockDim.x / tpr, g = threadIdx.x / tpr, t_in = threadIdx.x - g * tpr;
+    BeadRec* beads = reinterpret_cast<BeadRec*>(smem4) + size_t(g) * P.n_bead;
+    float* table = reinterpret_cast<float*>(reinterpret_cast<BeadRec*>(smem4) + size_t(G) * P.n_bead);
     int* rowoff = reinterpret_cast<int*>(table + (((P.n_type * (P.n_type + 1) / 2) * P.g.n_param + 3) & ~3));
     const PairTab T{table, rowoff};
     const int nb = P.n_bead;
     stage_table(P, table, rowoff);
-    for (int r = blockIdx.y; r < n_rep; r += gridDim.y) {
+    for (int rb = blockIdx.y * G; rb < n_rep; rb += gridDim.y * G) {
+        const int r = rb + g;
         __syncthreads();
-        stage_beads(P, r, beads);
+        if (r < n_rep) stage_beads(P, r, beads, t_in, tpr);
         __syncthreads();
+        if (r >= n_rep) continue;
         const int* rowstart = P.rowstart + size_t(r) * (nb + 1);
         const unsigned short* dj = P.dj + size_t(r) * P.cap_e;
         const float* ssr = P.ss + size_t(r) * P.cap_e;
         const unsigned short* order = P.order_d + size_t(r) * nb;
         const float* nm = P.node_marg + size_t(r) * P.n_res * MAXR;
         // boustrophedon over the length-sorted rows: a thread's long row of one pass is followed by a short one in the next
-        for (int t0 = 0, pass = 0; t0 < nb; t0 += gridDim.x * blockDim.x, ++pass) {
-            const int tl = blockIdx.x * blockDim.x + threadIdx.x;
-            const int t = t0 + ((pass & 1) ? gridDim.x * blockDim.x - 1 - tl : tl);
+        for (int t0 = 0, pass = 0; t0 < nb; t0 += gridDim.x * tpr, ++pass) {
+            const int tl = blockIdx.x * tpr + t_in;
+            const int t = t0 + ((pass & 1) ? gridDim.x * tpr - 1 - tl : tl);
             if (t >= nb) continue;
             const int i = order[t];
             const BeadRec bi = beads[i];
@@ -1201,7 +1220,7 @@ struct RotamerSidechain : PotentialNode {
     DevBuf<int> d_bead_res, d_bead_rot, d_res_nrot, inc, istart, stats, code, rowstart;
     DevBuf<float> pmat, node_marg, enode, fold, e11, table, ss;
     DevBuf<unsigned short> pair_ab, dj, lower, order_e, order_d;
-    int cap_e = 0, edge_tpb = EDGE_TPB, edge_split = 1;
+    int cap_e = 0, edge_tpb = EDGE_TPB, edge_split = 1, edge_G = 1, edge_grid = 1;
     float damping, tol;
     int max_iter, chunk;
     size_t smem_prep = 0, smem_edge = 0, smem_bp = 0, smem_bp2 = 0;
@@ -1312,7 +1331,10 @@ struct RotamerSidechain : PotentialNode {
             edge_tpb = 64;
             edge_split = std::max(1, std::min((ig.n1 + 63) / 64, 600 / std::max(1, engine->n_rep)));
         }
-        smem_edge = sizeof(BeadRec) * size_t(ig.n1) + sizeof(float) * (table.n + 4) + sizeof(int) * size_t(ig.n_type1) * ig.n_type1 + 64;
+        // replicas per CTA (they share one staged copy of the 52 KB table): as many as the thread bound of the build allows
+        edge_G = edge_split == 1 ? std::max(1, EDGE_MAXT / edge_tpb) : 1;
+        if (const char* e = getenv("UPSIDE_B200_EDGE_G")) edge_G = std::max(1, std::min(atoi(e), EDGE_MAXT / edge_tpb));
+        smem_edge = sizeof(BeadRec) * size_t(ig.n1) * edge_G + sizeof(float) * (table.n + 4) + sizeof(int) * size_t(ig.n_type1) * ig.n_type1 + 64;
         if (ig.n_type1 > 255) throw std::string("rotamer node: more than 255 bead types");
         if (smem_prep > (size_t)device_smem || smem_edge > (size_t)device_smem || fixed_bp > (size_t)device_smem)
             throw std::string("rotamer node: system too large for the shared-memory kernels");
@@ -1409,14 +1431,14 @@ struct RotamerSidechain : PotentialNode {
         ig.build(s);
         RotamerDev P = dev();
         int want = mode == PotentialAndDerivMode;
-        // edge kernels: persistent CTAs (3 resident per SM by shared memory) striding over the replicas
-        int persist = std::min(engine->n_rep, 148 * 3);
+        // edge kernels: persistent CTAs (as many as stay resident) striding over the replicas, edge_G replicas at a time
+        int persist = std::min((engine->n_rep + edge_G - 1) / edge_G, 148 * EDGE_OCC);
         engine->mark(s, "rotamer/pairlist");
         k_rot_prep<<<engine->n_rep, PREP_TPB, smem_prep, s>>>(P);
         engine->mark(s, "rotamer/prep");
         const bool ff1_knots = nka == 15 && nk == 16;   // the PARAM_7A_CUTOFF build of the reference (bead_interaction.h:12-27)
-        if (ff1_knots) k_rot_energy<15, 16><<<dim3(edge_split, persist), edge_tpb, smem_edge, s>>>(P, want, engine->n_rep);
-        else k_rot_energy<0, 0><<<dim3(edge_split, persist), edge_tpb, smem_edge, s>>>(P, want, engine->n_rep);
+        if (ff1_knots) k_rot_energy<15, 16><<<dim3(edge_split, persist), edge_tpb * edge_G, smem_edge, s>>>(P, want, engine->n_rep, edge_tpb);
+        else k_rot_energy<0, 0><<<dim3(edge_split, persist), edge_tpb * edge_G, smem_edge, s>>>(P, want, engine->n_rep, edge_tpb);
         engine->mark(s, "rotamer/energy");
         if (fast_bp) {
             k_rot_bp2<<<engine->n_rep, BP2_TPB, smem_bp2, s>>>(P, lay2, want);
@@ -1425,8 +1447,8 @@ struct RotamerSidechain : PotentialNode {
             k_rot_bp<<<engine->n_rep, BP_TPB, smem_bp, s>>>(P, want, 0);
         }
         engine->mark(s, "rotamer/bp");
-        if (ff1_knots) k_rot_deriv<15, 16><<<dim3(edge_split, persist), edge_tpb, smem_edge, s>>>(P, engine->n_rep);
-        else k_rot_deriv<0, 0><<<dim3(edge_split, persist), edge_tpb, smem_edge, s>>>(P, engine->n_rep);
+        if (ff1_knots) k_rot_deriv<15, 16><<<dim3(edge_split, persist), edge_tpb * edge_G, smem_edge, s>>>(P, engine->n_rep, edge_tpb);
+        else k_rot_deriv<0, 0><<<dim3(edge_split, persist), edge_tpb * edge_G, smem_edge, s>>>(P, engine->n_rep, edge_tpb);
         engine->mark(s, "rotamer/deriv");
     }
     bool get_pairlist(int replica, std::vector<int>& i1, std::vector<int>& i2) override { return ig.pairlist(replica, i1, i2); }
