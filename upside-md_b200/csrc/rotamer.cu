@@ -845,19 +845,24 @@ struct Bp2Lay {
     int Pcap;    // floats available for pair matrices
 };
 
+// Pair matrices and messages are PAIR-major with odd strides (NA*NB + 1 for the 6x6 and 3x6 blocks, 9 for 3x3, MSG_STRIDE =
+// 13 for the twelve message components): a thread's own block sits at one base address, so every element is a load with
+// an immediate offset (component-major blocks cost one address instruction per element), and consecutive threads still hit
+// different banks because the stride is coprime with 32.
+constexpr int MSG_STRIDE = 13;
 template <int NA, int NB>
-__device__ __forceinline__ void bp2_pair(const float* __restrict__ bel, int nRp, int F, int S, float* __restrict__ msg, int SP, int p,
-                                         const float* __restrict__ Pc, int nc, int q) {
+__device__ __forceinline__ void bp2_pair(const float* __restrict__ bel, int nRp, int F, int S, float* __restrict__ msg_p,
+                                         const float* __restrict__ Pq) {
     float v1[NA], v2[NB], m1[NA], m2[NB];
 #pragma unroll
-    for (int a = 0; a < NA; ++a) { v1[a] = __fdividef(bel[a * nRp + F], 1e-10f + msg[a * SP + p]); m1[a] = 0.f; }
+    for (int a = 0; a < NA; ++a) { v1[a] = __fdividef(bel[a * nRp + F], 1e-10f + msg_p[a]); m1[a] = 0.f; }
 #pragma unroll
-    for (int b = 0; b < NB; ++b) { v2[b] = __fdividef(bel[b * nRp + S], 1e-10f + msg[(6 + b) * SP + p]); m2[b] = 0.f; }
+    for (int b = 0; b < NB; ++b) { v2[b] = __fdividef(bel[b * nRp + S], 1e-10f + msg_p[6 + b]); m2[b] = 0.f; }
 #pragma unroll
     for (int a = 0; a < NA; ++a)
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
-            float pr = Pc[(a * NB + b) * nc + q];
+            float pr = Pq[a * NB + b];
             m1[a] = fmaf(pr, v2[b], m1[a]);   // apply_left : message to the first residue
             m2[b] = fmaf(v1[a], pr, m2[b]);   // apply_right: message to the second residue
         }
@@ -868,35 +873,35 @@ __device__ __forceinline__ void bp2_pair(const float* __restrict__ bel, int nRp,
     for (int b = 0; b < NB; ++b) s2 += m2[b];
     float i1 = __fdividef(1.f, s1), i2 = __fdividef(1.f, s2);
 #pragma unroll
-    for (int a = 0; a < NA; ++a) msg[a * SP + p] = m1[a] * i1;
+    for (int a = 0; a < NA; ++a) msg_p[a] = m1[a] * i1;
 #pragma unroll
-    for (int b = 0; b < NB; ++b) msg[(6 + b) * SP + p] = m2[b] * i2;
+    for (int b = 0; b < NB; ++b) msg_p[6 + b] = m2[b] * i2;
 }
 
 // pair marginal (rotamer.cpp:403-429), in place of the pair's probability matrix in shared memory, plus its Bethe term
 // (:431-451)
 template <int NA, int NB>
-__device__ __forceinline__ float bp2_pair_marginal(const float* __restrict__ bel, int nRp, int F, int S, const float* __restrict__ msg,
-                                                   int SP, int p, float* __restrict__ Pc, int nc, int q, int want_pot) {
+__device__ __forceinline__ float bp2_pair_marginal(const float* __restrict__ bel, int nRp, int F, int S, const float* __restrict__ msg_p,
+                                                   float* __restrict__ Pq, int want_pot) {
     float bc1[NA], bc2[NB], b1[NA], b2[NB];
 #pragma unroll
-    for (int a = 0; a < NA; ++a) { b1[a] = bel[a * nRp + F]; bc1[a] = b1[a] / (1e-10f + msg[a * SP + p]); }
+    for (int a = 0; a < NA; ++a) { b1[a] = bel[a * nRp + F]; bc1[a] = b1[a] / (1e-10f + msg_p[a]); }
 #pragma unroll
-    for (int b = 0; b < NB; ++b) { b2[b] = bel[b * nRp + S]; bc2[b] = b2[b] / (1e-10f + msg[(6 + b) * SP + p]); }
+    for (int b = 0; b < NB; ++b) { b2[b] = bel[b * nRp + S]; bc2[b] = b2[b] / (1e-10f + msg_p[6 + b]); }
     float s = 0.f;
 #pragma unroll
     for (int a = 0; a < NA; ++a)
 #pragma unroll
-        for (int b = 0; b < NB; ++b) s += Pc[(a * NB + b) * nc + q] * bc1[a] * bc2[b];
+        for (int b = 0; b < NB; ++b) s += Pq[a * NB + b] * bc1[a] * bc2[b];
     float is = 1.f / s, en = 0.f;
 #pragma unroll
     for (int a = 0; a < NA; ++a)
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
-            float pr = Pc[(a * NB + b) * nc + q];
+            float pr = Pq[a * NB + b];
             float mg = pr * bc1[a] * bc2[b] * is;
             if (want_pot) en += mg * __logf((1e-10f + mg) / (1e-10f + pr * b1[a] * b2[b]));
-            Pc[(a * NB + b) * nc + q] = mg;
+            Pq[a * NB + b] = mg;
         }
     return en;
 }
@@ -907,7 +912,7 @@ __device__ __forceinline__ float bp2_pair_marginal(const float* __restrict__ bel
 // past the end of the list read the column of ones.
 template <int NA>
 __device__ __forceinline__ float bp2_node(int A, const float* __restrict__ prob, float* __restrict__ bel, int nRp, int t0, int t1,
-                                          const int* __restrict__ inc2, const float* __restrict__ msg, int SP, int dummy, float damping) {
+                                          const int* __restrict__ inc2, const float* __restrict__ msg, int dummy, float damping) {
     float b[NA];
 #pragma unroll
     for (int a = 0; a < NA; ++a) b[a] = prob[a * nRp + A];
@@ -919,7 +924,7 @@ __device__ __forceinline__ float bp2_node(int A, const float* __restrict__ prob,
 #pragma unroll
         for (int u = 0; u < 4; ++u)
 #pragma unroll
-            for (int a = 0; a < NA; ++a) m[u][a] = msg[off[u] + a * SP];
+            for (int a = 0; a < NA; ++a) m[u][a] = msg[off[u] + a];
         float s = 0.f;
 #pragma unroll
         for (int a = 0; a < NA; ++a) { b[a] *= (m[0][a] * m[1][a]) * (m[2][a] * m[3][a]); s += b[a]; }
@@ -956,8 +961,8 @@ __global__ void __launch_bounds__(BP2_TPB, BP2_OCC) k_rot_bp2(RotamerDev P, Bp2L
     int* istart = reinterpret_cast<int*>(red + 32);     // [nR+1]
     int* nrot = istart + nR + 1;                         // [nR]
     unsigned long long* wscan = reinterpret_cast<unsigned long long*>(nrot + nR + ((nR + 1) & 1));   // [34], 8-byte aligned
-    float* msg = reinterpret_cast<float*>(wscan + 34);   // [12][SP]
-    float* Pm = msg + 12 * SP;                           // [Pcap]: 6x6 block [36][n66] | 3x6 block [18][n36] | 3x3 block [9][n33]
+    float* msg = reinterpret_cast<float*>(wscan + 34);   // [SP][13] pair-major: side 0 in 0..5, side 1 in 6..11
+    float* Pm = msg + MSG_STRIDE * SP;                   // [Pcap]: 6x6 block [n66][37] | 3x6 block [n36][19] | 3x3 block [n33][9]
     int* inc2 = reinterpret_cast<int*>(Pm + L.Pcap);     // [2*SP] word offset of component 0 of each incident message
     unsigned short* pos = reinterpret_cast<unsigned short*>(inc2 + 2 * SP);   // [SP] slot e -> sorted position p
     unsigned short* perm = pos + SP;                     // [SP] p -> e
@@ -1004,7 +1009,7 @@ __global__ void __launch_bounds__(BP2_TPB, BP2_OCC) k_rot_bp2(RotamerDev P, Bp2L
         __syncthreads();
         const unsigned long long tot = wscan[32];
         n66 = int(tot & 0x1fffff); n36 = int((tot >> 21) & 0x1fffff); n33 = int((tot >> 42) & 0x1fffff);
-        const bool fits = n_pair <= SP - 1 && 36 * n66 + 18 * n36 + 9 * n33 <= L.Pcap;   // column SP-1 is the neutral message
+        const bool fits = n_pair <= SP - 1 && 37 * n66 + 19 * n36 + 9 * n33 <= L.Pcap;   // row SP-1 is the neutral message
         if (!fits) {   // uniform: k_rot_bp solves this replica
             if (tid == 0) P.slow_list[atomicAdd(P.n_slow, 1)] = r;
             return;
@@ -1024,8 +1029,8 @@ __global__ void __launch_bounds__(BP2_TPB, BP2_OCC) k_rot_bp2(RotamerDev P, Bp2L
         }
     }
     float* P66 = Pm;
-    float* P36 = Pm + 36 * n66;
-    float* P33 = P36 + 18 * n36;
+    float* P36 = Pm + 37 * n66;
+    float* P33 = P36 + 19 * n36;
 
     // ---- node energies -> probabilities (convert_energy_to_prob :239-256; single-state partners already folded) ----------
     for (int i = tid; i < nR * MAXR; i += BP2_TPB) { int A = i / MAXR, a = i % MAXR; bel[a * nRp + A] = P.enode[size_t(r) * nR * MAXR + i]; }
@@ -1055,26 +1060,26 @@ __global__ void __launch_bounds__(BP2_TPB, BP2_OCC) k_rot_bp2(RotamerDev P, Bp2L
             const int p = pos[e];
             const bool sw = nA > nB;
             const int nF = sw ? nB : nA, nS = sw ? nA : nB;
-            float* blk; int nc, q;
-            if (nF == 6) { blk = Pm; nc = n66; q = p; }
-            else if (nS == 6) { blk = Pm + 36 * n66; nc = n36; q = p - n66; }
-            else { blk = Pm + 36 * n66 + 18 * n36; nc = n33; q = p - n66 - n36; }
+            float* blk;   // the pair's own block
+            if (nF == 6) blk = P66 + 37 * p;
+            else if (nS == 6) blk = P36 + 19 * (p - n66);
+            else blk = P33 + 9 * (p - n66 - n36);
             const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 int k = k0 + u, a = k / 6, b = k - a * 6;
                 if (a < nA && b < nB) {
                     int f = sw ? b : a, s2 = sw ? a : b;
-                    blk[(f * nS + s2) * nc + q] = __expf(-vv[u]);
+                    blk[f * nS + s2] = __expf(-vv[u]);
                 }
             }
         }
     }
     for (int t = tid; t < 2 * n_pair; t += BP2_TPB) {
         int cd = inc[t], p = pos[cd >> 1];
-        inc2[t] = ((cd & 1) ^ (fs[2 * p] >> 15)) * 6 * SP + p;
+        inc2[t] = p * MSG_STRIDE + ((cd & 1) ^ (fs[2 * p] >> 15)) * 6;
     }
-    for (int k = tid; k < 12; k += BP2_TPB) msg[k * SP + SP - 1] = 1.f;
+    for (int k = tid; k < 12; k += BP2_TPB) msg[(SP - 1) * MSG_STRIDE + k] = 1.f;
     // residues in the order the node update takes them: rank by (state count, degree) falling, ties by index, so that the
     // threads of a warp run the same unrolled body for about the same number of steps
     for (int A = tid; A < nR; A += BP2_TPB) {
@@ -1092,7 +1097,7 @@ __global__ void __launch_bounds__(BP2_TPB, BP2_OCC) k_rot_bp2(RotamerDev P, Bp2L
     }
     for (int p = tid; p < n_pair; p += BP2_TPB) {
         int nF = nrot[fs[2 * p] & 0x7fff], nS = nrot[fs[2 * p + 1]];
-        for (int a = 0; a < 6; ++a) { msg[a * SP + p] = a < nF ? 1.f : 0.f; msg[(6 + a) * SP + p] = a < nS ? 1.f : 0.f; }
+        for (int a = 0; a < 6; ++a) { msg[p * MSG_STRIDE + a] = a < nF ? 1.f : 0.f; msg[p * MSG_STRIDE + 6 + a] = a < nS ? 1.f : 0.f; }
     }
     __syncthreads();
     for (int i = tid; i < 6 * nRp; i += BP2_TPB) bel[i] = prob[i];
@@ -1102,20 +1107,20 @@ __global__ void __launch_bounds__(BP2_TPB, BP2_OCC) k_rot_bp2(RotamerDev P, Bp2L
     auto messages = [&]() {
         for (int p = tid; p < n_pair; p += BP2_TPB) {
             const int F = fs[2 * p] & 0x7fff, S = fs[2 * p + 1];
-            if (p < n66) bp2_pair<6, 6>(bel, nRp, F, S, msg, SP, p, P66, n66, p);
-            else if (p < n66 + n36) bp2_pair<3, 6>(bel, nRp, F, S, msg, SP, p, P36, n36, p - n66);
-            else bp2_pair<3, 3>(bel, nRp, F, S, msg, SP, p, P33, n33, p - n66 - n36);
+            if (p < n66) bp2_pair<6, 6>(bel, nRp, F, S, msg + p * MSG_STRIDE, P66 + 37 * p);
+            else if (p < n66 + n36) bp2_pair<3, 6>(bel, nRp, F, S, msg + p * MSG_STRIDE, P36 + 19 * (p - n66));
+            else bp2_pair<3, 3>(bel, nRp, F, S, msg + p * MSG_STRIDE, P33 + 9 * (p - n66 - n36));
         }
     };
     const int n_multi = n_multi_s;
     const float damping = P.damping;
-    const int dummy = SP - 1;   // column SP-1 of the side-0 rows holds ones: the neutral message
+    const int dummy = (SP - 1) * MSG_STRIDE;   // row SP-1 holds ones: the neutral message
     auto nodes = [&]() -> float {
         float dev = 0.f;
         for (int i = tid; i < n_multi; i += BP2_TPB) {
             const int A = nlist[i];
-            if (nrot[A] == 6) dev = fmaxf(dev, bp2_node<6>(A, prob, bel, nRp, istart[A], istart[A + 1], inc2, msg, SP, dummy, damping));
-            else dev = fmaxf(dev, bp2_node<3>(A, prob, bel, nRp, istart[A], istart[A + 1], inc2, msg, SP, dummy, damping));
+            if (nrot[A] == 6) dev = fmaxf(dev, bp2_node<6>(A, prob, bel, nRp, istart[A], istart[A + 1], inc2, msg, dummy, damping));
+            else dev = fmaxf(dev, bp2_node<3>(A, prob, bel, nRp, istart[A], istart[A + 1], inc2, msg, dummy, damping));
         }
         return dev;
     };
@@ -1161,9 +1166,9 @@ __global__ void __launch_bounds__(BP2_TPB, BP2_OCC) k_rot_bp2(RotamerDev P, Bp2L
     for (int p = tid; p < n_pair; p += BP2_TPB) {
         const int F = fs[2 * p] & 0x7fff, S = fs[2 * p + 1];
         float en_pair;
-        if (p < n66) en_pair = bp2_pair_marginal<6, 6>(bel, nRp, F, S, msg, SP, p, P66, n66, p, want_pot);
-        else if (p < n66 + n36) en_pair = bp2_pair_marginal<3, 6>(bel, nRp, F, S, msg, SP, p, P36, n36, p - n66, want_pot);
-        else en_pair = bp2_pair_marginal<3, 3>(bel, nRp, F, S, msg, SP, p, P33, n33, p - n66 - n36, want_pot);
+        if (p < n66) en_pair = bp2_pair_marginal<6, 6>(bel, nRp, F, S, msg + p * MSG_STRIDE, P66 + 37 * p, want_pot);
+        else if (p < n66 + n36) en_pair = bp2_pair_marginal<3, 6>(bel, nRp, F, S, msg + p * MSG_STRIDE, P36 + 19 * (p - n66), want_pot);
+        else en_pair = bp2_pair_marginal<3, 3>(bel, nRp, F, S, msg + p * MSG_STRIDE, P33 + 9 * (p - n66 - n36), want_pot);
         en += en_pair;
         if (fe_on) { atomicAdd(&P.res_fe[size_t(r) * nR + F], 0.5f * en_pair); atomicAdd(&P.res_fe[size_t(r) * nR + S], 0.5f * en_pair); }
     }
@@ -1175,9 +1180,9 @@ __global__ void __launch_bounds__(BP2_TPB, BP2_OCC) k_rot_bp2(RotamerDev P, Bp2L
             const int p = pos[slot];
             const bool sw = fs[2 * p] >> 15;
             const int f = sw ? b : a, s2 = sw ? a : b;
-            if (p < n66) return P66[(f * 6 + s2) * n66 + p];
-            if (p < n66 + n36) return P36[(f * 6 + s2) * n36 + (p - n66)];
-            return P33[(f * 3 + s2) * n33 + (p - n66 - n36)];
+            if (p < n66) return P66[37 * p + f * 6 + s2];
+            if (p < n66 + n36) return P36[19 * (p - n66) + f * 6 + s2];
+            return P33[9 * (p - n66 - n36) + f * 3 + s2];
         },
         [&](int node) { const int A = node / MAXR; return bel[(node - A * MAXR) * nRp + A]; });
     if (want_pot) {
@@ -1368,10 +1373,10 @@ struct RotamerSidechain : PotentialNode {
         order_d.alloc(B * ig.n1);
     }
     // Shared-memory plan of k_rot_bp2: the most resident CTAs per SM (at most 3) whose pair capacity still covers a typical
-    // replica (3.8 residue pairs per residue; measured 2.6-3.3 on coil-like chains) with 26 floats of
-    // pair matrix per pair (class mix of a uniform sequence: 21.8).  Larger replicas take the general kernel.
+    // replica (3.8 residue pairs per residue; measured 2.6-3.3 on coil-like chains) with 27 floats of
+    // pair matrix per pair (class mix of a uniform sequence: 21.5).  Larger replicas take the general kernel.
     static size_t bp2_bytes(int nR, const Bp2Lay& L) {
-        size_t words = size_t(12) * L.nRp + nR + 32 + (2 * nR + 1) + ((nR + 1) & 1) + 2 * 34 + size_t(12) * L.SP + L.Pcap;
+        size_t words = size_t(12) * L.nRp + nR + 32 + (2 * nR + 1) + ((nR + 1) & 1) + 2 * 34 + size_t(MSG_STRIDE) * L.SP + L.Pcap;
         return (words + 2 * size_t(L.SP)) * 4 + (size_t(4) * L.SP + nR) * 2 + 16;
     }
     void plan_fast_bp(int device_smem) {
@@ -1389,13 +1394,13 @@ struct RotamerSidechain : PotentialNode {
             L.SP = pad4(4); L.Pcap = 0;
             size_t fixed = bp2_bytes(n_res, L);
             if (fixed >= budget) continue;
-            int sp = (int)std::min<size_t>(max_pairs + 1, (budget - fixed) / (12 * 4 + 26 * 4 + 16));
+            int sp = (int)std::min<size_t>(max_pairs + 1, (budget - fixed) / (MSG_STRIDE * 4 + 27 * 4 + 16));
             sp = std::min(sp, 32767);
             if (sp < want_pairs + 1 && occ > 1) continue;
             if (sp < 8) continue;
             L.SP = pad4(sp) > sp ? pad4(sp) - 32 : sp;   // largest value <= sp that is 4 mod 32
             if (L.SP < 4) continue;
-            L.Pcap = 26 * L.SP;
+            L.Pcap = 27 * L.SP;
             lay2 = L;
             smem_bp2 = bp2_bytes(n_res, L);
             UB_CUDA(cudaFuncSetAttribute(k_rot_bp2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bp2));
