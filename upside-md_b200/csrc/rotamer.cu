@@ -840,7 +840,7 @@ constexpr int BP2_TPB = UB_BP2_TPB;
 constexpr int BP2_OCC = UB_BP2_OCC;
 
 struct Bp2Lay {
-    int nRp;     // padded residue count of the component-major belief arrays (== 4 mod 32: conflict-free node update)
+    int nRp;     // residue count of the node-major probability / belief arrays
     int SP;      // pair capacity (== 4 mod 32)
     int Pcap;    // floats available for pair matrices
 };
@@ -850,14 +850,15 @@ struct Bp2Lay {
 // an immediate offset (component-major blocks cost one address instruction per element), and consecutive threads still hit
 // different banks because the stride is coprime with 32.
 constexpr int MSG_STRIDE = 13;
+constexpr int NODE_STRIDE = 7;   // probabilities and beliefs node-major: six states + one word of padding (odd stride)
 template <int NA, int NB>
 __device__ __forceinline__ void bp2_pair(const float* __restrict__ bel, int nRp, int F, int S, float* __restrict__ msg_p,
                                          const float* __restrict__ Pq) {
     float v1[NA], v2[NB], m1[NA], m2[NB];
 #pragma unroll
-    for (int a = 0; a < NA; ++a) { v1[a] = __fdividef(bel[a * nRp + F], 1e-10f + msg_p[a]); m1[a] = 0.f; }
+    for (int a = 0; a < NA; ++a) { v1[a] = __fdividef(bel[(F) * NODE_STRIDE + a], 1e-10f + msg_p[a]); m1[a] = 0.f; }
 #pragma unroll
-    for (int b = 0; b < NB; ++b) { v2[b] = __fdividef(bel[b * nRp + S], 1e-10f + msg_p[6 + b]); m2[b] = 0.f; }
+    for (int b = 0; b < NB; ++b) { v2[b] = __fdividef(bel[(S) * NODE_STRIDE + b], 1e-10f + msg_p[6 + b]); m2[b] = 0.f; }
 #pragma unroll
     for (int a = 0; a < NA; ++a)
 #pragma unroll
@@ -885,9 +886,9 @@ __device__ __forceinline__ float bp2_pair_marginal(const float* __restrict__ bel
                                                    float* __restrict__ Pq, int want_pot) {
     float bc1[NA], bc2[NB], b1[NA], b2[NB];
 #pragma unroll
-    for (int a = 0; a < NA; ++a) { b1[a] = bel[a * nRp + F]; bc1[a] = b1[a] / (1e-10f + msg_p[a]); }
+    for (int a = 0; a < NA; ++a) { b1[a] = bel[(F) * NODE_STRIDE + a]; bc1[a] = b1[a] / (1e-10f + msg_p[a]); }
 #pragma unroll
-    for (int b = 0; b < NB; ++b) { b2[b] = bel[b * nRp + S]; bc2[b] = b2[b] / (1e-10f + msg_p[6 + b]); }
+    for (int b = 0; b < NB; ++b) { b2[b] = bel[(S) * NODE_STRIDE + b]; bc2[b] = b2[b] / (1e-10f + msg_p[6 + b]); }
     float s = 0.f;
 #pragma unroll
     for (int a = 0; a < NA; ++a)
@@ -915,7 +916,7 @@ __device__ __forceinline__ float bp2_node(int A, const float* __restrict__ prob,
                                           const int* __restrict__ inc2, const float* __restrict__ msg, int dummy, float damping) {
     float b[NA];
 #pragma unroll
-    for (int a = 0; a < NA; ++a) b[a] = prob[a * nRp + A];
+    for (int a = 0; a < NA; ++a) b[a] = prob[(A) * NODE_STRIDE + a];
     for (int t = t0; t < t1; t += 4) {
         int off[4];
         float m[4][NA];
@@ -940,10 +941,10 @@ __device__ __forceinline__ float bp2_node(int A, const float* __restrict__ prob,
     float dev = 0.f;
 #pragma unroll
     for (int a = 0; a < NA; ++a) {
-        const float o = bel[a * nRp + A];
+        const float o = bel[(A) * NODE_STRIDE + a];
         const float n = (damping != 0.f) ? (1.f - damping) * imx * b[a] + damping * o : imx * b[a];
         dev = fmaxf(dev, n - o);
-        bel[a * nRp + A] = n;
+        bel[(A) * NODE_STRIDE + a] = n;
     }
     return dev;
 }
@@ -954,9 +955,9 @@ __global__ void __launch_bounds__(BP2_TPB, BP2_OCC) k_rot_bp2(RotamerDev P, Bp2L
     const int nR = P.n_res, nRp = L.nRp, SP = L.SP;
     const bool fe_on = want_pot && *P.fe_flag;
     const int n_pair = P.stats[size_t(r) * 4 + 1];
-    float* prob = smem;                          // [6][nRp]
-    float* bel = prob + 6 * nRp;                 // [6][nRp]
-    float* offs = bel + 6 * nRp;                 // [nR]
+    float* prob = smem;                          // [nRp][7] node-major
+    float* bel = prob + NODE_STRIDE * nRp;       // [nRp][7]
+    float* offs = bel + NODE_STRIDE * nRp;       // [nR]
     float* red = offs + nR;                      // [32]
     int* istart = reinterpret_cast<int*>(red + 32);     // [nR+1]
     int* nrot = istart + nR + 1;                         // [nR]
@@ -979,7 +980,7 @@ __global__ void __launch_bounds__(BP2_TPB, BP2_OCC) k_rot_bp2(RotamerDev P, Bp2L
     if (tid == 0) n_multi_s = 0;
     for (int i = tid; i < nR; i += BP2_TPB) nrot[i] = P.res_nrot[i];
     for (int i = tid; i <= nR; i += BP2_TPB) istart[i] = P.istart[size_t(r) * (nR + 1) + i];
-    for (int i = tid; i < 6 * nRp; i += BP2_TPB) bel[i] = 0.f;
+    for (int i = tid; i < NODE_STRIDE * nRp; i += BP2_TPB) { bel[i] = 0.f; prob[i] = 0.f; }
     __syncthreads();
 
     // ---- orient and sort the pairs by class: one packed scan (three 21-bit counters) -------------------------------------
@@ -1033,23 +1034,23 @@ __global__ void __launch_bounds__(BP2_TPB, BP2_OCC) k_rot_bp2(RotamerDev P, Bp2L
     float* P33 = P36 + 19 * n36;
 
     // ---- node energies -> probabilities (convert_energy_to_prob :239-256; single-state partners already folded) ----------
-    for (int i = tid; i < nR * MAXR; i += BP2_TPB) { int A = i / MAXR, a = i % MAXR; bel[a * nRp + A] = P.enode[size_t(r) * nR * MAXR + i]; }
+    for (int i = tid; i < nR * MAXR; i += BP2_TPB) { int A = i / MAXR, a = i % MAXR; bel[(A) * NODE_STRIDE + a] = P.enode[size_t(r) * nR * MAXR + i]; }
     __syncthreads();
     for (int A = tid; A < nR; A += BP2_TPB) {   // energy offset = smallest 1-body energy
-        float m = bel[A];
-        for (int a = 1; a < nrot[A]; ++a) m = fminf(m, bel[a * nRp + A]);
+        float m = bel[A * NODE_STRIDE];
+        for (int a = 1; a < nrot[A]; ++a) m = fminf(m, bel[(A) * NODE_STRIDE + a]);
         offs[A] = m;
     }
     __syncthreads();
     for (int i = tid; i < P.n_bead; i += BP2_TPB) {
         float f = P.fold[size_t(r) * P.n_bead + i];
-        if (f != 0.f) { float* b = &bel[P.bead_rot[i] * nRp + P.bead_res[i]]; if (P.multi_bead_states) atomicAdd(b, f); else *b += f; }
+        if (f != 0.f) { float* b = &bel[P.bead_res[i] * NODE_STRIDE + P.bead_rot[i]]; if (P.multi_bead_states) atomicAdd(b, f); else *b += f; }
     }
     __syncthreads();
     for (int i = tid; i < 6 * nR; i += BP2_TPB) {
         int a = i / nR, A = i - a * nR;
-        float pr = a < nrot[A] ? __expf(offs[A] - bel[a * nRp + A]) : 0.f;
-        prob[a * nRp + A] = pr;
+        float pr = a < nrot[A] ? __expf(offs[A] - bel[(A) * NODE_STRIDE + a]) : 0.f;
+        prob[(A) * NODE_STRIDE + a] = pr;
     }
     {   // pair energies -> probabilities: coalesced 16-byte reads of the replica's pair-major energy array
         const float4* src = reinterpret_cast<const float4*>(g_pmat);
@@ -1100,7 +1101,7 @@ __global__ void __launch_bounds__(BP2_TPB, BP2_OCC) k_rot_bp2(RotamerDev P, Bp2L
         for (int a = 0; a < 6; ++a) { msg[p * MSG_STRIDE + a] = a < nF ? 1.f : 0.f; msg[p * MSG_STRIDE + 6 + a] = a < nS ? 1.f : 0.f; }
     }
     __syncthreads();
-    for (int i = tid; i < 6 * nRp; i += BP2_TPB) bel[i] = prob[i];
+    for (int i = tid; i < NODE_STRIDE * nRp; i += BP2_TPB) bel[i] = prob[i];
     __syncthreads();
 
     // ---- sweeps -------------------------------------------------------------------------------------------------------------
@@ -1128,10 +1129,10 @@ __global__ void __launch_bounds__(BP2_TPB, BP2_OCC) k_rot_bp2(RotamerDev P, Bp2L
     messages();
     __syncthreads();
     for (int A = tid; A < nR; A += BP2_TPB) {
-        float mx = prob[A];
-        for (int k = 1; k < MAXR; ++k) mx = fmaxf(mx, prob[k * nRp + A]);
+        float mx = prob[A * NODE_STRIDE];
+        for (int k = 1; k < MAXR; ++k) mx = fmaxf(mx, prob[(A) * NODE_STRIDE + k]);
         float imx = 1.f / mx;
-        for (int k = 0; k < MAXR; ++k) bel[k * nRp + A] = prob[k * nRp + A] * imx;
+        for (int k = 0; k < MAXR; ++k) bel[(A) * NODE_STRIDE + k] = prob[(A) * NODE_STRIDE + k] * imx;
     }
     __syncthreads();
     int iter = 0, unconverged = 1;
@@ -1152,12 +1153,12 @@ __global__ void __launch_bounds__(BP2_TPB, BP2_OCC) k_rot_bp2(RotamerDev P, Bp2L
     for (int A = tid; A < nR; A += BP2_TPB) {
         int nA = nrot[A];
         float b[MAXR], s = 0.f;
-        for (int k = 0; k < MAXR; ++k) { b[k] = nA > 1 ? bel[k * nRp + A] : (k == 0 ? 1.f : 0.f); s += b[k]; }
+        for (int k = 0; k < MAXR; ++k) { b[k] = nA > 1 ? bel[(A) * NODE_STRIDE + k] : (k == 0 ? 1.f : 0.f); s += b[k]; }
         float is = 1.f / s;
-        for (int k = 0; k < MAXR; ++k) { b[k] *= is; bel[k * nRp + A] = b[k]; node_marg[A * MAXR + k] = b[k]; }
+        for (int k = 0; k < MAXR; ++k) { b[k] *= is; bel[(A) * NODE_STRIDE + k] = b[k]; node_marg[A * MAXR + k] = b[k]; }
         if (want_pot) {
             float e = offs[A];
-            for (int k = 0; k < nA; ++k) e += b[k] * __logf((1e-10f + b[k]) / (1e-10f + prob[k * nRp + A]));
+            for (int k = 0; k < nA; ++k) e += b[k] * __logf((1e-10f + b[k]) / (1e-10f + prob[(A) * NODE_STRIDE + k]));
             en += e;
             if (fe_on) atomicAdd(&P.res_fe[size_t(r) * nR + A], e);
         }
@@ -1184,7 +1185,7 @@ __global__ void __launch_bounds__(BP2_TPB, BP2_OCC) k_rot_bp2(RotamerDev P, Bp2L
             if (p < n66 + n36) return P36[19 * (p - n66) + f * 6 + s2];
             return P33[9 * (p - n66 - n36) + f * 3 + s2];
         },
-        [&](int node) { const int A = node / MAXR; return bel[(node - A * MAXR) * nRp + A]; });
+        [&](int node) { const int A = node / MAXR; return bel[(A) * NODE_STRIDE + (node - A * MAXR)]; });
     if (want_pot) {
         float tot = block_sum(en, red);
         if (tid == 0) P.potential[r] = tot + P.e11[r];
@@ -1376,7 +1377,7 @@ struct RotamerSidechain : PotentialNode {
     // replica (3.8 residue pairs per residue; measured 2.6-3.3 on coil-like chains) with 27 floats of
     // pair matrix per pair (class mix of a uniform sequence: 21.5).  Larger replicas take the general kernel.
     static size_t bp2_bytes(int nR, const Bp2Lay& L) {
-        size_t words = size_t(12) * L.nRp + nR + 32 + (2 * nR + 1) + ((nR + 1) & 1) + 2 * 34 + size_t(MSG_STRIDE) * L.SP + L.Pcap;
+        size_t words = size_t(2 * NODE_STRIDE) * L.nRp + nR + 32 + (2 * nR + 1) + ((nR + 1) & 1) + 2 * 34 + size_t(MSG_STRIDE) * L.SP + L.Pcap;
         return (words + 2 * size_t(L.SP)) * 4 + (size_t(4) * L.SP + nR) * 2 + 16;
     }
     void plan_fast_bp(int device_smem) {
@@ -1390,7 +1391,7 @@ struct RotamerSidechain : PotentialNode {
         for (int occ = BP2_OCC; occ >= 1; --occ) {
             size_t budget = std::min<size_t>(device_smem, size_t(sm_total) / occ - 1024);
             Bp2Lay L;
-            L.nRp = pad4(n_res);
+            L.nRp = n_res;
             L.SP = pad4(4); L.Pcap = 0;
             size_t fixed = bp2_bytes(n_res, L);
             if (fixed >= budget) continue;
@@ -1398,7 +1399,7 @@ struct RotamerSidechain : PotentialNode {
             sp = std::min(sp, 32767);
             if (sp < want_pairs + 1 && occ > 1) continue;
             if (sp < 8) continue;
-            L.SP = pad4(sp) > sp ? pad4(sp) - 32 : sp;   // largest value <= sp that is 4 mod 32
+            L.SP = sp;   // (pair-major rows with odd strides: no alignment constraint on the capacity)
             if (L.SP < 4) continue;
             L.Pcap = 27 * L.SP;
             lay2 = L;
