@@ -1226,7 +1226,7 @@ struct RotamerSidechain : PotentialNode {
     DevBuf<int> d_bead_res, d_bead_rot, d_res_nrot, inc, istart, stats, code, rowstart;
     DevBuf<float> pmat, node_marg, enode, fold, e11, table, ss;
     DevBuf<unsigned short> pair_ab, dj, lower, order_e, order_d;
-    int cap_e = 0, edge_tpb = EDGE_TPB, edge_split = 1, edge_G = 1, edge_grid = 1;
+    int cap_e = 0, edge_tpb = EDGE_TPB, edge_split = 1, edge_G = 1;
     float damping, tol;
     int max_iter, chunk;
     size_t smem_prep = 0, smem_edge = 0, smem_bp = 0, smem_bp2 = 0;
@@ -1340,7 +1340,12 @@ struct RotamerSidechain : PotentialNode {
         // replicas per CTA (they share one staged copy of the 52 KB table): as many as the thread bound of the build allows
         edge_G = edge_split == 1 ? std::max(1, EDGE_MAXT / edge_tpb) : 1;
         if (const char* e = getenv("UPSIDE_B200_EDGE_G")) edge_G = std::max(1, std::min(atoi(e), EDGE_MAXT / edge_tpb));
-        smem_edge = sizeof(BeadRec) * size_t(ig.n1) * edge_G + sizeof(float) * (table.n + 4) + sizeof(int) * size_t(ig.n_type1) * ig.n_type1 + 64;
+        auto edge_bytes = [&](int G) {
+            return sizeof(BeadRec) * size_t(ig.n1) * G + sizeof(float) * (table.n + 4) + sizeof(int) * size_t(ig.n_type1) * ig.n_type1 + 64;
+        };
+        // sharing pays while two CTAs still fit an SM; a large system falls back to one replica per CTA
+        while (edge_G > 1 && edge_bytes(edge_G) > std::min<size_t>(device_smem, 112 * 1024)) --edge_G;
+        smem_edge = edge_bytes(edge_G);
         if (ig.n_type1 > 255) throw std::string("rotamer node: more than 255 bead types");
         if (smem_prep > (size_t)device_smem || smem_edge > (size_t)device_smem || fixed_bp > (size_t)device_smem)
             throw std::string("rotamer node: system too large for the shared-memory kernels");
