@@ -7,8 +7,9 @@
 // GPU and advance together, one CUDA graph launch per MD round for the whole group.  Replica exchange needs two batched
 // energy evaluations per swap set instead of 2*n_system serial ones (the reference's serial bottleneck, main.cpp:227-275).
 //
-// Monte-Carlo pivot/jump moves (--monte-carlo-interval) run batched on the device (monte_carlo.cu).  Not provided (out of
-// scope): the node-specific "detailed"/"extensive" loggers.
+// Monte-Carlo pivot/jump moves (--monte-carlo-interval) run batched on the device (monte_carlo.cu).  --log-level defaults
+// to detailed as in the reference (main.cpp:475): the node loggers hbond, rama, rama_map_potential, nonlinear_coupling,
+// nonbonded_spring_energy and the rotamer series are written unless --log-level basic is given.
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -246,7 +247,8 @@ int run(int argc, const char* const* argv, int verbose) {
         throw string("Illegal value for --log-level");
     // main.cpp:474-479.  The extensive-only loggers (placement_pos, virtual, environment_coverage) are not offered: with
     // several placement nodes the reference itself cannot create them (duplicate dataset name).
-    const int log_level = args.log_level == "detailed" ? 1 : (args.log_level == "extensive" ? 2 : 0);
+    // an empty --log-level means detailed, as in the reference (main.cpp:475)
+    const int log_level = args.log_level == "basic" ? 0 : (args.log_level == "extensive" ? 2 : 1);
 
     // ---- load the configurations and group identical ones into batched engines --------------------------------------------
     // (errors while setting the systems up return 2, as the reference does: main.cpp:562-573)
@@ -265,8 +267,19 @@ int run(int argc, const char* const* argv, int verbose) {
         if (pos->data.dims[2] != 1) throw string("must have n_system 1 from config");
         const h5l::Node* pot = h5l::find(sys.root.get(), "/input/potential");
         if (!pot || !pot->is_group) throw string("unable to open group /input/potential (does it exist?)");
+        // the samplers of a group are read from its first system: systems whose move sets differ are not batched together
+        // (the reference builds its samplers per system, main.cpp:543-546)
+        auto same_moves = [&](const System& other) {
+            if (!mc_interval) return true;
+            for (const char* nm : {"/input/pivot_moves", "/input/jump_moves"}) {
+                const h5l::Node *a = h5l::find(other.root.get(), nm), *b = h5l::find(sys.root.get(), nm);
+                if (bool(a) != bool(b) || (a && !tree_equal(*a, *b))) return false;
+            }
+            return true;
+        };
         for (size_t g = 0; g < groups.size() && sys.group < 0; ++g)
-            if (groups[g].n_atom == sys.n_atom && tree_equal(*groups[g].potential, *pot)) sys.group = (int)g;
+            if (groups[g].n_atom == sys.n_atom && tree_equal(*groups[g].potential, *pot) && same_moves(systems[groups[g].systems[0]]))
+                sys.group = (int)g;
         if (sys.group < 0) {
             groups.emplace_back();
             groups.back().potential = pot;
@@ -484,6 +497,10 @@ int run(int argc, const char* const* argv, int verbose) {
 
     auto tstart = std::chrono::high_resolution_clock::now();
     uint64_t nr = 0, last_start = 0;
+    // a failure inside the loop (pair-list capacity, CUDA error) must not lose the frames already sampled: they are
+    // written before the error propagates (the reference's H5Logger flushes as it goes)
+    auto flush_all = [&]() { for (int ns = 0; ns < n_system; ++ns) write_output(systems[ns], invocation, bool(replex), replex.get(), ns); };
+    try {
     while (nr < n_round && !received_signal) {
         // no pivot at t=0, so that a partially strained system may relax first (main.cpp:628-631)
         if (nr && mc_interval && !(nr % mc_interval)) for (auto& g : groups) g.engine->mc_execute(nr);
@@ -519,9 +536,13 @@ int run(int argc, const char* const* argv, int verbose) {
             attempt_swaps(base_random_seed, nr);
         }
     }
+    } catch (...) {
+        try { flush_all(); } catch (...) {}
+        throw;
+    }
     if (received_signal) fprintf(stderr, "Received early termination signal\n");
     double elapsed = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - tstart).count();
-    for (int ns = 0; ns < n_system; ++ns) write_output(systems[ns], invocation, bool(replex), replex.get(), ns);
+    flush_all();
     if (verbose) {
         printf("\n\nfinished in %.1f seconds (%.2f us/systems/step, %.1e simulation_time_unit/hour)\n", elapsed,
                elapsed * 1e6 / n_system / std::max<uint64_t>(nr, 1) / 3, nr * 3 * dt / elapsed * 3600.);

@@ -226,7 +226,9 @@ void Engine::enqueue_compute(cudaStream_t s, ComputeMode mode) {
     // their parents' sens during compute_value (deriv_engine.cpp:143-151).  Zeroing everything first and running
     // forward in construction (topological) order, then backward in reverse order, is equivalent.
     UB_CUDA(cudaMemsetAsync(sens_arena.p, 0, sens_arena.n * sizeof(float), s));
-    if (mode == PotentialAndDerivMode) UB_CUDA(cudaMemsetAsync(pot_arena.p, 0, pot_arena.n * sizeof(float), s));
+    // every mode: nodes that report their potential in DerivMode too (tension, AFM) add into a zeroed slot, so the slot holds
+    // the last evaluation's value as in the reference, not a running sum
+    UB_CUDA(cudaMemsetAsync(pot_arena.p, 0, pot_arena.n * sizeof(float), s));
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     UB_CUDA(cudaStreamIsCapturing(s, &cap));
     if (use_dag && cap == cudaStreamCaptureStatusActive) {

@@ -506,6 +506,7 @@ struct IGraphHost {
     // which exact tables the owning node's kernels read (asymmetric graphs; set before allocate()): a table nobody gathers
     // from is neither rebuilt nor refined
     bool need1 = true, need2 = true;
+    bool lists = true;   // false: the owning node builds its own pair structure (rotamer fast build); no tables are allocated
     Engine* engine = nullptr;
 
     // reads index/type/id(+1/2) and interaction_param (n_type1,n_type2,n_param): interaction_graph.h:305-381

@@ -57,6 +57,7 @@ void IGraphHost::allocate(Engine* e) {
     engine = e;
     K1 = neighbor_capacity(cutoff, n2);
     K2 = symmetric ? K1 : neighbor_capacity(cutoff, n1);
+    if (!lists) { use_cache = false; return; }
     if (symmetric) need1 = need2 = true;
     if (!need1 && !need2) throw std::string("interaction graph without a neighbour table");
     if (need1) {
@@ -87,6 +88,18 @@ void IGraphHost::allocate(Engine* e) {
                 ccnt2.alloc(size_t(e->n_rep) * n2);
             }
             cpos2.alloc(size_t(e->n_rep) * n2 * 4);
+        }
+        {   // k_refine stages the positions of both groups in shared memory: opt in above the 48 KB default, and give a
+            // system that does not fit the uncached all-pairs path instead of a launch failure
+            int device_smem = 0;
+            UB_CUDA(cudaDeviceGetAttribute(&device_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, e->device));
+            const size_t smem = sizeof(float4) * size_t(symmetric ? n1 + 1 : n1 + n2 + 2);
+            if (smem > (size_t)device_smem) {
+                use_cache = false;
+                cand1.alloc(0); cand2.alloc(0); ccnt1.alloc(0); ccnt2.alloc(0); cpos1.alloc(0); cpos2.alloc(0);
+                return;
+            }
+            UB_CUDA(cudaFuncSetAttribute(k_refine<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
         }
         flag.upload(std::vector<int>(e->n_rep, 2));   // 2 = never built
         rep_list.alloc(e->n_rep);

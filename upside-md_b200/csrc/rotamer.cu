@@ -60,6 +60,7 @@ struct RotamerDev {
     QuadSplineShape q;
     int n_bead, n_res, n_words, n_type;
     const int *bead_res, *bead_rot, *res_nrot;
+    const int* res_first;   // first bead of a residue (fast build: the beads of a residue are contiguous, one per state)
     const float* table;   // symmetric-compressed B-spline table: rows (t1<=t2), n_param floats each
     int n_prob;
     const float* prob_out[MAX_PROB_NODES];
@@ -85,7 +86,7 @@ struct RotamerDev {
     int* istart;              // [B][n_res+1]
     float* node_marg;         // [B][n_res][6]
     int* stats;               // [B][4]: n_iter, n_pair, converged, -
-    int* n_bad;               // [B] solves that hit max_iter without converging (n_bad_solve, rotamer.cpp:604,785)
+    int* n_bad;               // [B] solves that ran to (within a chunk of) max_iter (n_bad_solve, rotamer.cpp:604,784-785)
     int* slow_list;           // [B] replicas the fast BP kernel declined
     int* n_slow;              // [1] (reset by k_rot_prep)
     // per-residue free energy (residue_free_energies, rotamer.cpp:868-902): node term + half of every incident pair term;
@@ -305,6 +306,336 @@ __global__ void __launch_bounds__(PREP_TPB) k_rot_prep(RotamerDev P) {
     __syncthreads();
     for (int i = tid; i < nb; i += PREP_TPB) P.lower[size_t(r) * nb + i] = lo_s[i];
     // thread-per-row consumers take the rows in order of falling length, so that the threads of a warp finish together
+    sort_rows_desc_u16(nb, [&](int i) { return (int)ce_s[i]; }, P.order_e + size_t(r) * nb, hist);
+    sort_rows_desc_u16(nb, [&](int i) { return rs[i + 1] - rs[i]; }, P.order_d + size_t(r) * nb, hist);
+}
+
+// ================================================================================================ build (fast path)
+// k_rot_build replaces the Verlet cache, k_refine and k_rot_prep for the rotamer graph when every (residue, state) owns
+// exactly one bead and the beads of a residue are contiguous (ff_1).  The beads of a residue are its rotamer states - up
+// to six points a few Angstrom apart - so the bead pair list is a RESIDUE pair list with a 36-bit mask per pair:
+//   1. one bounding sphere per residue; all residue pairs (A<B) are tested sphere against sphere (n_res^2/2 cheap tests,
+//      no cached candidate list to keep valid), survivors compacted in (A,B) order;
+//   2. one thread per surviving residue pair applies the reference's exact bead predicate (interaction_graph.h:223-244,
+//      __fadd_rn/__fmul_rn, no FMA) to its nA x nB bead pairs -> mask; non-empty masks set the residue adjacency bits;
+//   3. the same slot arithmetic as k_rot_prep (prefix popcounts over adjacency rows) names every active pair, and one
+//      thread per bead walks its residue's adjacency row and reads its partners off the masks: the CSR rows, codes, pair
+//      slots and incidence lists come out exactly as k_rot_prep writes them, so the consumers are unchanged.
+// Nothing is read from or written to global memory between the bead positions and the CSR rows.
+constexpr int BUILD_TPB = 256;
+struct BuildLay { int capc, capa; };   // capacities: sphere-test survivors, active residue pairs
+
+__device__ __forceinline__ int block_excl_scan(int v, int* wtot, int& total) {   // every thread calls; contains barriers
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(UB_FULL_MASK, incl, o); if (lane >= o) incl += t; }
+    __syncthreads();   // previous readers of wtot are done
+    if (lane == 31) wtot[w] = incl;
+    __syncthreads();
+    int base = 0, tot = 0;
+    const int nw = blockDim.x >> 5;
+    for (int k = 0; k < nw; ++k) { const int t = wtot[k]; base += k < w ? t : 0; tot += t; }
+    total = tot;
+    return base + incl - v;
+}
+
+__global__ void __launch_bounds__(BUILD_TPB) k_rot_build(RotamerDev P, BuildLay L) {
+    extern __shared__ unsigned long long smem_ull[];
+    const int r = blockIdx.x, tid = threadIdx.x;
+    const int nR = P.n_res, nW = P.n_words, nb = P.n_bead;
+    unsigned long long* cmask = smem_ull;                                   // [capc] bead-pair mask of candidate c (bit a*6+b)
+    float4* bpos = reinterpret_cast<float4*>(cmask + L.capc);               // [nb]
+    float4* rc = bpos + nb;                                                 // [nR] bounding sphere (centre, radius)
+    unsigned* bitmap = reinterpret_cast<unsigned*>(rc + nR);                // [nR][nW] adjacency, both residues multi-state
+    unsigned* adj = bitmap + nR * nW;                                       // [nR][nW] adjacency, every active pair
+    unsigned* cand = adj + nR * nW;                                         // [capc] A | B << 16
+    int* estart = reinterpret_cast<int*>(cand + L.capc);                    // [nR+1]
+    int* istart = estart + nR + 1;                                          // [nR+1]
+    int* deg = istart + nR + 1;                                             // [nR]
+    int* ebase = deg + nR;                                                  // [nR]
+    int* abase = ebase + nR;                                                // [nR+1]
+    int* rfirst = abase + nR + 1;                                           // [nR] first bead of the residue
+    int* nrot = rfirst + nR;                                                // [nR]
+    float* en = reinterpret_cast<float*>(nrot + nR);                        // [nR*6]
+    int* rr = reinterpret_cast<int*>(en + nR * MAXR);                       // [nb] res << 4 | rot << 1 | multi-state
+    int* rs = rr + nb;                                                      // [nb+1]
+    int* wtot = rs + nb + 1;                                                // [33]
+    int* hist = wtot + 33;                                                  // [256]
+    unsigned short* wpre = reinterpret_cast<unsigned short*>(hist + 256);   // [nR][nW]
+    unsigned short* awpre = wpre + nR * nW;                                 // [nR][nW]
+    unsigned short* a2c = awpre + nR * nW;                                  // [capa] active slot -> candidate
+    unsigned short* lo_s = a2c + L.capa;                                    // [nb]
+    unsigned short* ce_s = lo_s + nb;                                       // [nb]
+
+    for (int i = tid; i < nR * nW; i += BUILD_TPB) { bitmap[i] = 0u; adj[i] = 0u; }
+    for (int A = tid; A < nR; A += BUILD_TPB) { nrot[A] = P.res_nrot[A]; rfirst[A] = P.res_first[A]; }
+    for (int i = tid; i < nb; i += BUILD_TPB) {
+        const float4 a = *reinterpret_cast<const float4*>(elem_ptr(P.g.s1, r, i));
+        bpos[i] = a;
+        float e = 0.f;
+        const int loc = P.g.s1.loc[i];
+        for (int p = 0; p < P.n_prob; ++p) e += P.prob_out[p][(size_t(r) * P.prob_n[p] + loc) * P.prob_wp[p]];
+        const int A = P.bead_res[i], ra = P.bead_rot[i];
+        en[A * MAXR + ra] = e;
+        rr[i] = (A << 4) | (ra << 1) | (P.res_nrot[A] > 1 ? 1 : 0);
+    }
+    __syncthreads();
+    for (int i = tid; i < nR * MAXR; i += BUILD_TPB) if ((i % MAXR) >= nrot[i / MAXR]) en[i] = 0.f;
+    for (int A = tid; A < nR; A += BUILD_TPB) {   // bounding sphere: centre = mean of the beads
+        const int f = rfirst[A], n = nrot[A];
+        float cx = 0.f, cy = 0.f, cz = 0.f;
+        for (int a = 0; a < n; ++a) { const float4 p = bpos[f + a]; cx += p.x; cy += p.y; cz += p.z; }
+        const float inv = 1.f / float(n);
+        cx *= inv; cy *= inv; cz *= inv;
+        float r2 = 0.f;
+        for (int a = 0; a < n; ++a) {
+            const float4 p = bpos[f + a];
+            const float dx = p.x - cx, dy = p.y - cy, dz = p.z - cz;
+            r2 = fmaxf(r2, dx * dx + dy * dy + dz * dz);
+        }
+        rc[A] = make_float4(cx, cy, cz, sqrtf(r2));
+    }
+    __syncthreads();
+
+    // ---- 1. sphere tests over all residue pairs, survivors in (A,B) order ------------------------------------------------
+    const int nP = nR * (nR - 1) / 2;
+    const int CH = min(32, max(1, (nP + BUILD_TPB - 1) / BUILD_TPB));
+    const float reach = P.g.cutoff + 1e-3f;   // slack >> the rounding of centre, radius and distance
+    int nc = 0;
+    for (int q00 = 0; q00 < nP; q00 += BUILD_TPB * CH) {
+        const int q0 = q00 + tid * CH;
+        unsigned hits = 0u;
+        int A0 = 0, B0 = 0;
+        if (q0 < nP) {
+            const float t = float(2 * nR - 1);
+            int A = (int)((t - sqrtf(fmaxf(0.f, t * t - 8.f * float(q0)))) * 0.5f);
+            A = max(0, min(A, nR - 2));
+            while (A + 1 <= nR - 2 && ((A + 1) * (2 * nR - A - 2)) / 2 <= q0) ++A;
+            while (A > 0 && (A * (2 * nR - A - 1)) / 2 > q0) --A;
+            int B = q0 - (A * (2 * nR - A - 1)) / 2 + A + 1;
+            A0 = A; B0 = B;
+            float4 ca = rc[A];
+            for (int k = 0; k < CH && q0 + k < nP; ++k) {
+                const float4 cb = rc[B];
+                const float dx = ca.x - cb.x, dy = ca.y - cb.y, dz = ca.z - cb.z;
+                const float lim = reach + ca.w + cb.w;
+                if (dx * dx + dy * dy + dz * dz < lim * lim) hits |= 1u << k;
+                if (++B == nR) { ++A; B = A + 1; if (A < nR - 1) ca = rc[A]; }
+            }
+        }
+        int tot;
+        int at = nc + block_excl_scan(__popc(hits), wtot, tot);
+        {
+            int A = A0, B = B0;
+            for (int k = 0; k < CH && hits; ++k) {
+                if (hits & (1u << k)) { if (at < L.capc) cand[at] = (unsigned)A | ((unsigned)B << 16); ++at; hits &= ~(1u << k); }
+                if (++B == nR) { ++A; B = A + 1; }
+            }
+        }
+        nc += tot;
+    }
+    __syncthreads();
+    const bool cand_overflow = nc > L.capc;
+    if (cand_overflow) nc = 0;
+
+    // ---- 2. exact bead predicate per surviving residue pair ----------------------------------------------------------------
+    const float cutoff2 = P.g.cutoff2;
+    for (int c = tid; c < nc; c += BUILD_TPB) {
+        const unsigned ab = cand[c];
+        const int A = ab & 0xffffu, B = ab >> 16;
+        const int nA = nrot[A], nB = nrot[B], fA = rfirst[A], fB = rfirst[B];
+        unsigned long long m = 0ull;
+        for (int a = 0; a < nA; ++a) {
+            const float4 pi = bpos[fA + a];
+            for (int b = 0; b < nB; ++b) {
+                const float4 pj = bpos[fB + b];
+                const float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
+                const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+                if (d2 < cutoff2) m |= 1ull << (a * 6 + b);
+            }
+        }
+        cmask[c] = m;
+        if (m) {
+            atomicOr(&adj[A * nW + (B >> 5)], 1u << (B & 31));
+            atomicOr(&adj[B * nW + (A >> 5)], 1u << (A & 31));
+            if (nA > 1 && nB > 1) {
+                atomicOr(&bitmap[A * nW + (B >> 5)], 1u << (B & 31));
+                atomicOr(&bitmap[B * nW + (A >> 5)], 1u << (A & 31));
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- 3. slots: running popcounts, degrees, scans (as k_rot_prep; `adj` gets the same treatment for the active slots) -----
+    for (int A = tid; A < nR; A += BUILD_TPB) {
+        int run = 0, below = 0, arun = 0, abelow = 0;
+        for (int w = 0; w < nW; ++w) {
+            const unsigned bits = bitmap[A * nW + w], abits = adj[A * nW + w];
+            wpre[A * nW + w] = (unsigned short)run;
+            awpre[A * nW + w] = (unsigned short)arun;
+            if (w == (A >> 5)) {
+                below = run + __popc(bits & ((1u << (A & 31)) - 1u));
+                abelow = arun + __popc(abits & ((1u << (A & 31)) - 1u));
+            }
+            run += __popc(bits);
+            arun += __popc(abits);
+        }
+        deg[A] = run;
+        ebase[A] = -below;
+        estart[A] = run - below;
+        abase[A] = arun - abelow;      // upper active degree, scanned below; the lower count is recovered from awpre
+    }
+    __syncthreads();
+    if (tid < 32) {
+        int per = (nR + 31) / 32, a0 = min(nR, tid * per), a1 = min(nR, a0 + per);
+        int su = 0, sf = 0, sa = 0;
+        for (int A = a0; A < a1; ++A) { su += estart[A]; sf += deg[A]; sa += abase[A]; }
+        int pu = su, pf = sf, pa = sa;
+        for (int o = 1; o < 32; o <<= 1) {
+            int tu = __shfl_up_sync(UB_FULL_MASK, pu, o), tf = __shfl_up_sync(UB_FULL_MASK, pf, o), ta = __shfl_up_sync(UB_FULL_MASK, pa, o);
+            if (tid >= o) { pu += tu; pf += tf; pa += ta; }
+        }
+        int eu = pu - su, ef = pf - sf, ea = pa - sa;
+        for (int A = a0; A < a1; ++A) {
+            const int up = estart[A], aup = abase[A];
+            estart[A] = eu; istart[A] = ef; ebase[A] += eu;
+            // active slot base: first upper slot minus the active neighbours below A
+            abase[A] = ea - (awpre[A * nW + (A >> 5)] + __popc(adj[A * nW + (A >> 5)] & ((1u << (A & 31)) - 1u)));
+            eu += up; ef += deg[A]; ea += aup;
+        }
+        if (tid == 31) { estart[nR] = pu; istart[nR] = pf; abase[nR] = pa; }
+    }
+    __syncthreads();
+    auto slot_of = [&](int A, int B) {   // A < B, both multi-state, adjacent
+        return ebase[A] + (int)wpre[A * nW + (B >> 5)] + __popc(bitmap[A * nW + (B >> 5)] & ((1u << (B & 31)) - 1u));
+    };
+    auto aslot_of = [&](int A, int B) {  // A < B, active pair
+        return abase[A] + (int)awpre[A * nW + (B >> 5)] + __popc(adj[A * nW + (B >> 5)] & ((1u << (B & 31)) - 1u));
+    };
+    const int n_pair = estart[nR], n_act = abase[nR];
+    if (tid == 0) { P.stats[size_t(r) * 4 + 1] = n_pair; P.e11[r] = 0.f; }
+    if (tid == 0 && r == 0) *P.n_slow = 0;
+    if (*P.fe_flag) for (int A = tid; A < nR; A += BUILD_TPB) P.res_fe[size_t(r) * nR + A] = 0.f;
+    int* rowstart = P.rowstart + size_t(r) * (nb + 1);
+    auto fail = [&](int code) {   // uniform across the block: report, and leave an empty graph behind
+        if (tid == 0) { atomicExch(P.error_flag, code); P.stats[size_t(r) * 4 + 1] = 0; }
+        for (int A = tid; A <= nR; A += BUILD_TPB) P.istart[size_t(r) * (nR + 1) + A] = 0;
+        for (int i = tid; i <= nb; i += BUILD_TPB) rowstart[i] = 0;
+        for (int i = tid; i < nb; i += BUILD_TPB) {
+            P.lower[size_t(r) * nb + i] = 0; P.order_e[size_t(r) * nb + i] = P.order_d[size_t(r) * nb + i] = (unsigned short)i;
+        }
+    };
+    if (cand_overflow || n_act > L.capa) { fail(4); return; }
+    if (n_pair > P.max_pairs) { fail(2); return; }
+    for (int c = tid; c < nc; c += BUILD_TPB)
+        if (cmask[c]) { const unsigned ab = cand[c]; a2c[aslot_of(ab & 0xffffu, ab >> 16)] = (unsigned short)c; }
+    unsigned short* pair_ab = P.pair_ab + size_t(r) * P.max_pairs * 2;
+    int* inc = P.inc + size_t(r) * 2 * P.max_pairs;
+    for (int A = tid; A <= nR; A += BUILD_TPB) P.istart[size_t(r) * (nR + 1) + A] = istart[A];
+    for (int A = tid; A < nR; A += BUILD_TPB) {
+        const unsigned* row = bitmap + A * nW;
+        int t = istart[A], up = 0;
+        for (int w = 0; w < nW; ++w) {
+            unsigned bits = row[w];
+            while (bits) {
+                int C = (w << 5) + __ffs(bits) - 1;
+                bits &= bits - 1;
+                if (C > A) {
+                    int e = estart[A] + up++;
+                    pair_ab[2 * e] = (unsigned short)A;
+                    pair_ab[2 * e + 1] = (unsigned short)C;
+                    inc[t++] = 2 * e;
+                } else {
+                    inc[t++] = 2 * slot_of(C, A) + 1;
+                }
+            }
+        }
+    }
+    for (int i = tid; i < nR * MAXR; i += BUILD_TPB) P.enode[size_t(r) * nR * MAXR + i] = en[i];
+    {
+        float4* pm4 = reinterpret_cast<float4*>(P.pmat + size_t(r) * P.max_pairs * 36);
+        for (int i = tid; i < n_pair * 9; i += BUILD_TPB) pm4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();   // a2c complete
+
+    // ---- 4. CSR rows, one thread per bead: its residue's adjacency row x the masks ----------------------------------------
+    // partner states of residue C seen from state a of residue A: a row (A<C) or a column (A>C) of the pair's mask
+    auto partner_bits = [&](int A, int a, int C) -> unsigned {
+        const bool up = A < C;
+        const unsigned long long m = cmask[a2c[up ? aslot_of(A, C) : aslot_of(C, A)]];
+        if (up) return (unsigned)(m >> (a * 6)) & 63u;
+        const unsigned x = (unsigned)(m >> a) & 0x41041041u;   // bits b*6
+        return (x & 1u) | ((x >> 5) & 2u) | ((x >> 10) & 4u) | ((x >> 15) & 8u) | ((x >> 20) & 16u) | ((x >> 25) & 32u);
+    };
+    for (int i = tid; i < nb; i += BUILD_TPB) {   // pass 1: row length, partners below, folding partners below, evaluated entries
+        const int me = rr[i], A = me >> 4, a = (me >> 1) & 7;
+        const bool mA = me & 1;
+        int cnt = 0, lo = 0, nfl = 0, nev = 0;
+        for (int w = 0; w < nW; ++w) {
+            unsigned bits = adj[A * nW + w];
+            while (bits) {
+                const int C = (w << 5) + __ffs(bits) - 1;
+                bits &= bits - 1;
+                const int n = __popc(partner_bits(A, a, C));
+                const bool mB = nrot[C] > 1, below = C < A;
+                cnt += n;
+                if (below) { lo += n; if (mA && !mB) { nfl += n; nev += n; } }
+                else if (mA || !mB) nev += n;
+            }
+        }
+        rs[i] = cnt;   // scanned in place below
+        lo_s[i] = (unsigned short)(lo - nfl);
+        ce_s[i] = (unsigned short)nev;
+    }
+    __syncthreads();
+    {   // exclusive scan of the row lengths in place (rs[nb] = total)
+        const int per = (nb + BUILD_TPB - 1) / BUILD_TPB;
+        const int r0 = min(nb, tid * per), r1 = min(nb, r0 + per);
+        int s = 0;
+        for (int i = r0; i < r1; ++i) s += rs[i];
+        int tot;
+        int run = block_excl_scan(s, wtot, tot);
+        for (int i = r0; i < r1; ++i) { const int c = rs[i]; rs[i] = run; run += c; }
+        if (tid == 0) rs[nb] = tot;
+    }
+    __syncthreads();
+    if (rs[nb] > P.cap_e) { fail(3); return; }
+    for (int i = tid; i <= nb; i += BUILD_TPB) rowstart[i] = rs[i];
+    unsigned short* dj = P.dj + size_t(r) * P.cap_e;
+    int* code = P.code + size_t(r) * P.cap_e;
+    for (int i = tid; i < nb; i += BUILD_TPB) {   // pass 2: place the entries (order inside a row: see k_rot_prep)
+        const int me = rr[i], A = me >> 4, a = (me >> 1) & 7, base = rs[i];
+        const bool mA = me & 1;
+        int run_f = lo_s[i], run_o = 0, k = 0;
+        for (int w = 0; w < nW; ++w) {
+            unsigned bits = adj[A * nW + w];
+            while (bits) {
+                const int C = (w << 5) + __ffs(bits) - 1;
+                bits &= bits - 1;
+                unsigned pb = partner_bits(A, a, C);
+                if (!pb) continue;
+                const bool mB = nrot[C] > 1, below = C < A;
+                const int fC = rfirst[C];
+                const int slot36 = (mA && mB) ? 36 * (A < C ? slot_of(A, C) : slot_of(C, A)) : 0;
+                while (pb) {
+                    const int b = __ffs(pb) - 1;
+                    pb &= pb - 1;
+                    int cd;
+                    if (mA && mB) cd = slot36 + (A < C ? a * 6 + b : b * 6 + a);
+                    else if (mA) cd = code_node(A * MAXR + a, true);
+                    else if (mB) cd = code_node(C * MAXR + b, false);
+                    else cd = CODE_SS;
+                    const int at = !below ? k : ((mA && !mB) ? run_f++ : run_o++);
+                    dj[base + at] = (unsigned short)(fC + b);
+                    code[base + at] = cd;
+                    ++k;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < nb; i += BUILD_TPB) P.lower[size_t(r) * nb + i] = lo_s[i];
     sort_rows_desc_u16(nb, [&](int i) { return (int)ce_s[i]; }, P.order_e + size_t(r) * nb, hist);
     sort_rows_desc_u16(nb, [&](int i) { return rs[i + 1] - rs[i]; }, P.order_d + size_t(r) * nb, hist);
 }
@@ -769,7 +1100,7 @@ __device__ void bp_solve_generic(const RotamerDev& P, int want_pot, int r, float
     if (tid == 0) {
         int* st = P.stats + size_t(r) * 4;
         st[0] = iter; st[2] = max_dev <= P.tol;
-        if (!(max_dev <= P.tol)) P.n_bad[r] += 1;
+        if (iter >= P.max_iter - P.chunk - 1) P.n_bad[r] += 1;   // the reference's criterion (rotamer.cpp:784-785)
     }
     // ---- marginals (and Bethe free energy) ----------------------------------------------------------------------------------
     float en = 0.f;
@@ -1146,7 +1477,7 @@ __global__ void __launch_bounds__(BP2_TPB, BP2_OCC) k_rot_bp2(RotamerDev P, Bp2L
         }
         unconverged = __syncthreads_or(dev > P.tol);
     }
-    if (tid == 0) { st[0] = iter; st[2] = !unconverged; st[3] = n66 | (n36 << 16); if (unconverged) P.n_bad[r] += 1; }   // st[3]: class counts for the flop audit
+    if (tid == 0) { st[0] = iter; st[2] = !unconverged; st[3] = n66 | (n36 << 16); if (iter >= P.max_iter - P.chunk - 1) P.n_bad[r] += 1; }   // st[3]: class counts for the flop audit
 
     // ---- marginals (and Bethe free energy) ----------------------------------------------------------------------------------
     float en = 0.f;
@@ -1223,13 +1554,15 @@ struct RotamerSidechain : PotentialNode {
     float knot_spacing = 0.5f;
     int n_res = 0, n_words = 0, max_pairs = 0, smem_pairs = 0, multi_bead_states = 0;
     std::vector<int> bead_res, bead_rot, res_nrot, res_key;
-    DevBuf<int> d_bead_res, d_bead_rot, d_res_nrot, inc, istart, stats, code, rowstart;
+    DevBuf<int> d_bead_res, d_bead_rot, d_res_nrot, d_res_first, inc, istart, stats, code, rowstart;
     DevBuf<float> pmat, node_marg, enode, fold, e11, table, ss;
     DevBuf<unsigned short> pair_ab, dj, lower, order_e, order_d;
     int cap_e = 0, edge_tpb = EDGE_TPB, edge_split = 1, edge_G = 1;
     float damping, tol;
     int max_iter, chunk;
-    size_t smem_prep = 0, smem_edge = 0, smem_bp = 0, smem_bp2 = 0;
+    size_t smem_prep = 0, smem_edge = 0, smem_bp = 0, smem_bp2 = 0, smem_build = 0;
+    bool fast_build = false;   // k_rot_build instead of Verlet cache + k_refine + k_rot_prep
+    BuildLay blay{0, 0};
     Bp2Lay lay2{0, 0, 0};
     bool fast_bp = false;
     DevBuf<int> slow_list, n_slow, n_bad, fe_flag;
@@ -1285,6 +1618,16 @@ struct RotamerSidechain : PotentialNode {
         d_bead_res.upload(bead_res);
         d_bead_rot.upload(bead_rot);
         d_res_nrot.upload(res_nrot);
+        // fast build: one bead per (residue, state), the beads of a residue contiguous with ascending state (ff_1)
+        std::vector<int> res_first(n_res, -1);
+        fast_build = !multi_bead_states && !getenv("UPSIDE_B200_NO_FAST_BUILD");
+        for (int b = 0; b < ig.n1 && fast_build; ++b) {
+            if (bead_rot[b] == 0) res_first[bead_res[b]] = b;
+            if (res_first[bead_res[b]] < 0 || b - res_first[bead_res[b]] != bead_rot[b]) fast_build = false;
+        }
+        for (int A = 0; A < n_res && fast_build; ++A)
+            if (res_first[A] < 0 || (A + 1 < n_res ? res_first[A + 1] : ig.n1) != res_first[A] + res_nrot[A]) fast_build = false;
+        d_res_first.upload(res_first);
     }
     // symmetric tables must satisfy p(t1,t2).ang1 == p(t2,t1).ang2 and equal radial parts (bead_interaction.h:209-218);
     // that lets the device keep only the rows t1<=t2
@@ -1306,10 +1649,20 @@ struct RotamerSidechain : PotentialNode {
         table.upload(t);
     }
     void finalize() override {
-        ig.allocate(engine);
         size_t B = engine->n_rep;
         int device_smem = 0;
         UB_CUDA(cudaDeviceGetAttribute(&device_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, engine->device));
+        if (fast_build) {   // capacities per residue: sphere-test survivors (A<B) and active pairs; an overflow is reported
+            double scale = 1.0;
+            if (const char* s = getenv("UPSIDE_B200_NEIGHBOR_SCALE")) scale = std::max(0.05, atof(s));
+            const long all_pairs = long(n_res) * (n_res - 1) / 2;
+            blay.capc = (int)((std::max<long>(4, std::min<long>(all_pairs, (long)std::ceil(24 * scale * n_res))) + 3) & ~3L);
+            blay.capa = (int)((std::max<long>(4, std::min<long>(all_pairs, (long)std::ceil(16 * scale * n_res))) + 3) & ~3L);
+            smem_build = build_bytes();
+            if (blay.capc > 65535 || smem_build > (size_t)device_smem) fast_build = false;   // large systems keep the Verlet path
+        }
+        ig.lists = !fast_build;
+        ig.allocate(engine);
         // BP kernel: fixed part + 204 bytes per pair; aim for two resident CTAs per SM, never more pairs than can occur
         size_t fixed_bp = sizeof(float) * (size_t(n_res) * MAXR * 2 + n_res + 32) + sizeof(int) * (2 * n_res + 1);
         size_t per_pair = 12 * 4 + 36 * 4 + 2 * 4 + 2 * 2;
@@ -1350,6 +1703,7 @@ struct RotamerSidechain : PotentialNode {
         if (smem_prep > (size_t)device_smem || smem_edge > (size_t)device_smem || fixed_bp > (size_t)device_smem)
             throw std::string("rotamer node: system too large for the shared-memory kernels");
         UB_CUDA(cudaFuncSetAttribute(k_rot_prep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_prep));
+        if (fast_build) UB_CUDA(cudaFuncSetAttribute(k_rot_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_build));
         UB_CUDA(cudaFuncSetAttribute(k_rot_energy<15, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_edge));
         UB_CUDA(cudaFuncSetAttribute(k_rot_deriv<15, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_edge));
         UB_CUDA(cudaFuncSetAttribute(k_rot_energy<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_edge));
@@ -1414,12 +1768,17 @@ struct RotamerSidechain : PotentialNode {
             return;
         }
     }
+    size_t build_bytes() const {
+        const size_t nR = n_res, nW = n_words, nb = ig.n1;
+        return 8 * size_t(blay.capc) + 16 * (nb + nR) + 4 * (2 * nR * nW + blay.capc) + 4 * (7 * nR + 3) + 4 * nR * MAXR +
+               4 * (2 * nb + 1 + 33 + 256) + 2 * (2 * nR * nW + blay.capa + 2 * nb) + 16;
+    }
     RotamerDev dev() {
         RotamerDev P;
         P.g = ig.dev();
         P.q.nka = nka; P.q.nk = nk; P.q.inv_dx = 1.f / knot_spacing; P.q.inv_dtheta = (nka - 3) / 2.f;
         P.n_bead = ig.n1; P.n_res = n_res; P.n_words = n_words; P.n_type = ig.n_type1;
-        P.bead_res = d_bead_res.p; P.bead_rot = d_bead_rot.p; P.res_nrot = d_res_nrot.p;
+        P.bead_res = d_bead_res.p; P.bead_rot = d_bead_rot.p; P.res_nrot = d_res_nrot.p; P.res_first = d_res_first.p;
         P.table = table.p;
         P.n_prob = (int)prob_nodes.size();
         for (int i = 0; i < P.n_prob; ++i) {
@@ -1439,14 +1798,19 @@ struct RotamerSidechain : PotentialNode {
     }
     void compute_value(cudaStream_t s, ComputeMode mode) override {
         if (!ig.n1) return;
-        ig.build(s);
         RotamerDev P = dev();
         int want = mode == PotentialAndDerivMode;
         // edge kernels: persistent CTAs (as many as stay resident) striding over the replicas, edge_G replicas at a time
         int persist = std::min((engine->n_rep + edge_G - 1) / edge_G, 148 * EDGE_OCC);
-        engine->mark(s, "rotamer/pairlist");
-        k_rot_prep<<<engine->n_rep, PREP_TPB, smem_prep, s>>>(P);
-        engine->mark(s, "rotamer/prep");
+        if (fast_build) {
+            k_rot_build<<<engine->n_rep, BUILD_TPB, smem_build, s>>>(P, blay);
+            engine->mark(s, "rotamer/build");
+        } else {
+            ig.build(s);
+            engine->mark(s, "rotamer/pairlist");
+            k_rot_prep<<<engine->n_rep, PREP_TPB, smem_prep, s>>>(P);
+            engine->mark(s, "rotamer/prep");
+        }
         const bool ff1_knots = nka == 15 && nk == 16;   // the PARAM_7A_CUTOFF build of the reference (bead_interaction.h:12-27)
         if (ff1_knots) k_rot_energy<15, 16><<<dim3(edge_split, persist), edge_tpb * edge_G, smem_edge, s>>>(P, want, engine->n_rep, edge_tpb);
         else k_rot_energy<0, 0><<<dim3(edge_split, persist), edge_tpb * edge_G, smem_edge, s>>>(P, want, engine->n_rep, edge_tpb);
@@ -1462,7 +1826,32 @@ struct RotamerSidechain : PotentialNode {
         else k_rot_deriv<0, 0><<<dim3(edge_split, persist), edge_tpb * edge_G, smem_edge, s>>>(P, engine->n_rep, edge_tpb);
         engine->mark(s, "rotamer/deriv");
     }
-    bool get_pairlist(int replica, std::vector<int>& i1, std::vector<int>& i2) override { return ig.pairlist(replica, i1, i2); }
+    // the bead pair list in the reference's emission order; the fast build keeps no ELL table, the CSR rows hold every pair
+    // in both directions
+    bool get_pairlist(int replica, std::vector<int>& i1, std::vector<int>& i2) override {
+        if (!fast_build) return ig.pairlist(replica, i1, i2);
+        if (replica < 0 || replica >= engine->n_rep) throw std::string("replica out of range");
+        engine->sync_and_check();
+        std::vector<int> rs(ig.n1 + 1);
+        UB_CUDA(cudaMemcpy(rs.data(), rowstart.p + size_t(replica) * (ig.n1 + 1), rs.size() * sizeof(int), cudaMemcpyDeviceToHost));
+        std::vector<unsigned short> partner(rs[ig.n1]);
+        if (!partner.empty())
+            UB_CUDA(cudaMemcpy(partner.data(), dj.p + size_t(replica) * cap_e, partner.size() * sizeof(unsigned short), cudaMemcpyDeviceToHost));
+        i1.clear();
+        i2.clear();
+        for (int i = 0; i < ig.n1; ++i)
+            for (int e = rs[i]; e < rs[i + 1]; ++e)
+                if (i < (int)partner[e]) { i1.push_back(i); i2.push_back(partner[e]); }
+        sort_reference_order(i1, i2);
+        return true;
+    }
+    std::vector<float> count_edges_by_type(int replica) {
+        std::vector<int> i1, i2;
+        get_pairlist(replica, i1, i2);
+        std::vector<float> ret(size_t(ig.n_type1) * ig.n_type2, 0.f);
+        for (size_t e = 0; e < i1.size(); ++e) ret[ig.type1[i1[e]] * ig.n_type2 + ig.type2[i2[e]]] += 1.f;
+        return ret;
+    }
     std::vector<float> get_param() const override { return ig.h_param; }
     void set_param(const std::vector<float>& p) override { ig.set_param(p); upload_table(); }
     std::vector<float> get_param_deriv(int replica) override {
@@ -1500,7 +1889,7 @@ struct RotamerSidechain : PotentialNode {
     std::vector<float> get_value_by_name(int replica, const char* log_name) override {
         std::string nm(log_name);
         engine->sync_and_check();
-        if (nm == "count_edges_by_type") return ig.count_edges_by_type(replica);
+        if (nm == "count_edges_by_type") return count_edges_by_type(replica);
         if (nm == "n_node") return {float(n_res)};
         if (nm == "bead_marginal") {   // B200 extension: node marginal of each bead's (residue, rotamer)
             std::vector<float> nmg(size_t(n_res) * MAXR);
