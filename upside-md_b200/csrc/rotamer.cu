@@ -323,7 +323,19 @@ __global__ void __launch_bounds__(PREP_TPB) k_rot_prep(RotamerDev P) {
 //      slots and incidence lists come out exactly as k_rot_prep writes them, so the consumers are unchanged.
 // Nothing is read from or written to global memory between the bead positions and the CSR rows.
 constexpr int BUILD_TPB = 256;
-struct BuildLay { int capc, capa; };   // capacities: sphere-test survivors, active residue pairs
+// capacities of the shared-memory arrays (sphere-test survivors, active residue pairs); what does not fit spills to a
+// per-replica global scratch area (clashing start structures have several times the pairs of a relaxed chain) up to
+// capc_tot / capa_tot, beyond which the error flag is raised
+struct BuildLay { int capc, capa, capc_tot, capa_tot; unsigned long long* spill; int* bstats; };
+template <typename T, bool SPILL> struct SpillArr {
+    T* s; T* g; int cap;
+    // SPILL: one generic-address access behind a pointer select; otherwise a plain shared-memory access
+    __device__ __forceinline__ T& operator[](int k) const {
+        if (!SPILL) return s[k];
+        T* p = k < cap ? s + k : g + (k - cap);
+        return *p;
+    }
+};
 
 __device__ __forceinline__ int block_excl_scan(int v, int* wtot, int& total) {   // every thread calls; contains barriers
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -340,48 +352,69 @@ __device__ __forceinline__ int block_excl_scan(int v, int* wtot, int& total) {  
     return base + incl - v;
 }
 
-__global__ void __launch_bounds__(BUILD_TPB) k_rot_build(RotamerDev P, BuildLay L) {
-    extern __shared__ unsigned long long smem_ull[];
+// one neighbour of a residue in 64 bits: the pair's mask as seen from that residue (bits 0-35: bit a*6+b, a = own state,
+// b = the neighbour's), whether the neighbour lies above (bit 36), the neighbour (bits 37-47) and the pair's matrix slot
+// (bits 48-63; both multi-state, else unused)
+__device__ __forceinline__ unsigned long long nbr_pack(unsigned long long mask, bool up, int C, int slot) {
+    return mask | ((unsigned long long)(up ? 1 : 0) << 36) | ((unsigned long long)C << 37) | ((unsigned long long)slot << 48);
+}
+constexpr int BUILD_MAX_RES = 2047, BUILD_MAX_SLOT = 65535;
+
+__host__ __device__ inline size_t build_spill_words(const BuildLay& L) {   // 64-bit words of global scratch per replica
+    const size_t n_row_g = 2 * size_t(L.capa_tot - L.capa), n_c_g = size_t(L.capc_tot - L.capc);
+    return n_row_g + n_c_g + (n_c_g + 1) / 2 + (6 * n_row_g + 3) / 4;
+}
+
+// returns false (uniformly, nothing written) if SPILL is off and the shared-memory capacities do not hold this replica
+template <bool SPILL>
+__device__ __forceinline__ bool rot_build_body(const RotamerDev& P, const BuildLay& L, unsigned long long* smem_ull) {
     const int r = blockIdx.x, tid = threadIdx.x;
     const int nR = P.n_res, nW = P.n_words, nb = P.n_bead;
-    unsigned long long* cmask = smem_ull;                                   // [capc] bead-pair mask of candidate c (bit a*6+b)
-    float4* bpos = reinterpret_cast<float4*>(cmask + L.capc);               // [nb]
+    unsigned long long* rown_s = smem_ull;                                  // [2*capa] neighbour rows of the residues (CSR by astart)
+    unsigned long long* cmask_s = smem_ull + 2 * size_t(L.capa);            // [capc] bead-pair mask of candidate c (bit a*6+b)
+    unsigned* cand_s = reinterpret_cast<unsigned*>(cmask_s + L.capc);       // [capc] A | B << 16   (capc is a multiple of 4)
+    // entry offsets per (neighbour-row entry, own state), written by pass 1 of step 5 when masks and candidates are dead
+    unsigned short* off_s = reinterpret_cast<unsigned short*>(cmask_s);     // [2*capa][6]  (12*capc >= 24*capa bytes)
+    float4* bpos = reinterpret_cast<float4*>(cand_s + L.capc);              // [nb]
     float4* rc = bpos + nb;                                                 // [nR] bounding sphere (centre, radius)
     unsigned* bitmap = reinterpret_cast<unsigned*>(rc + nR);                // [nR][nW] adjacency, both residues multi-state
     unsigned* adj = bitmap + nR * nW;                                       // [nR][nW] adjacency, every active pair
-    unsigned* cand = adj + nR * nW;                                         // [capc] A | B << 16
-    int* estart = reinterpret_cast<int*>(cand + L.capc);                    // [nR+1]
-    int* istart = estart + nR + 1;                                          // [nR+1]
-    int* deg = istart + nR + 1;                                             // [nR]
-    int* ebase = deg + nR;                                                  // [nR]
-    int* abase = ebase + nR;                                                // [nR+1]
-    int* rfirst = abase + nR + 1;                                           // [nR] first bead of the residue
+    int* estart = reinterpret_cast<int*>(adj + nR * nW);                    // [nR+1] first matrix slot of pairs (A, B>A)
+    int* istart = estart + nR + 1;                                          // [nR+1] incidence lists of the residue graph
+    int* astart = istart + nR + 1;                                          // [nR+1] neighbour rows
+    int* ebase = astart + nR + 1;                                           // [nR]
+    int* rfirst = ebase + nR;                                               // [nR] first bead of the residue
     int* nrot = rfirst + nR;                                                // [nR]
     float* en = reinterpret_cast<float*>(nrot + nR);                        // [nR*6]
-    int* rr = reinterpret_cast<int*>(en + nR * MAXR);                       // [nb] res << 4 | rot << 1 | multi-state
-    int* rs = rr + nb;                                                      // [nb+1]
+    int* rs = reinterpret_cast<int*>(en + nR * MAXR);                       // [nb+1]
     int* wtot = rs + nb + 1;                                                // [33]
     int* hist = wtot + 33;                                                  // [256]
-    unsigned short* wpre = reinterpret_cast<unsigned short*>(hist + 256);   // [nR][nW]
-    unsigned short* awpre = wpre + nR * nW;                                 // [nR][nW]
-    unsigned short* a2c = awpre + nR * nW;                                  // [capa] active slot -> candidate
-    unsigned short* lo_s = a2c + L.capa;                                    // [nb]
+    unsigned short* wpre = reinterpret_cast<unsigned short*>(hist + 256);   // [nR][nW] set bits of `bitmap` in the words before w
+    unsigned short* awpre = wpre + nR * nW;                                 // [nR][nW] the same for `adj`
+    unsigned short* lo_s = awpre + nR * nW;                                 // [nb]
     unsigned short* ce_s = lo_s + nb;                                       // [nb]
 
+    // spill areas of this replica: [2*(capa_tot-capa)] rows | [capc_tot-capc] masks | [capc_tot-capc] candidates | offsets
+    const size_t n_row_g = 2 * size_t(L.capa_tot - L.capa), n_c_g = size_t(L.capc_tot - L.capc);
+    unsigned long long* sp = L.spill + size_t(r) * build_spill_words(L);
+    const SpillArr<unsigned long long, SPILL> rown{rown_s, sp, 2 * L.capa};
+    const SpillArr<unsigned long long, SPILL> cmask{cmask_s, sp + n_row_g, L.capc};
+    const SpillArr<unsigned, SPILL> cand{cand_s, reinterpret_cast<unsigned*>(sp + n_row_g + n_c_g), L.capc};
+    const SpillArr<unsigned short, SPILL> off{off_s, reinterpret_cast<unsigned short*>(sp + n_row_g + n_c_g + (n_c_g + 1) / 2), 12 * L.capa};
+    const int capc_use = SPILL ? L.capc_tot : L.capc, capa_use = SPILL ? L.capa_tot : L.capa;
+
     for (int i = tid; i < nR * nW; i += BUILD_TPB) { bitmap[i] = 0u; adj[i] = 0u; }
+    for (int i = tid; i < nR * MAXR; i += BUILD_TPB) en[i] = 0.f;
     for (int A = tid; A < nR; A += BUILD_TPB) { nrot[A] = P.res_nrot[A]; rfirst[A] = P.res_first[A]; }
+    __syncthreads();
     for (int i = tid; i < nb; i += BUILD_TPB) {
-        const float4 a = *reinterpret_cast<const float4*>(elem_ptr(P.g.s1, r, i));
-        bpos[i] = a;
+        bpos[i] = *reinterpret_cast<const float4*>(elem_ptr(P.g.s1, r, i));
         float e = 0.f;
         const int loc = P.g.s1.loc[i];
         for (int p = 0; p < P.n_prob; ++p) e += P.prob_out[p][(size_t(r) * P.prob_n[p] + loc) * P.prob_wp[p]];
-        const int A = P.bead_res[i], ra = P.bead_rot[i];
-        en[A * MAXR + ra] = e;
-        rr[i] = (A << 4) | (ra << 1) | (P.res_nrot[A] > 1 ? 1 : 0);
+        en[P.bead_res[i] * MAXR + P.bead_rot[i]] = e;   // one bead per state
     }
     __syncthreads();
-    for (int i = tid; i < nR * MAXR; i += BUILD_TPB) if ((i % MAXR) >= nrot[i / MAXR]) en[i] = 0.f;
     for (int A = tid; A < nR; A += BUILD_TPB) {   // bounding sphere: centre = mean of the beads
         const int f = rfirst[A], n = nrot[A];
         float cx = 0.f, cy = 0.f, cz = 0.f;
@@ -426,17 +459,19 @@ __global__ void __launch_bounds__(BUILD_TPB) k_rot_build(RotamerDev P, BuildLay 
         }
         int tot;
         int at = nc + block_excl_scan(__popc(hits), wtot, tot);
-        {
-            int A = A0, B = B0;
-            for (int k = 0; k < CH && hits; ++k) {
-                if (hits & (1u << k)) { if (at < L.capc) cand[at] = (unsigned)A | ((unsigned)B << 16); ++at; hits &= ~(1u << k); }
-                if (++B == nR) { ++A; B = A + 1; }
-            }
+        while (hits) {   // pair number q0 + k of the upper triangle, walked from (A0,B0)
+            const int k = __ffs(hits) - 1;
+            hits &= hits - 1;
+            int A = A0, B = B0 + k;
+            while (B >= nR) { B = B - nR + A + 2; ++A; }
+            if (at < capc_use) cand[at] = (unsigned)A | ((unsigned)B << 16);
+            ++at;
         }
         nc += tot;
     }
     __syncthreads();
-    const bool cand_overflow = nc > L.capc;
+    const bool cand_overflow = nc > capc_use;
+    if (cand_overflow && !SPILL) return false;
     if (cand_overflow) nc = 0;
 
     // ---- 2. exact bead predicate per surviving residue pair ----------------------------------------------------------------
@@ -445,16 +480,26 @@ __global__ void __launch_bounds__(BUILD_TPB) k_rot_build(RotamerDev P, BuildLay 
         const unsigned ab = cand[c];
         const int A = ab & 0xffffu, B = ab >> 16;
         const int nA = nrot[A], nB = nrot[B], fA = rfirst[A], fB = rfirst[B];
-        unsigned long long m = 0ull;
-        for (int a = 0; a < nA; ++a) {
-            const float4 pi = bpos[fA + a];
-            for (int b = 0; b < nB; ++b) {
-                const float4 pj = bpos[fB + b];
-                const float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
-                const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-                if (d2 < cutoff2) m |= 1ull << (a * 6 + b);
+        // the beads of B in registers (absent states sit far away), then one unrolled row of six tests per bead of A
+        float4 pj[MAXR];
+#pragma unroll
+        for (int b = 0; b < MAXR; ++b) pj[b] = b < nB ? bpos[fB + b] : make_float4(1e18f, 1e18f, 1e18f, 0.f);
+        unsigned rows_lo = 0u, rows_hi = 0u;   // states 0-2 and 3-5 of A, six bits each
+#pragma unroll
+        for (int a = 0; a < MAXR; ++a) {
+            if (a < nA) {
+                const float4 pi = bpos[fA + a];
+                unsigned row = 0u;
+#pragma unroll
+                for (int b = 0; b < MAXR; ++b) {
+                    const float dx = pi.x - pj[b].x, dy = pi.y - pj[b].y, dz = pi.z - pj[b].z;
+                    const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+                    row |= (d2 < cutoff2 ? 1u : 0u) << b;
+                }
+                if (a < 3) rows_lo |= row << (6 * a); else rows_hi |= row << (6 * (a - 3));
             }
         }
+        const unsigned long long m = (unsigned long long)rows_lo | ((unsigned long long)rows_hi << 18);
         cmask[c] = m;
         if (m) {
             atomicOr(&adj[A * nW + (B >> 5)], 1u << (B & 31));
@@ -467,30 +512,29 @@ __global__ void __launch_bounds__(BUILD_TPB) k_rot_build(RotamerDev P, BuildLay 
     }
     __syncthreads();
 
-    // ---- 3. slots: running popcounts, degrees, scans (as k_rot_prep; `adj` gets the same treatment for the active slots) -----
+    // ---- 3. per residue: running popcounts of both adjacency rows, degrees; scans ------------------------------------------
+    // With them the position of B among the neighbours of A is wpre[A][B>>5] + popc(row_A[B>>5] below bit B) - two
+    // independent loads - and the matrix slot of pair (A,B>A) is ebase[A] + that position.
     for (int A = tid; A < nR; A += BUILD_TPB) {
-        int run = 0, below = 0, arun = 0, abelow = 0;
+        int run = 0, below = 0, arun = 0;
         for (int w = 0; w < nW; ++w) {
             const unsigned bits = bitmap[A * nW + w], abits = adj[A * nW + w];
             wpre[A * nW + w] = (unsigned short)run;
             awpre[A * nW + w] = (unsigned short)arun;
-            if (w == (A >> 5)) {
-                below = run + __popc(bits & ((1u << (A & 31)) - 1u));
-                abelow = arun + __popc(abits & ((1u << (A & 31)) - 1u));
-            }
+            if (w == (A >> 5)) below = run + __popc(bits & ((1u << (A & 31)) - 1u));
             run += __popc(bits);
             arun += __popc(abits);
         }
-        deg[A] = run;
+        istart[A] = run;              // degree in the residue graph, scanned below
         ebase[A] = -below;
-        estart[A] = run - below;
-        abase[A] = arun - abelow;      // upper active degree, scanned below; the lower count is recovered from awpre
+        estart[A] = run - below;      // upper degree
+        astart[A] = arun;             // active degree
     }
     __syncthreads();
     if (tid < 32) {
         int per = (nR + 31) / 32, a0 = min(nR, tid * per), a1 = min(nR, a0 + per);
         int su = 0, sf = 0, sa = 0;
-        for (int A = a0; A < a1; ++A) { su += estart[A]; sf += deg[A]; sa += abase[A]; }
+        for (int A = a0; A < a1; ++A) { su += estart[A]; sf += istart[A]; sa += astart[A]; }
         int pu = su, pf = sf, pa = sa;
         for (int o = 1; o < 32; o <<= 1) {
             int tu = __shfl_up_sync(UB_FULL_MASK, pu, o), tf = __shfl_up_sync(UB_FULL_MASK, pf, o), ta = __shfl_up_sync(UB_FULL_MASK, pa, o);
@@ -498,22 +542,15 @@ __global__ void __launch_bounds__(BUILD_TPB) k_rot_build(RotamerDev P, BuildLay 
         }
         int eu = pu - su, ef = pf - sf, ea = pa - sa;
         for (int A = a0; A < a1; ++A) {
-            const int up = estart[A], aup = abase[A];
-            estart[A] = eu; istart[A] = ef; ebase[A] += eu;
-            // active slot base: first upper slot minus the active neighbours below A
-            abase[A] = ea - (awpre[A * nW + (A >> 5)] + __popc(adj[A * nW + (A >> 5)] & ((1u << (A & 31)) - 1u)));
-            eu += up; ef += deg[A]; ea += aup;
+            const int up = estart[A], dg = istart[A], ad = astart[A];
+            estart[A] = eu; istart[A] = ef; astart[A] = ea; ebase[A] += eu;
+            eu += up; ef += dg; ea += ad;
         }
-        if (tid == 31) { estart[nR] = pu; istart[nR] = pf; abase[nR] = pa; }
+        if (tid == 31) { estart[nR] = pu; istart[nR] = pf; astart[nR] = pa; }
     }
     __syncthreads();
-    auto slot_of = [&](int A, int B) {   // A < B, both multi-state, adjacent
-        return ebase[A] + (int)wpre[A * nW + (B >> 5)] + __popc(bitmap[A * nW + (B >> 5)] & ((1u << (B & 31)) - 1u));
-    };
-    auto aslot_of = [&](int A, int B) {  // A < B, active pair
-        return abase[A] + (int)awpre[A * nW + (B >> 5)] + __popc(adj[A * nW + (B >> 5)] & ((1u << (B & 31)) - 1u));
-    };
-    const int n_pair = estart[nR], n_act = abase[nR];
+    const int n_pair = estart[nR], n_act2 = astart[nR];   // n_act2 = 2 x active pairs
+    if (!SPILL && n_act2 > 2 * capa_use) return false;
     if (tid == 0) { P.stats[size_t(r) * 4 + 1] = n_pair; P.e11[r] = 0.f; }
     if (tid == 0 && r == 0) *P.n_slow = 0;
     if (*P.fe_flag) for (int A = tid; A < nR; A += BUILD_TPB) P.res_fe[size_t(r) * nR + A] = 0.f;
@@ -526,63 +563,66 @@ __global__ void __launch_bounds__(BUILD_TPB) k_rot_build(RotamerDev P, BuildLay 
             P.lower[size_t(r) * nb + i] = 0; P.order_e[size_t(r) * nb + i] = P.order_d[size_t(r) * nb + i] = (unsigned short)i;
         }
     };
-    if (cand_overflow || n_act > L.capa) { fail(4); return; }
-    if (n_pair > P.max_pairs) { fail(2); return; }
-    for (int c = tid; c < nc; c += BUILD_TPB)
-        if (cmask[c]) { const unsigned ab = cand[c]; a2c[aslot_of(ab & 0xffffu, ab >> 16)] = (unsigned short)c; }
+    if (tid == 0 && L.bstats) { L.bstats[2 * r] = nc; L.bstats[2 * r + 1] = n_act2 / 2; }
+    if (cand_overflow || n_act2 > 2 * capa_use) { fail(4); return true; }
+    if (n_pair > P.max_pairs) { fail(2); return true; }
+
+    // ---- 4. one thread per active pair: both neighbour-row entries, the matrix slot, both incidence-list entries -----------
     unsigned short* pair_ab = P.pair_ab + size_t(r) * P.max_pairs * 2;
     int* inc = P.inc + size_t(r) * 2 * P.max_pairs;
-    for (int A = tid; A <= nR; A += BUILD_TPB) P.istart[size_t(r) * (nR + 1) + A] = istart[A];
-    for (int A = tid; A < nR; A += BUILD_TPB) {
-        const unsigned* row = bitmap + A * nW;
-        int t = istart[A], up = 0;
-        for (int w = 0; w < nW; ++w) {
-            unsigned bits = row[w];
-            while (bits) {
-                int C = (w << 5) + __ffs(bits) - 1;
-                bits &= bits - 1;
-                if (C > A) {
-                    int e = estart[A] + up++;
-                    pair_ab[2 * e] = (unsigned short)A;
-                    pair_ab[2 * e + 1] = (unsigned short)C;
-                    inc[t++] = 2 * e;
-                } else {
-                    inc[t++] = 2 * slot_of(C, A) + 1;
-                }
-            }
+    for (int c = tid; c < nc; c += BUILD_TPB) {
+        const unsigned long long m = cmask[c];
+        if (!m) continue;
+        const unsigned ab = cand[c];
+        const int A = ab & 0xffffu, B = ab >> 16;
+        unsigned long long mt = 0ull;   // the transpose: bit b*6+a
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+            const unsigned row = (unsigned)(m >> (a * 6)) & 63u;
+#pragma unroll
+            for (int b = 0; b < 6; ++b) mt |= (unsigned long long)((row >> b) & 1u) << (b * 6 + a);
         }
+        const unsigned lowB = (1u << (B & 31)) - 1u, lowA = (1u << (A & 31)) - 1u;
+        const int pa = (int)awpre[A * nW + (B >> 5)] + __popc(adj[A * nW + (B >> 5)] & lowB);   // B among A's neighbours
+        const int pb = (int)awpre[B * nW + (A >> 5)] + __popc(adj[B * nW + (A >> 5)] & lowA);   // A among B's neighbours
+        int slot = 0;
+        if (nrot[A] > 1 && nrot[B] > 1) {
+            const int ia = (int)wpre[A * nW + (B >> 5)] + __popc(bitmap[A * nW + (B >> 5)] & lowB);
+            const int ib = (int)wpre[B * nW + (A >> 5)] + __popc(bitmap[B * nW + (A >> 5)] & lowA);
+            const int e = ebase[A] + ia;
+            slot = e;
+            pair_ab[2 * e] = (unsigned short)A;
+            pair_ab[2 * e + 1] = (unsigned short)B;
+            inc[istart[A] + ia] = 2 * e;        // incidence lists list the neighbours in ascending order, as k_rot_prep does
+            inc[istart[B] + ib] = 2 * e + 1;
+        }
+        rown[astart[A] + pa] = nbr_pack(m, true, B, slot);
+        rown[astart[B] + pb] = nbr_pack(mt, false, A, slot);
     }
+    for (int A = tid; A <= nR; A += BUILD_TPB) P.istart[size_t(r) * (nR + 1) + A] = istart[A];
     for (int i = tid; i < nR * MAXR; i += BUILD_TPB) P.enode[size_t(r) * nR * MAXR + i] = en[i];
     {
         float4* pm4 = reinterpret_cast<float4*>(P.pmat + size_t(r) * P.max_pairs * 36);
         for (int i = tid; i < n_pair * 9; i += BUILD_TPB) pm4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    __syncthreads();   // a2c complete
+    __syncthreads();
 
-    // ---- 4. CSR rows, one thread per bead: its residue's adjacency row x the masks ----------------------------------------
-    // partner states of residue C seen from state a of residue A: a row (A<C) or a column (A>C) of the pair's mask
-    auto partner_bits = [&](int A, int a, int C) -> unsigned {
-        const bool up = A < C;
-        const unsigned long long m = cmask[a2c[up ? aslot_of(A, C) : aslot_of(C, A)]];
-        if (up) return (unsigned)(m >> (a * 6)) & 63u;
-        const unsigned x = (unsigned)(m >> a) & 0x41041041u;   // bits b*6
-        return (x & 1u) | ((x >> 5) & 2u) | ((x >> 10) & 4u) | ((x >> 15) & 8u) | ((x >> 20) & 16u) | ((x >> 25) & 32u);
-    };
-    for (int i = tid; i < nb; i += BUILD_TPB) {   // pass 1: row length, partners below, folding partners below, evaluated entries
-        const int me = rr[i], A = me >> 4, a = (me >> 1) & 7;
-        const bool mA = me & 1;
+    // ---- 5. CSR rows ------------------------------------------------------------------------------------------------------
+    // pass 1, one thread per bead: walk the residue's neighbour row; row length, partners below, folding partners below,
+    // evaluated entries - and for every neighbour the offset its entries get inside the bead's row (among the partners
+    // above: position in the whole row; among those below: position inside the folding / non-folding group)
+    for (int i = tid; i < nb; i += BUILD_TPB) {
+        const int A = P.bead_res[i], a = P.bead_rot[i], a6 = 6 * a;
+        const bool mA = nrot[A] > 1;
         int cnt = 0, lo = 0, nfl = 0, nev = 0;
-        for (int w = 0; w < nW; ++w) {
-            unsigned bits = adj[A * nW + w];
-            while (bits) {
-                const int C = (w << 5) + __ffs(bits) - 1;
-                bits &= bits - 1;
-                const int n = __popc(partner_bits(A, a, C));
-                const bool mB = nrot[C] > 1, below = C < A;
-                cnt += n;
-                if (below) { lo += n; if (mA && !mB) { nfl += n; nev += n; } }
-                else if (mA || !mB) nev += n;
-            }
+        for (int t = astart[A]; t < astart[A + 1]; ++t) {
+            const unsigned long long nr = rown[t];
+            const int n = __popc((unsigned)(nr >> a6) & 63u);
+            const bool mB = nrot[(int)(nr >> 37) & 0x7ff] > 1, below = !((nr >> 36) & 1ull), fold = mA && !mB;
+            off[6 * t + a] = (unsigned short)(below ? (fold ? nfl : lo - nfl) : cnt);
+            cnt += n;
+            if (below) { lo += n; if (fold) { nfl += n; nev += n; } }
+            else if (mA || !mB) nev += n;
         }
         rs[i] = cnt;   // scanned in place below
         lo_s[i] = (unsigned short)(lo - nfl);
@@ -600,44 +640,58 @@ __global__ void __launch_bounds__(BUILD_TPB) k_rot_build(RotamerDev P, BuildLay 
         if (tid == 0) rs[nb] = tot;
     }
     __syncthreads();
-    if (rs[nb] > P.cap_e) { fail(3); return; }
+    if (rs[nb] > P.cap_e) { fail(3); return true; }
     for (int i = tid; i <= nb; i += BUILD_TPB) rowstart[i] = rs[i];
     unsigned short* dj = P.dj + size_t(r) * P.cap_e;
     int* code = P.code + size_t(r) * P.cap_e;
-    for (int i = tid; i < nb; i += BUILD_TPB) {   // pass 2: place the entries (order inside a row: see k_rot_prep)
-        const int me = rr[i], A = me >> 4, a = (me >> 1) & 7, base = rs[i];
-        const bool mA = me & 1;
-        int run_f = lo_s[i], run_o = 0, k = 0;
-        for (int w = 0; w < nW; ++w) {
-            unsigned bits = adj[A * nW + w];
-            while (bits) {
-                const int C = (w << 5) + __ffs(bits) - 1;
-                bits &= bits - 1;
-                unsigned pb = partner_bits(A, a, C);
-                if (!pb) continue;
-                const bool mB = nrot[C] > 1, below = C < A;
-                const int fC = rfirst[C];
-                const int slot36 = (mA && mB) ? 36 * (A < C ? slot_of(A, C) : slot_of(C, A)) : 0;
-                while (pb) {
-                    const int b = __ffs(pb) - 1;
-                    pb &= pb - 1;
-                    int cd;
-                    if (mA && mB) cd = slot36 + (A < C ? a * 6 + b : b * 6 + a);
-                    else if (mA) cd = code_node(A * MAXR + a, true);
-                    else if (mB) cd = code_node(C * MAXR + b, false);
-                    else cd = CODE_SS;
-                    const int at = !below ? k : ((mA && !mB) ? run_f++ : run_o++);
-                    dj[base + at] = (unsigned short)(fC + b);
-                    code[base + at] = cd;
-                    ++k;
+    // pass 2, one thread per (residue, neighbour): the entries of all the residue's beads against that neighbour.  What a
+    // pair decides - who folds, which matrix, where the neighbour's beads start - is worked out once, not once per bead.
+    // Order inside a row as k_rot_prep: partners below that do not fold, those that fold, partners above ascending.
+    for (int t = tid; t < n_act2; t += BUILD_TPB) {
+        const unsigned long long nr = rown[t];
+        const int C = (int)(nr >> 37) & 0x7ff, slot36 = 36 * (int)(nr >> 48);
+        const bool up = (nr >> 36) & 1ull;
+        int A;   // owner of entry t: the residue whose neighbour row contains it
+        {
+            int lo_r = 0, hi_r = nR - 1;
+            while (lo_r < hi_r) { const int mid = (lo_r + hi_r + 1) >> 1; if (astart[mid] <= t) lo_r = mid; else hi_r = mid - 1; }
+            A = lo_r;
+        }
+        const int nA = nrot[A], fA = rfirst[A], fC = rfirst[C];
+        const bool mA = nA > 1, mB = nrot[C] > 1, fold = mA && !mB;
+        for (int a = 0; a < nA; ++a) {
+            const unsigned pb = (unsigned)(nr >> (6 * a)) & 63u;
+            if (!pb) continue;
+            const int i = fA + a;
+            int at = rs[i] + (int)off[6 * t + a] + ((!up && fold) ? (int)lo_s[i] : 0);
+            // code of partner state b = cbase + b * cstep (matrix element / node whose marginal weights the entry)
+            int cbase, cstep;
+            if (mA && mB) { cbase = slot36 + (up ? a * 6 : a); cstep = up ? 1 : 6; }
+            else if (mA) { cbase = code_node(A * MAXR + a, true); cstep = 0; }
+            else if (mB) { cbase = code_node(C * MAXR, false); cstep = -2; }
+            else { cbase = CODE_SS; cstep = 0; }
+#pragma unroll
+            for (int b = 0; b < MAXR; ++b)
+                if (pb & (1u << b)) {
+                    dj[at] = (unsigned short)(fC + b);
+                    code[at] = cbase + b * cstep;
+                    ++at;
                 }
-            }
         }
     }
-    __syncthreads();
     for (int i = tid; i < nb; i += BUILD_TPB) P.lower[size_t(r) * nb + i] = lo_s[i];
     sort_rows_desc_u16(nb, [&](int i) { return (int)ce_s[i]; }, P.order_e + size_t(r) * nb, hist);
     sort_rows_desc_u16(nb, [&](int i) { return rs[i + 1] - rs[i]; }, P.order_d + size_t(r) * nb, hist);
+    return true;
+}
+
+// the shared-memory-only body first; a replica that overflows its capacities (clashing start structures) is redone by the
+// body whose arrays continue in global memory
+__global__ void __launch_bounds__(BUILD_TPB, 4) k_rot_build(RotamerDev P, BuildLay L) {
+    extern __shared__ unsigned long long smem_ull[];
+    if (rot_build_body<false>(P, L, smem_ull)) return;
+    __syncthreads();
+    rot_build_body<true>(P, L, smem_ull);
 }
 
 // ================================================================================================ edge kernels
@@ -1562,7 +1616,9 @@ struct RotamerSidechain : PotentialNode {
     int max_iter, chunk;
     size_t smem_prep = 0, smem_edge = 0, smem_bp = 0, smem_bp2 = 0, smem_build = 0;
     bool fast_build = false;   // k_rot_build instead of Verlet cache + k_refine + k_rot_prep
-    BuildLay blay{0, 0};
+    BuildLay blay{0, 0, 0, 0, nullptr, nullptr};
+    DevBuf<unsigned long long> build_spill;
+    DevBuf<int> build_stats;
     Bp2Lay lay2{0, 0, 0};
     bool fast_bp = false;
     DevBuf<int> slow_list, n_slow, n_bad, fe_flag;
@@ -1656,12 +1712,23 @@ struct RotamerSidechain : PotentialNode {
             double scale = 1.0;
             if (const char* s = getenv("UPSIDE_B200_NEIGHBOR_SCALE")) scale = std::max(0.05, atof(s));
             const long all_pairs = long(n_res) * (n_res - 1) / 2;
-            blay.capc = (int)((std::max<long>(4, std::min<long>(all_pairs, (long)std::ceil(24 * scale * n_res))) + 3) & ~3L);
-            blay.capa = (int)((std::max<long>(4, std::min<long>(all_pairs, (long)std::ceil(16 * scale * n_res))) + 3) & ~3L);
+            // shared-memory capacities cover a relaxed chain (measured at 100 residues, T = 0.8: see DESIGN.md); the totals
+            // cover clashing start structures
+            double cs = 12, as = 6;
+            if (const char* e = getenv("UPSIDE_B200_BUILD_CAPS")) sscanf(e, "%lf,%lf", &cs, &as);
+            auto cap = [&](double per_res) { return (int)((std::max<long>(4, std::min<long>(all_pairs, (long)std::ceil(per_res * scale * n_res))) + 3) & ~3L); };
+            blay.capa = cap(as); blay.capc = std::max(cap(cs), 2 * blay.capa);   // (the offsets of pass 2 reuse the mask + candidate arrays)
+            blay.capc_tot = std::max(blay.capc, cap(64)); blay.capa_tot = std::max(blay.capa, cap(32));
             smem_build = build_bytes();
-            if (blay.capc > 65535 || smem_build > (size_t)device_smem) fast_build = false;   // large systems keep the Verlet path
+            // large systems keep the Verlet path
+            if (n_res > BUILD_MAX_RES || max_pairs > BUILD_MAX_SLOT || smem_build > (size_t)device_smem) fast_build = false;
         }
         ig.lists = !fast_build;
+        if (fast_build) {
+            build_spill.alloc(B * build_spill_words(blay) + 1);
+            build_stats.alloc(B * 2);
+            blay.spill = build_spill.p; blay.bstats = build_stats.p;
+        }
         ig.allocate(engine);
         // BP kernel: fixed part + 204 bytes per pair; aim for two resident CTAs per SM, never more pairs than can occur
         size_t fixed_bp = sizeof(float) * (size_t(n_res) * MAXR * 2 + n_res + 32) + sizeof(int) * (2 * n_res + 1);
@@ -1770,8 +1837,8 @@ struct RotamerSidechain : PotentialNode {
     }
     size_t build_bytes() const {
         const size_t nR = n_res, nW = n_words, nb = ig.n1;
-        return 8 * size_t(blay.capc) + 16 * (nb + nR) + 4 * (2 * nR * nW + blay.capc) + 4 * (7 * nR + 3) + 4 * nR * MAXR +
-               4 * (2 * nb + 1 + 33 + 256) + 2 * (2 * nR * nW + blay.capa + 2 * nb) + 16;
+        return 16 * size_t(blay.capa) + 8 * size_t(blay.capc) + 16 * (nb + nR) + 4 * (2 * nR * nW + blay.capc) + 4 * (6 * nR + 3) +
+               4 * nR * MAXR + 4 * (nb + 1 + 33 + 256) + 2 * (2 * nR * nW + 2 * nb) + 16;
     }
     RotamerDev dev() {
         RotamerDev P;
@@ -1897,6 +1964,11 @@ struct RotamerSidechain : PotentialNode {
             std::vector<float> out(ig.n1);
             for (int b = 0; b < ig.n1; ++b) out[b] = nmg[bead_res[b] * MAXR + bead_rot[b]];
             return out;
+        }
+        if (nm == "build_stats") {     // B200 extension: (sphere-test survivors, active residue pairs) of the fast build
+            std::vector<int> st(2, 0);
+            if (fast_build) UB_CUDA(cudaMemcpy(st.data(), build_stats.p + size_t(replica) * 2, 2 * sizeof(int), cudaMemcpyDeviceToHost));
+            return {float(st[0]), float(st[1])};
         }
         if (nm == "solve_stats") {     // B200 extension: (n_iter, n residue pairs, converged, n 6x6 pairs, n 3x6 pairs)
             std::vector<int> st(4);
