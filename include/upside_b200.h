@@ -94,6 +94,33 @@ int ub_replex_decide(UbReplex* h, int set, const float* old_lboltz, const float*
 int ub_replex_decide_same_hamiltonian(UbReplex* h, int set, const float* beta, const float* energy, int* accept);
 int ub_replex_replica_indices(const UbReplex* h, int* out /* n_system */);
 int ub_replex_counts(const UbReplex* h, int set, uint64_t* n_attempt, uint64_t* n_success);
+/* Replica exchange of a ladder SHARDED OVER GPUs, on the device and on the engine's stream (src/main.cpp:227-275; the 8-GPU
+ * ladder of BASELINE.json config 4).  Rank g of `world` owns the contiguous rungs [g*n_local, (g+1)*n_local) as the replicas
+ * of its engine (n_local = n_global/world = ub_n_replica(e)).  One attempt = one batched energy evaluation, an
+ * ncclAllGather of the energies, the Metropolis pass of ALL swap sets on the device (same counter-based random stream as
+ * the reference; identical on every rank, nothing is broadcast), and per swap set a grouped ncclSend/ncclRecv of the
+ * coordinates of block-boundary rungs.  Asynchronous like ub_md_run; nothing synchronises with the host.
+ *   nccl_comm: an ncclComm_t whose rank/size match (NULL for world == 1).  ub_nccl_unique_id + ub_nccl_comm_create make
+ *   one (rank 0 creates the 128-byte id and hands it to the other ranks by any means); ub_nccl_comm_create_all makes one
+ *   per device for a single process driving several GPUs.  NCCL is bound at run time (dlopen), not linked. */
+typedef struct UbLadder UbLadder;
+const char* ub_ladder_last_error(void);
+int ub_nccl_unique_id(char* out, int len /* >= 128 */);
+void* ub_nccl_comm_create(const char* unique_id, int world, int rank, int device);
+int ub_nccl_comm_create_all(int n_device, const int* devices, void** comms /* n_device */);
+void ub_nccl_comm_destroy(void* comm);
+UbLadder* ub_ladder_create(UbEngine* e, void* nccl_comm, int rank, int world, int n_global, int n_set, const char* const* swap_sets,
+                           uint32_t seed, const float* temperature_all /* n_global */);
+void ub_ladder_destroy(UbLadder* h);
+int ub_ladder_attempt(UbLadder* h, uint64_t round);
+int ub_ladder_set_temperature(UbLadder* h, const float* temperature_all);
+int ub_ladder_n_pairs(const UbLadder* h);
+/* waits for the stream; any pointer may be NULL.  replica_indices: n_global; accept / n_attempt / n_success: one entry per
+ * swap pair, sets concatenated; energies: the n_global energies the last attempt decided on */
+int ub_ladder_state(UbLadder* h, int* replica_indices, int* accept, uint64_t* n_attempt, uint64_t* n_success, float* energies);
+/* bytes this rank receives in the all-gather and sends as boundary coordinates per attempt */
+int ub_ladder_comm_bytes(const UbLadder* h, uint64_t* allgather_bytes, uint64_t* coordinate_bytes);
+
 /* known-answer access to the host generator: n_draw successive uniform_open_closed().x values (+ raw bits of the first) */
 int ub_host_rng_uniform(uint32_t seed, uint32_t stream, uint32_t atom, uint64_t timestep, int n_draw, float* out,
                         uint32_t* bits_first /* 4 or NULL */);

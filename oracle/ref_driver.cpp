@@ -122,6 +122,68 @@ int ref_md_run(const char* config_path, int n_sys, int n_atom, float* pos, float
     return 1;
 } catch(...) { return 1; }
 
+// Timing variant of ref_md_run for bench.py's CPU arms: engines are constructed once, `warm_round` untimed rounds run first
+// (thread team spawned, pair lists built, caches warm), then `n_rep` repetitions of `n_round` rounds are timed one by one
+// into seconds[n_rep] (the caller quotes the median).  pos: [n_sys][n_atom][3] in/out.
+int ref_md_bench(const char* config_path, int n_sys, int n_atom, float* pos, const float* temperature, uint32_t base_seed,
+                 float dt, float thermostat_timescale, long warm_round, long n_round, int n_rep, int n_thread,
+                 double* seconds) try {
+    struct Sys { DerivEngine* e; VecArrayStorage mom; OrnsteinUhlenbeckThermostat th; Sys(int n): e(nullptr), mom(3,round_up(n,4)) {} };
+    std::vector<std::unique_ptr<Sys>> sys;
+    for(int s=0; s<n_sys; ++s) {
+        sys.emplace_back(new Sys(n_atom));
+        auto& S = *sys.back();
+        S.e = construct_deriv_engine(n_atom, config_path, true);
+        if(!S.e) return 1;
+        for(int na=0; na<n_atom; ++na) for(int d=0; d<3; ++d) S.e->pos->output(d,na) = pos[(size_t(s)*n_atom+na)*3+d];
+        fill(S.mom, 0.f);
+        S.th = OrnsteinUhlenbeckThermostat(base_seed + s, thermostat_timescale, 1., 1e8);
+        S.th.set_temp(temperature[s]);
+        S.th.apply(S.mom, n_atom);
+        S.th.set_delta_t(3*dt);
+    }
+    if(n_thread>0) omp_set_num_threads(n_thread);
+    auto run = [&](long rounds) {
+        #pragma omp parallel for schedule(static,1)
+        for(int s=0; s<n_sys; ++s) {
+            auto& S = *sys[s];
+            for(long nr=0; nr<rounds; ++nr) {
+                S.th.apply(S.mom, n_atom);
+                S.e->integration_cycle(S.mom, dt, 0.f, DerivEngine::Verlet);
+            }
+        }
+    };
+    run(warm_round);
+    for(int rep=0; rep<n_rep; ++rep) {
+        auto t0 = std::chrono::high_resolution_clock::now();
+        run(n_round);
+        seconds[rep] = std::chrono::duration<double>(std::chrono::high_resolution_clock::now()-t0).count();
+    }
+    for(int s=0; s<n_sys; ++s) {
+        auto& S = *sys[s];
+        for(int na=0; na<n_atom; ++na) for(int d=0; d<3; ++d) pos[(size_t(s)*n_atom+na)*3+d] = S.e->pos->output(d,na);
+        free_deriv_engine(S.e);
+    }
+    return 0;
+} catch(const std::string& e) {
+    fprintf(stderr, "ref_md_bench: %s\n", e.c_str());
+    return 1;
+} catch(...) { return 1; }
+
+// Latency of single evaluations through the reference's own C ABI (evaluate_deriv, engine_c_library.cpp:47-64): n_eval
+// calls on the same coordinates after n_warm untimed ones; returns microseconds per call in *us.
+int ref_eval_latency(const char* config_path, int n_atom, const float* pos, int n_warm, int n_eval, double* us) try {
+    DerivEngine* e = construct_deriv_engine(n_atom, config_path, true);
+    if(!e) return 1;
+    std::vector<float> deriv(size_t(n_atom)*3);
+    for(int i=0; i<n_warm; ++i) evaluate_deriv(deriv.data(), e, pos);
+    auto t0 = std::chrono::high_resolution_clock::now();
+    for(int i=0; i<n_eval; ++i) evaluate_deriv(deriv.data(), e, pos);
+    *us = std::chrono::duration<double>(std::chrono::high_resolution_clock::now()-t0).count() * 1e6 / n_eval;
+    free_deriv_engine(e);
+    return 0;
+} catch(...) { return 1; }
+
 // n_step Monte-Carlo executes (rounds first_round, first_round+1, ...) on n_sys copies of the configuration `rw_copy_path`
 // (a scratch copy without /output: the samplers register loggers, which need a writable file; use n_sys = 1 per copy).  pos: [n_sys][n_atom][3] in/out;
 // stats_out: [n_sys][n_sampler][2] (n_success, n_attempt); returns the number of samplers, negative on error.

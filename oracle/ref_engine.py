@@ -187,6 +187,36 @@ def md_run(config_path, pos, temperature, n_round, seed=42, dt=0.009, timescale=
     return dict(pos=pos, mom=mom, potential=pot, seconds=sec.value)
 
 
+def md_bench(config_path, pos, temperature, warm_rounds, n_round, n_rep=3, seed=42, dt=0.009, timescale=5.0, n_thread=0,
+             flavour='fast'):
+    """Timed reference MD (ref_driver.cpp:ref_md_bench): engines built once, warm_rounds untimed rounds, then n_rep timed
+    repetitions of n_round rounds.  Returns dict(pos, seconds=[n_rep])."""
+    L = load(flavour)
+    pos = np.array(pos, dtype='f4', order='C')
+    n_sys, n_atom = pos.shape[0], pos.shape[1]
+    T = np.ascontiguousarray(np.broadcast_to(np.asarray(temperature, dtype='f4'), (n_sys,)))
+    sec = (ct.c_double * n_rep)()
+    L.ref_md_bench.restype = ct.c_int
+    L.ref_md_bench.argtypes = [ct.c_char_p, ct.c_int, ct.c_int, ct.POINTER(ct.c_float), ct.POINTER(ct.c_float), ct.c_uint32, ct.c_float,
+                               ct.c_float, ct.c_long, ct.c_long, ct.c_int, ct.c_int, ct.POINTER(ct.c_double)]
+    if L.ref_md_bench(config_path.encode(), n_sys, n_atom, _fp(pos), _fp(T), seed, dt, timescale, int(warm_rounds), int(n_round),
+                      int(n_rep), int(n_thread), sec):
+        raise RuntimeError('ref_md_bench failed')
+    return dict(pos=pos, seconds=list(sec))
+
+
+def eval_latency(config_path, pos, n_warm=20, n_eval=200, flavour='fast'):
+    """microseconds per evaluate_deriv call of the reference's C ABI on one system (ref_driver.cpp:ref_eval_latency)"""
+    L = load(flavour)
+    pos = np.array(pos, dtype='f4', order='C')
+    us = ct.c_double()
+    L.ref_eval_latency.restype = ct.c_int
+    L.ref_eval_latency.argtypes = [ct.c_char_p, ct.c_int, ct.POINTER(ct.c_float), ct.c_int, ct.c_int, ct.POINTER(ct.c_double)]
+    if L.ref_eval_latency(config_path.encode(), pos.shape[0], _fp(pos), int(n_warm), int(n_eval), ct.byref(us)):
+        raise RuntimeError('ref_eval_latency failed')
+    return us.value
+
+
 def mc_steps(config_path, pos, temperature, base_seed, first_round, n_step, flavour='pinned', max_sampler=4):
     """Reference Monte-Carlo samplers (ref_driver.cpp:ref_mc_steps) on copies of `pos` (n_sys, n_atom, 3), system s seeded
     base_seed + s.  Returns (new positions, stats[n_sys, n_sampler, 2] = n_success, n_attempt)."""

@@ -22,6 +22,8 @@ struct DerivEngine {
     UbEngine u;
 };
 
+namespace ub { Engine* engine_of(UbEngine* e) { return e->eng.get(); } }   // for the translation units that extend the ABI
+
 static thread_local std::string g_last_error;
 
 static int fail(const std::string& e) {

@@ -1577,6 +1577,13 @@ __global__ void __launch_bounds__(BP2_TPB, BP2_OCC) k_rot_bp2(RotamerDev P, Bp2L
     }
 }
 
+// (Measured and rejected in round 2: a kernel that gives every DIRECTED message its own lane - cavity, matrix-vector product,
+// normalisation, then the product of a residue's incoming messages inside an aligned power-of-two lane group, beliefs and
+// messages double-buffered, ONE barrier per sweep.  It removes k_rot_bp2's second barrier and its idle warps, but every lane
+// repeats the cavity division and loads its own copy of the pair matrix (rows for one direction, columns for the other,
+// so the two kinds of lane diverge): 175 k warp instructions per solve against 112 k, 1377 us against 650 us per batched
+// evaluation at B = 4096, and 56 bytes of shared memory per lane left room for two CTAs per SM only.)
+
 // parameter derivative (interaction_graph.h:404-415 with bead_interaction.h:204-207): sum over bead pairs (i<j, the
 // reference's edge orientation) of the backward weight ss[e] (pair marginal / node marginal / 1) times
 // d(quadspline)/d(param) of the ordered type pair; off the hot path, one thread per CSR row, atomics into the table

@@ -101,6 +101,23 @@ def lib():
     L.ub_replex_replica_indices.argtypes = [ct.c_void_p, _ip]
     L.ub_replex_counts.argtypes = [ct.c_void_p, ct.c_int, ct.POINTER(ct.c_uint64), ct.POINTER(ct.c_uint64)]
     L.ub_host_rng_uniform.argtypes = [ct.c_uint32, ct.c_uint32, ct.c_uint32, ct.c_uint64, ct.c_int, _fp, ct.POINTER(ct.c_uint32)]
+    # device-resident ladder exchange over NCCL (csrc/ladder_nccl.cu)
+    _u64p = ct.POINTER(ct.c_uint64)
+    L.ub_ladder_last_error.restype = ct.c_char_p
+    L.ub_nccl_unique_id.argtypes = [ct.c_char_p, ct.c_int]
+    L.ub_nccl_comm_create.restype = ct.c_void_p
+    L.ub_nccl_comm_create.argtypes = [ct.c_char_p, ct.c_int, ct.c_int, ct.c_int]
+    L.ub_nccl_comm_destroy.restype = None
+    L.ub_nccl_comm_destroy.argtypes = [ct.c_void_p]
+    L.ub_ladder_create.restype = ct.c_void_p
+    L.ub_ladder_create.argtypes = [ct.c_void_p, ct.c_void_p, ct.c_int, ct.c_int, ct.c_int, ct.c_int, ct.POINTER(ct.c_char_p), ct.c_uint32, _fp]
+    L.ub_ladder_destroy.restype = None
+    L.ub_ladder_destroy.argtypes = [ct.c_void_p]
+    L.ub_ladder_attempt.argtypes = [ct.c_void_p, ct.c_uint64]
+    L.ub_ladder_set_temperature.argtypes = [ct.c_void_p, _fp]
+    L.ub_ladder_n_pairs.argtypes = [ct.c_void_p]
+    L.ub_ladder_state.argtypes = [ct.c_void_p, _ip, _ip, _u64p, _u64p, _fp]
+    L.ub_ladder_comm_bytes.argtypes = [ct.c_void_p, _u64p, _u64p]
     _lib = L
     return L
 
@@ -407,6 +424,72 @@ class BatchEngine(object):
 
     def launches_per_eval(self):
         return self.L.ub_launches_per_eval(self.e)
+
+
+class Ladder(object):
+    """Replica exchange of a temperature ladder sharded over GPUs, on the device (csrc/ladder_nccl.cu; reference
+    ReplicaExchange::attempt_swaps, src/main.cpp:227-275).  `engine` holds this rank's contiguous block of rungs;
+    `temperature_all` the temperatures of all n_global rungs; `swap_sets` the reference's --swap-set strings
+    ("0-1,2-3,...").  With world > 1 pass nccl_comm (see nccl_comm_from_torch)."""
+
+    def __init__(self, engine, swap_sets, temperature_all, seed=42, rank=0, world=1, nccl_comm=None):
+        self.L, self.engine = lib(), engine
+        t = np.ascontiguousarray(temperature_all, dtype='f4')
+        self.n_global = len(t)
+        arr = (ct.c_char_p * len(swap_sets))(*[s.encode() for s in swap_sets])
+        self.h = self.L.ub_ladder_create(engine.e, nccl_comm, rank, world, self.n_global, len(swap_sets), arr, seed, _f(t))
+        if not self.h:
+            raise RuntimeError('ub_ladder_create: %s' % (self.L.ub_ladder_last_error() or b'').decode())
+        self.n_pairs = self.L.ub_ladder_n_pairs(self.h)
+
+    def attempt(self, round_num):
+        """asynchronous: enqueued on the engine's stream"""
+        if self.L.ub_ladder_attempt(self.h, int(round_num)):
+            raise RuntimeError('ub_ladder_attempt: %s' % (self.L.ub_ladder_last_error() or b'').decode())
+
+    def state(self):
+        """(replica_indices, accept of the last attempt, n_attempt, n_success, energies of the last attempt); waits for the stream"""
+        ri, acc = np.zeros(self.n_global, dtype='i4'), np.zeros(max(1, self.n_pairs), dtype='i4')
+        na, ns = np.zeros(max(1, self.n_pairs), dtype='u8'), np.zeros(max(1, self.n_pairs), dtype='u8')
+        en = np.zeros(self.n_global, dtype='f4')
+        u64p = ct.POINTER(ct.c_uint64)
+        if self.L.ub_ladder_state(self.h, ri.ctypes.data_as(_ip), acc.ctypes.data_as(_ip), na.ctypes.data_as(u64p), ns.ctypes.data_as(u64p), _f(en)):
+            raise RuntimeError('ub_ladder_state: %s' % (self.L.ub_ladder_last_error() or b'').decode())
+        return ri, acc[:self.n_pairs], na[:self.n_pairs], ns[:self.n_pairs], en
+
+    def comm_bytes(self):
+        a, c = ct.c_uint64(), ct.c_uint64()
+        self.L.ub_ladder_comm_bytes(self.h, ct.byref(a), ct.byref(c))
+        return int(a.value), int(c.value)
+
+    def close(self):
+        if self.h:
+            self.L.ub_ladder_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def nccl_comm_from_torch(dist, device):
+    """an ncclComm_t of our own for the ranks of an initialised torch.distributed job: rank 0 creates the unique id, the
+    job's existing backend carries its 128 bytes to the other ranks (plumbing only), every rank joins"""
+    import torch
+    L = lib()
+    buf = ct.create_string_buffer(128)
+    if dist.get_rank() == 0 and L.ub_nccl_unique_id(buf, 128):
+        raise RuntimeError('ub_nccl_unique_id: %s' % (L.ub_ladder_last_error() or b'').decode())
+    dev = torch.device('cuda', device) if dist.get_backend() == 'nccl' else torch.device('cpu')
+    t = torch.tensor(list(buf.raw), dtype=torch.uint8, device=dev)
+    dist.broadcast(t, 0)
+    raw = bytes(t.cpu().tolist())
+    comm = L.ub_nccl_comm_create(raw, dist.get_world_size(), dist.get_rank(), device)
+    if not comm:
+        raise RuntimeError('ub_nccl_comm_create: %s' % (L.ub_ladder_last_error() or b'').decode())
+    return comm
 
 
 def measure_fp32_peak(device=0):
