@@ -24,6 +24,8 @@ def _check_report(rep):
         assert abs(e_g - e_r) <= E_RTOL * max(1.0, abs(e_r)), r['energy']
         assert r['deriv_maxabs'] <= F_RTOL * max(1.0, r['deriv_scale']), (r['deriv_maxabs'], r['deriv_scale'])
         assert r['marginal_maxabs'] <= MARG_ATOL
+        # same stopping rule as the oracle (rotamer.cpp:1037-1049): equal sweep counts, at most one chunk apart on a borderline deviation
+        assert abs(int(r['bp_stats'][0][0]) - r['bp_stats'][1]['n_iter']) <= 2, r['bp_stats']
         for name, d in r['pairlists'].items():
             # bit-exact (edges and order) given identical inputs to the pair-list stage: the reference predicate applied
             # to the GPU's own node outputs.  End to end the two engines' bead coordinates differ by ~1e-5 A of upstream
@@ -35,7 +37,10 @@ def _check_report(rep):
         for name, d in r['nodes'].items():
             if 'pot' in d:
                 a, b = d['pot']
-                assert abs(a - b) <= E_RTOL * max(1.0, abs(b)) + 5e-3, (name, d)   # small terms: absolute floor
+                # small terms: absolute floor 1e-3.  The rotamer free energy is evaluated at beliefs that both engines iterate
+                # only to |delta belief| <= 1e-3 (same sweep count, marginals within 1e-3 of each other): floor 5e-3 there
+                floor = 5e-3 if name.startswith('rotamer') else 1e-3
+                assert abs(a - b) <= E_RTOL * max(1.0, abs(b)) + floor, (name, d)
             else:
                 assert d['out'] <= 2e-3 * max(1.0, d['out_scale']), (name, d)
                 assert d['sens'] <= 2e-3 * max(1.0, d['sens_scale']), (name, d)
@@ -66,7 +71,7 @@ def test_golden_fixtures(cid):
                 assert pl.shape == g[key].shape and (pl == g[key]).all(), name
     for k in g.files:
         if k.startswith('pot_'):
-            np.testing.assert_allclose(be.node_potential(k[4:]), g[k], rtol=E_RTOL, atol=5e-3)
+            np.testing.assert_allclose(be.node_potential(k[4:]), g[k], rtol=E_RTOL, atol=5e-3 if k[4:].startswith('rotamer') else 1e-3)
     be.close()
 
 
@@ -140,6 +145,39 @@ def test_monte_carlo_pivot_moves_match_reference(cid):
     be.close()
 
 
+@pytest.mark.skipif(not ref_engine.available('pinned'), reason='oracle/_ref not shipped')
+def test_monte_carlo_jump_moves_match_reference(tmp_path):
+    """rigid-body jump moves (JumpSampler, src/monte_carlo_sampler.cpp:203-251) next to the pivot moves: config 5 (the membrane
+    potential makes the energy depend on where the molecule sits, so the Metropolis test of a jump is not vacuous) with a
+    /input/jump_moves group over the whole chain; same seeds and rounds on both engines => the same proposals (translation
+    or rotation from the reference's random stream), the same decisions, the same coordinates"""
+    from upside_md_b200 import config
+    cfg = str(tmp_path / 'config5_jump.up')
+    w = config.ConfigWriter.from_file(parity.CONFIGS[5])
+    w.write_jump_moves([[0, w.n_atom]], 1.5, 0.4)
+    w.save(cfg)
+    pos = parity.test_positions(parity.CONFIGS[5], 7, relax_rounds=20)[1:]
+    rounds = list(range(5, 15))
+    ref_pos, ref_stats = ref_engine.mc_steps(cfg, pos, 0.8, 42, rounds[0], len(rounds))
+    be = ue.BatchEngine(cfg, len(pos))
+    names = be.mc_samplers()
+    assert names == ['pivot', 'jump']
+    be.set_pos(pos); be.md_init(0.8, seed=42)
+    for nr in rounds:
+        be.mc_execute(nr)
+    same = np.ones(len(pos), dtype=bool)
+    for m, nm in enumerate(names):
+        ok, tr = be.mc_stats(m)
+        assert (tr == len(rounds)).all() and (ref_stats[:, m, 1] == len(rounds)).all()
+        same &= ok == ref_stats[:, m, 0]
+    n_jump_ok = ref_stats[:, 1, 0].sum()
+    assert 0 < n_jump_ok < len(pos) * len(rounds)                        # jumps were both accepted and rejected
+    assert same.sum() >= len(pos) - 1                                   # a Metropolis test within rounding of its variate may flip
+    got = be.get_pos()
+    assert np.abs(got[same] - ref_pos[same]).max() <= 5e-3              # coordinates after up to 20 rigid moves of a 300-residue chain
+    be.close()
+
+
 @pytest.mark.parametrize('cid', [1, 3])
 def test_trajectory_matches_golden(cid):
     g = np.load(os.path.join(GOLD, 'config%d.npz' % cid))
@@ -148,7 +186,7 @@ def test_trajectory_matches_golden(cid):
     assert np.abs(be.get_pos() - g['traj_pos_1']).max() <= 1e-4
     assert np.abs(be.get_mom() - g['traj_mom_1']).max() <= 2e-3
     be.set_pos(g['pos']); be.md_init(0.8, seed=42); be.md_run(10)       # 30 timesteps
-    assert np.abs(be.get_pos() - g['traj_pos_10']).max() <= 5e-3
+    assert np.abs(be.get_pos() - g['traj_pos_10']).max() <= 1e-3      # 1e-3 A after 30 deterministic-noise steps
     be.close()
 
 

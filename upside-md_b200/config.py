@@ -547,6 +547,15 @@ class ConfigWriter:
         self.arr(g, 'pivot_range', np.column_stack((pivot_atom[nonterm][:, 4] + 1,
                                                     np.zeros(nonterm.sum(), 'i') + self.n_atom)))
 
+    def write_jump_moves(self, atom_ranges, sigma_trans, sigma_rot):
+        """/input/jump_moves as JumpSampler reads it (src/monte_carlo_sampler.cpp:174-201): rigid translations (sigma_trans,
+        Angstrom) and rotations about the centre of mass (sigma_rot, radians) of the atom ranges [first, next_first)"""
+        atom_ranges = np.asarray(atom_ranges, dtype='i4').reshape(-1, 2)
+        g = self.root['input'].create_group('jump_moves')
+        self.arr(g, 'atom_range', atom_ranges)
+        self.arr(g, 'sigma_trans', np.broadcast_to(np.asarray(sigma_trans, dtype='f4'), (len(atom_ranges),)).copy())
+        self.arr(g, 'sigma_rot', np.broadcast_to(np.asarray(sigma_rot, dtype='f4'), (len(atom_ranges),)).copy())
+
     def save(self, path):
         h5lite.save(self.root, path)
 
