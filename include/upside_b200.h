@@ -124,6 +124,14 @@ int ub_ladder_comm_bytes(const UbLadder* h, uint64_t* allgather_bytes, uint64_t*
 /* known-answer access to the host generator: n_draw successive uniform_open_closed().x values (+ raw bits of the first) */
 int ub_host_rng_uniform(uint32_t seed, uint32_t stream, uint32_t atom, uint64_t timestep, int n_draw, float* out,
                         uint32_t* bits_first /* 4 or NULL */);
+/* Checkpoint of the MD state of all replicas: positions, momenta, RNG keys, temperatures, thermostat invocation counter and
+ * round number, integrator settings - a run resumed from it draws the same thermostat noise as the uninterrupted run
+ * (the reference's continue_sim, py/run_upside.py:231-257, restarts from the last frame with
+ * fresh momenta).  ub_checkpoint_size: upper bound of the blob; save writes it into buf (*written = its size); load
+ * restores into an engine of the same configuration and batch size (no md_init needed before). */
+long ub_checkpoint_size(UbEngine* e);
+int ub_checkpoint_save(UbEngine* e, void* buf, long buf_size, long* written);
+int ub_checkpoint_load(UbEngine* e, const void* buf, long size);
 int ub_md_run(UbEngine* e, long n_round);      /* asynchronous; ub_sync waits and reports device-side failures */
 int ub_sync(UbEngine* e);
 int ub_recenter(UbEngine* e, int xy_only);     /* src/deriv_engine.cpp:37-48 */

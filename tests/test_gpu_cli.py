@@ -2,6 +2,7 @@
 Golden data: tests/golden/cli_replex.npz = the reference binary (unmodified src/main.cpp, oracle/_ref/upside_ref) run with
 the same flags on the same inputs (tools/make_golden_cli.py)."""
 import os
+import shutil
 import sys
 
 import numpy as np
@@ -153,3 +154,49 @@ def test_sharded_ladder_on_the_engine_single_rank():
     lad.run(4, 2)
     assert np.isfinite(be.get_pos()).all()
     be.close()
+
+
+def test_checkpoint_resumes_the_random_stream():
+    """pos + mom + RNG keys + (thermostat invocations, round number): a run restored into a FRESH engine continues like the
+    uninterrupted one - same thermostat noise - to within the rounding of the force evaluations (float atomics in the
+    element-wise nodes), far inside the 1e-3 A trajectory gate; without the counters the noise differs and so do the paths"""
+    g = np.load(os.path.join(parity.ROOT, 'tests', 'golden', 'config1.npz'))
+    pos = np.repeat(g['pos'][:1], 4, 0)
+    T = np.array([0.7, 0.8, 0.9, 1.0], dtype='f4')
+    a = ue.BatchEngine(parity.CONFIGS[1], 4)
+    a.set_pos(pos); a.md_init(T, seed=5); a.md_run(7)
+    blob = a.checkpoint()
+    mom_at_ckpt = a.get_mom()
+    a.md_run(9)
+    want_pos, want_mom = a.get_pos(), a.get_mom()
+    a.close()
+    b = ue.BatchEngine(parity.CONFIGS[1], 4)
+    b.restore(blob)
+    assert (b.get_mom() == mom_at_ckpt).all()
+    b.md_run(9)
+    assert np.abs(b.get_pos() - want_pos).max() <= 2e-4
+    assert np.abs(b.get_mom() - want_mom).max() <= 5e-3
+    # a restart that forgets the counters (fresh md_init on the same coordinates) takes a different path
+    c = ue.BatchEngine(parity.CONFIGS[1], 4)
+    c.restore(blob); c.md_init(T, seed=5); c.md_run(9)
+    assert np.abs(c.get_pos() - want_pos).max() > 1e-2
+    with pytest.raises(RuntimeError):
+        ue.BatchEngine(parity.CONFIGS[1], 3).restore(blob)          # other batch size
+    b.close(); c.close()
+
+
+def test_continue_config_like_the_reference(tmp_path):
+    """continue_sim of py/run_upside.py:231-257: last frame -> /input/pos, /output -> /output_previous_0, run again"""
+    cfg = str(tmp_path / 'c1.up')
+    shutil.copy(parity.CONFIGS[1], cfg)
+    flags = ['--duration', '0.3', '--frame-interval', '0.1', '--temperature', '0.8', '--seed', '3']
+    ue.in_process_upside(flags + [cfg], verbose=False)
+    last = np.array(h5lite.load(cfg)['output/pos'].data)[-1, 0]
+    T = ue.continue_config(cfg)
+    t = h5lite.load(cfg)
+    assert T == pytest.approx(0.8) and 'output' not in t and 'output_previous_0' in t
+    np.testing.assert_array_equal(np.array(t['input/pos'].data)[:, :, 0], last)
+    ue.in_process_upside(flags + [cfg], verbose=False)
+    t = h5lite.load(cfg)
+    assert 'output' in t and 'output_previous_0' in t
+    np.testing.assert_allclose(np.array(t['output/pos'].data)[0, 0], last, atol=1e-5)   # the new run starts where the old one stopped

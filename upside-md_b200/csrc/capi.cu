@@ -228,6 +228,25 @@ int ub_swap_pos(UbEngine* e, int n_pair, const int* pairs) {
     UB_TRY e->eng->sync_and_check(); e->eng->swap_pos(std::vector<int>(pairs, pairs + 2 * n_pair)); return 0; UB_CATCH
 }
 int ub_md_set_temperature(UbEngine* e, const float* temperature) { UB_TRY e->eng->set_temperature(temperature); return 0; UB_CATCH }
+long ub_checkpoint_size(UbEngine* e) {
+    const ub::Engine& g = *e->eng;
+    return long(64 + sizeof(float) * (2 * size_t(g.n_rep) * g.n_atom * 3 + g.n_rep) + sizeof(uint32_t) * g.n_rep);
+}
+int ub_checkpoint_save(UbEngine* e, void* buf, long buf_size, long* written) {
+    UB_TRY
+    auto blob = e->eng->checkpoint_save();
+    if (written) *written = (long)blob.size();
+    if ((long)blob.size() > buf_size) throw std::string("checkpoint buffer too small");
+    memcpy(buf, blob.data(), blob.size());
+    return 0;
+    UB_CATCH
+}
+int ub_checkpoint_load(UbEngine* e, const void* buf, long size) {
+    UB_TRY
+    e->eng->checkpoint_load(static_cast<const char*>(buf), (size_t)size);
+    return 0;
+    UB_CATCH
+}
 int ub_md_run(UbEngine* e, long n_round) { UB_TRY e->eng->md_run(n_round); return 0; UB_CATCH }
 int ub_sync(UbEngine* e) { UB_TRY e->eng->sync_and_check(); return 0; UB_CATCH }
 int ub_mc_n_samplers(UbEngine* e) { return e->eng->mc_n_samplers(); }

@@ -542,6 +542,61 @@ void Engine::md_run(long n_round) {
     UB_CUDA(cudaGetLastError());
 }
 
+// ---- checkpoint ------------------------------------------------------------------------------------------------------------
+namespace {
+struct CheckpointHeader {
+    char magic[8];            // "UBCKPT1\0"
+    int32_t n_rep, n_atom, thermostat_interval, reserved;
+    float dt, thermostat_timescale;
+    uint64_t n_thermostat_invocations, round_num;
+};
+}
+std::vector<char> Engine::checkpoint_save() {
+    UB_CUDA(cudaSetDevice(device));
+    if (!seed.p) throw std::string("md_init must be called before a checkpoint is taken");
+    sync_and_check();
+    CheckpointHeader h{};
+    memcpy(h.magic, "UBCKPT1", 8);
+    h.n_rep = n_rep; h.n_atom = n_atom; h.thermostat_interval = thermostat_interval;
+    h.dt = dt; h.thermostat_timescale = thermostat_timescale;
+    h.n_thermostat_invocations = n_thermostat_invocations; h.round_num = round_num;
+    const size_t n3 = size_t(n_rep) * n_atom * 3;
+    std::vector<char> blob(sizeof(h) + sizeof(float) * (2 * n3 + n_rep) + sizeof(uint32_t) * n_rep);
+    char* p = blob.data();
+    memcpy(p, &h, sizeof(h)); p += sizeof(h);
+    get_pos(reinterpret_cast<float*>(p)); p += sizeof(float) * n3;
+    get_mom(reinterpret_cast<float*>(p)); p += sizeof(float) * n3;
+    memcpy(p, h_temperature.data(), sizeof(float) * n_rep); p += sizeof(float) * n_rep;
+    memcpy(p, h_seed.data(), sizeof(uint32_t) * n_rep);
+    return blob;
+}
+void Engine::checkpoint_load(const char* data, size_t size) {
+    UB_CUDA(cudaSetDevice(device));
+    CheckpointHeader h;
+    if (size < sizeof(h)) throw std::string("checkpoint too small");
+    memcpy(&h, data, sizeof(h));
+    if (memcmp(h.magic, "UBCKPT1", 8)) throw std::string("not a checkpoint of this engine");
+    if (h.n_rep != n_rep || h.n_atom != n_atom)
+        throw "checkpoint holds " + std::to_string(h.n_rep) + " replicas of " + std::to_string(h.n_atom) + " atoms, the engine " +
+            std::to_string(n_rep) + " of " + std::to_string(n_atom);
+    const size_t n3 = size_t(n_rep) * n_atom * 3;
+    if (size != sizeof(h) + sizeof(float) * (2 * n3 + n_rep) + sizeof(uint32_t) * n_rep) throw std::string("checkpoint size mismatch");
+    const char* p = data + sizeof(h);
+    const float* pos_in = reinterpret_cast<const float*>(p); p += sizeof(float) * n3;
+    const float* mom_in = reinterpret_cast<const float*>(p); p += sizeof(float) * n3;
+    std::vector<float> T(n_rep);
+    memcpy(T.data(), p, sizeof(float) * n_rep); p += sizeof(float) * n_rep;
+    std::vector<uint32_t> seeds(n_rep);
+    memcpy(seeds.data(), p, sizeof(uint32_t) * n_rep);
+    md_init_seeds(seeds.data(), T.data(), h.dt, h.thermostat_timescale, h.thermostat_interval);   // (draws momenta: overwritten below)
+    set_pos(pos_in);
+    set_mom(mom_in);
+    n_thermostat_invocations = h.n_thermostat_invocations;
+    round_num = h.round_num;
+    const unsigned long long inv = h.n_thermostat_invocations;
+    UB_CUDA(cudaMemcpy(d_invocation.p, &inv, sizeof(inv), cudaMemcpyHostToDevice));
+}
+
 __global__ void k_recenter(float* __restrict__ pos, int n_atom, int xy_only) {
     __shared__ float sc[32];
     __shared__ float ctr[3];

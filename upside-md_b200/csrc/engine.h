@@ -277,6 +277,13 @@ struct Engine {
     void swap_pos(const std::vector<int>& pairs);   // pairs = (a0,b0,a1,b1,...): exchange coordinates of replicas a_k and b_k
     std::vector<float> kinetic_energy();
 
+    // Checkpoint of the MD state: positions, momenta, per-replica RNG keys and temperatures, the thermostat invocation
+    // counter and the round number (the counter-based random stream resumes exactly where it stopped), integrator settings.
+    // The reference has no such thing: its continue_sim (py/run_upside.py:231-257) restarts from the last logged frame with
+    // freshly drawn momenta.  A blob restores into an engine of the same configuration and batch size.
+    std::vector<char> checkpoint_save();
+    void checkpoint_load(const char* data, size_t size);
+
     // Monte-Carlo moves (reference monte_carlo_sampler.cpp; main.cpp:545,630-631): samplers read from the /input group of a
     // configuration (pivot_moves, jump_moves); one execute = one Metropolis step of every sampler for every replica, with
     // the replica's md_init seed and current temperature

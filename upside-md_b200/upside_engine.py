@@ -71,6 +71,10 @@ def lib():
     L.ub_md_init.argtypes = [ct.c_void_p, ct.c_uint32, _fp, ct.c_float, ct.c_float, ct.c_int]
     L.ub_md_set_temperature.argtypes = [ct.c_void_p, _fp]
     L.ub_md_run.argtypes = [ct.c_void_p, ct.c_long]
+    L.ub_checkpoint_size.restype = ct.c_long
+    L.ub_checkpoint_size.argtypes = [ct.c_void_p]
+    L.ub_checkpoint_save.argtypes = [ct.c_void_p, ct.c_void_p, ct.c_long, ct.POINTER(ct.c_long)]
+    L.ub_checkpoint_load.argtypes = [ct.c_void_p, ct.c_void_p, ct.c_long]
     L.ub_sync.argtypes = [ct.c_void_p]
     L.ub_mc_n_samplers.argtypes = [ct.c_void_p]
     L.ub_mc_sampler_name.argtypes = [ct.c_void_p, ct.c_int, ct.c_char_p, ct.c_int]
@@ -371,6 +375,20 @@ class BatchEngine(object):
         T = np.ascontiguousarray(np.broadcast_to(np.asarray(temperature, dtype='f4'), (self.n_replica,)))
         if self.L.ub_md_set_temperature(self.e, _f(T)): raise _err('md_set_temperature')
 
+    def checkpoint(self):
+        """bytes holding positions, momenta, RNG keys and counters, temperatures and integrator settings of every replica"""
+        n = self.L.ub_checkpoint_size(self.e)
+        buf = ct.create_string_buffer(n)
+        w = ct.c_long()
+        if self.L.ub_checkpoint_save(self.e, buf, n, ct.byref(w)):
+            raise _err('checkpoint_save')
+        return buf.raw[:w.value]
+
+    def restore(self, blob):
+        """resume from checkpoint(): the run continues with the thermostat noise of the uninterrupted run"""
+        if self.L.ub_checkpoint_load(self.e, blob, len(blob)):
+            raise _err('checkpoint_load')
+
     def md_run(self, n_round, sync=True):
         if self.L.ub_md_run(self.e, int(n_round)): raise _err('md_run')
         if sync:
@@ -522,6 +540,25 @@ def in_process_upside(args, verbose=True):
     retcode = lib().upside_main(len(exec_args), arr, int(verbose))
     if retcode:
         raise RuntimeError('In process Upside returned %i' % retcode)
+
+
+def continue_config(config_file_path):
+    """Prepare a finished run for continuation as the reference's continue_sim does (py/run_upside.py:231-257): the last
+    frame of /output/pos becomes /input/pos and /output is renamed /output_previous_<i>.  Returns the last logged
+    temperature, to be passed to the next run (the momenta are drawn afresh, as in the reference; for an exact
+    continuation inside one process use BatchEngine.checkpoint / restore)."""
+    t = h5lite.load(str(config_file_path))
+    i = 0
+    while 'output_previous_%i' % i in t:
+        i += 1
+    n = t['output'] if 'output' in t else t['output_previous_%i' % (i - 1)]
+    pos = np.asarray(n['pos'].data)                    # (n_frame, 1, n_atom, 3)
+    t['input/pos'].data[:, :, 0] = pos[-1, 0]
+    temperature = float(np.asarray(n['temperature'].data)[-1, 0])
+    if 'output' in t:
+        t.children['output_previous_%i' % i] = t.children.pop('output')
+    h5lite.save(t, str(config_file_path))
+    return temperature
 
 
 def clamped_spline_value(bspline_coeff, x):
