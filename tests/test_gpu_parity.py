@@ -47,11 +47,38 @@ def _check_report(rep):
 
 
 @pytest.mark.skipif(not ref_engine.available('pinned'), reason='oracle/_ref not shipped')
-@pytest.mark.parametrize('cid,n_rep', [(1, 4), (2, 2), (3, 3), (4, 2), (5, 2), (6, 3)])
+@pytest.mark.parametrize('cid,n_rep', [(1, 4), (2, 2), (3, 3), (4, 2), (5, 2), (6, 3), (8, 3)])
 def test_every_node_matches_oracle(cid, n_rep):
     cfg = parity.CONFIGS[cid]
     pos = parity.test_positions(cfg, n_rep + 1)[1:]     # relaxed structures (see DESIGN.md on /input/pos itself)
     _check_report(parity.compare_engines(cfg, pos, verbose=False))
+
+
+def test_radial_pair_lists_are_the_reference_predicate():
+    """radial / hbond_sc_radial (src/sidechain_radial.cpp:16-136; energies, forces and node potentials of config 8 are compared
+    with the oracle in test_every_node_matches_oracle): their pair lists equal the reference's predicate and emission order
+    (oracle/restate.py) applied to the engine's own node outputs; cutoff = the largest (16-2-1e-6)/inv_dx over the type pairs"""
+    cfg = parity.CONFIGS[8]
+    pot = h5lite.load(cfg)['input/potential']
+    pos = parity.test_positions(cfg, 3)[1:]
+    be = ue.BatchEngine(cfg, len(pos))
+    be.evaluate(pos)
+    for name, sym in (('radial', True), ('hbond_sc_radial', False)):
+        g = pot[name]
+        args = [parity._s(x) for x in g.attrs['arguments']]
+        prm = np.asarray(g['interaction_param'].data, dtype='f4')
+        cutoff = np.float32(((16 - 2 - 1e-6) / prm[..., 0].astype('f8')).max())
+        i1, id1 = (g['index'].data, g['id'].data) if sym else (g['index1'].data, g['id1'].data)
+        i2, id2 = (i1, id1) if sym else (g['index2'].data, g['id2'].data)
+        n_edge = 0
+        for r in range(len(pos)):
+            o1, o2 = be.get_output(args[0], r), be.get_output(args[-1], r)
+            want = restate.pairlist(o1[i1][:, :3], id1, o2[i2][:, :3], id2, cutoff, 'seq2', sym)
+            got = be.pairlist(name, r)
+            assert got.shape == want.shape and (got == want).all(), name
+            n_edge += len(got)
+        assert n_edge > 0, name
+    be.close()
 
 
 @pytest.mark.parametrize('cid', [1, 2, 3, 5])

@@ -55,6 +55,35 @@ def main():
     w.save(path)
     print(path, os.path.getsize(path))
 
+    # config 8: radial + hbond_sc_radial pair nodes (src/sidechain_radial.cpp:16-136) on top of config 1.  Synthetic tables
+    # that obey RadialHelper's four conditions (p[0] = 1/dx, p[1] == p[3], p[-3] == p[-1], zero at the cutoff)
+    w = config.ConfigWriter.from_file(os.path.join(ROOT, 'configs', 'config1_20res.up'))
+    names = list(config.restypes)
+
+    def radial_table(n1, n2, symmetric, seed):
+        r = np.random.default_rng(seed)
+        p = np.zeros((n1, n2, 17), dtype='f4')
+        for a in range(n1):
+            for b in range(a if symmetric else 0, n2):
+                knots = np.zeros(16)
+                depth, width = r.uniform(0.2, 1.2), r.uniform(1.5, 3.0)
+                x = np.arange(16) - 1.0
+                knots[:] = 3.0 * np.exp(-x / 1.5) - depth * np.exp(-((x - 9.0) / width) ** 2)
+                knots[-3:] = 0.0                      # continuity at the cutoff and terminal clamp
+                knots[-4] *= 0.3
+                knots[0] = knots[2]                   # origin clamp
+                inv_dx = r.choice([2.0, 2.5])         # cutoffs of 7 and 5.6 Angstrom: the graph takes the largest
+                p[a, b, 0] = inv_dx
+                p[a, b, 1:] = knots
+                if symmetric:
+                    p[b, a] = p[a, b]
+        return p
+    w.write_sidechain_radial(radial_table(20, 20, True, 81), names)
+    w.write_hbond_sc_radial(radial_table(2, 20, False, 82), names)
+    path = os.path.join(ROOT, 'configs', 'config8_radial_20res.up')
+    w.save(path)
+    print(path, os.path.getsize(path))
+
 
 if __name__ == '__main__':
     main()

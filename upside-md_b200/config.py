@@ -547,6 +547,34 @@ class ConfigWriter:
         self.arr(g, 'pivot_range', np.column_stack((pivot_atom[nonterm][:, 4] + 1,
                                                     np.zeros(nonterm.sum(), 'i') + self.n_atom)))
 
+    def write_sidechain_radial(self, interaction_param, restype_names, excluded_residues=(), argument='placement_fixed_point_vector_only_CB',
+                               suffix=''):
+        """upside_config.py:866-883 (--sidechain-radial): a radial pair potential between one point per residue;
+        interaction_param (n_type, n_type, 17) = 1/dx then 16 clamped B-spline knots per residue-type pair"""
+        name2type = dict((_s(x), i) for i, x in enumerate(restype_names))
+        residues = sorted(set(range(self.n_res)).difference(excluded_residues))
+        g = self.group('radial' + suffix, [argument])
+        self.arr(g, 'index', np.array(residues, dtype='i'))
+        self.arr(g, 'type', np.array([name2type[self.fasta[r]] for r in residues], dtype='i'))
+        self.arr(g, 'id', np.array(residues, dtype='i'))
+        self.arr(g, 'interaction_param', np.asarray(interaction_param, dtype='f4'))
+
+    def write_hbond_sc_radial(self, interaction_param, restype_names, argument='placement_fixed_point_vector_only_CB'):
+        """the two-group radial node of src/sidechain_radial.cpp:108-136 (registered as hbond_sc_radial; the reference's
+        config generator has no writer for it): backbone H / O virtual sites of protein_hbond (types 0 / 1) against one point
+        per residue; interaction_param (2, n_type, 17)"""
+        name2type = dict((_s(x), i) for i, x in enumerate(restype_names))
+        ph = self.potential['protein_hbond']
+        don, acc = np.asarray(ph['id1'].data), np.asarray(ph['id2'].data)
+        g = self.group('hbond_sc_radial', ['protein_hbond', argument])
+        self.arr(g, 'index1', np.arange(len(don) + len(acc), dtype='i'))
+        self.arr(g, 'type1', np.array([0] * len(don) + [1] * len(acc), dtype='i'))
+        self.arr(g, 'id1', np.concatenate([don, acc]).astype('i'))
+        self.arr(g, 'index2', np.arange(self.n_res, dtype='i'))
+        self.arr(g, 'type2', np.array([name2type[x] for x in self.fasta], dtype='i'))
+        self.arr(g, 'id2', np.arange(self.n_res, dtype='i'))
+        self.arr(g, 'interaction_param', np.asarray(interaction_param, dtype='f4'))
+
     def write_jump_moves(self, atom_ranges, sigma_trans, sigma_rot):
         """/input/jump_moves as JumpSampler reads it (src/monte_carlo_sampler.cpp:174-201): rigid translations (sigma_trans,
         Angstrom) and rotations about the centre of mass (sigma_rot, radians) of the atom ranges [first, next_first)"""

@@ -265,6 +265,96 @@ __global__ void k_protein_hbond_deriv(IGraphDev g, const float* __restrict__ out
     atomicAdd(dst, make_float4(acc[0], acc[1], acc[2], acc[3]));
     atomicAdd(dst + 1, make_float4(acc[4], acc[5], 0.f, 0.f));
 }
+// ================================================================================================ radial / hbond_sc_radial
+// RadialHelper (sidechain_radial.cpp:16-79): clamped cubic B-spline of the distance, 16 knots behind p[0] = 1/dx per type
+// pair; exclusion |id1-id2| <= 2; SidechainRadialPairs (:83-105, one group, symmetric) and HBondSidechainRadialPairs
+// (:108-136, two groups).  Gather form: one thread per element walks its ELL row, keeps its own half of every pair's force
+// in registers (a symmetric graph lists every pair in both rows; an asymmetric one is walked from both tables) and adds it
+// to the element's sens row once; the energy counts every pair once.
+constexpr int RADIAL_KNOT = 16;
+__device__ __forceinline__ float radial_edge(const float* __restrict__ p, f3 x1, f3 x2, f3& d1) {
+    const float inv_dx = p[0];
+    const f3 disp = x1 - x2;
+    const float dist2 = mag2(disp);
+    const float inv_dist = rsqrtf(dist2 + 1e-7f);   // 1e-7 is divergence protection (sidechain_radial.cpp:54)
+    const float dist_coord = dist2 * (inv_dist * inv_dx);
+    float v, dv;
+    clamped_deboor_vd(p + 1, RADIAL_KNOT, dist_coord, v, dv);
+    d1 = (inv_dist * inv_dx * dv) * disp;
+    return v;
+}
+// second = 0: elements of group 1 over nbr1; second = 1: elements of group 2 over nbr2 (asymmetric graphs only)
+__global__ void k_radial(IGraphDev g, int second, int want_pot, float* __restrict__ potential) {
+    const int r = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+    const IGraphSide& mine = second ? g.s2 : g.s1;
+    const IGraphSide& other = second ? g.s1 : g.s2;
+    float e = 0.f;
+    if (i < mine.n) {
+        const int cnt = second ? g.cnt2[size_t(r) * mine.n + i] : g.cnt1[size_t(r) * mine.n + i];
+        const unsigned short* row = second ? g.nbr2 + (size_t(r) * mine.n + i) * g.K2 : g.nbr1 + (size_t(r) * mine.n + i) * g.K1;
+        const f3 xi = ld3(elem_ptr(mine, r, i));
+        const int ti = mine.type[i];
+        f3 acc = mk3(0.f, 0.f, 0.f);
+        for (int k = 0; k < cnt; ++k) {
+            const int j = row[k];
+            const f3 xj = ld3(elem_ptr(other, r, j));
+            const int tj = other.type[j];
+            const int t1 = second ? tj : ti, t2 = second ? ti : tj;
+            f3 d1;
+            // operands in (group 1, group 2) order - for a symmetric graph (lower index, higher index), the reference's edge
+            const bool first = second ? false : (g.symmetric ? i < j : true);
+            const float v = first ? radial_edge(g.param + size_t(t1 * g.n_type2 + t2) * g.n_param, xi, xj, d1)
+                                  : radial_edge(g.param + size_t(t1 * g.n_type2 + t2) * g.n_param, xj, xi, d1);
+            acc += first ? d1 : -d1;
+            if (first) e += v;   // every pair counted once
+        }
+        if (cnt) atomic_add3(elem_sens_ptr(mine, r, i), acc);
+    }
+    if (want_pot && !second) {
+        e = warp_sum(e);
+        if ((threadIdx.x & 31) == 0 && e != 0.f) atomicAdd(potential + r, e);
+    }
+}
+template <bool SYM> struct RadialPairs : PotentialNode {
+    IGraphHost ig;
+    RadialPairs(Engine&, const h5l::Node& g, CoordNode& a) : ig(g, true, EXCL_SEQ2, 3, 3, &a, nullptr) { init(); }
+    RadialPairs(Engine&, const h5l::Node& g, CoordNode& a, CoordNode& b) : ig(g, false, EXCL_SEQ2, 3, 3, &a, &b) { init(); }
+    void init() {
+        if (ig.n_param != 1 + RADIAL_KNOT) throw "radial interaction expects " + std::to_string(1 + RADIAL_KNOT) + " parameters per type pair";
+        update_cutoff();
+    }
+    void update_cutoff() {   // update_cutoffs (interaction_graph.h:383-398) with RadialHelper::cutoff (sidechain_radial.cpp:33-36)
+        float c = 0.f;
+        for (int t1 = 0; t1 < ig.n_type1; ++t1)
+            for (int t2 = 0; t2 < ig.n_type2; ++t2) {
+                const float* p = &ig.h_param[size_t(t1 * ig.n_type2 + t2) * ig.n_param];
+                c = std::max(c, float((RADIAL_KNOT - 2 - 1e-6) / p[0]));
+                if (SYM)
+                    for (int k = 0; k < ig.n_param; ++k)
+                        if (p[k] != ig.h_param[size_t(t2 * ig.n_type2 + t1) * ig.n_param + k]) throw std::string("incompatible parameters");
+            }
+        ig.cutoff = c;
+    }
+    void finalize() override { ig.allocate(engine); }
+    void compute_value(cudaStream_t s, ComputeMode mode) override {
+        if (!ig.n1 || !ig.n2) return;
+        ig.build(s);
+        const int want = mode == PotentialAndDerivMode;
+        k_radial<<<dim3((ig.n1 + TPB - 1) / TPB, engine->n_rep), TPB, 0, s>>>(ig.dev(), 0, want, potential);
+        if (!SYM) k_radial<<<dim3((ig.n2 + TPB - 1) / TPB, engine->n_rep), TPB, 0, s>>>(ig.dev(), 1, want, potential);
+    }
+    bool get_pairlist(int replica, std::vector<int>& i1, std::vector<int>& i2) override { return ig.pairlist(replica, i1, i2); }
+    std::vector<float> get_param() const override { return ig.h_param; }
+    void set_param(const std::vector<float>& p) override {   // the cutoff follows the parameters; the tables keep their capacity
+        const float old = ig.cutoff;
+        ig.set_param(p);
+        update_cutoff();
+        if (ig.cutoff > old) { ig.cutoff = old; throw std::string("radial: new parameters enlarge the cutoff beyond the allocated pair-list capacity"); }
+    }
+};
+typedef RadialPairs<true> SidechainRadialPairs;
+typedef RadialPairs<false> HBondSidechainRadialPairs;
+
 struct ProteinHBond : CoordNode {
     CoordNode& infer;
     IGraphHost ig;
@@ -301,6 +391,8 @@ struct ProteinHBond : CoordNode {
     }
 };
 RegisterNodeType<ProteinHBond, 1> protein_hbond_node("protein_hbond");
+RegisterNodeType<SidechainRadialPairs, 1> radial_node("radial");                         // sidechain_radial.cpp:209
+RegisterNodeType<HBondSidechainRadialPairs, 2> hbond_sc_radial_node("hbond_sc_radial");   // sidechain_radial.cpp:210
 
 }  // namespace
 }  // namespace ub
