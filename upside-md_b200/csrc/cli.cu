@@ -23,6 +23,7 @@
 
 #include "../../include/engine_c_library.h"
 #include "engine.h"
+#include "ladder_nccl.h"
 #include "replica_exchange.h"
 
 namespace {
@@ -145,6 +146,8 @@ struct Group {   // configuration files that share one batched engine
     vector<int> systems;   // slot r of the engine = system systems[r]
     const h5l::Node* potential = nullptr;
     int n_atom = 0;
+    int device = 0;    // GPU of this engine
+    int origin = -1;   // index of the potential the group was split from (UPSIDE_B200_DEVICES)
 };
 struct System {
     string path;
@@ -290,8 +293,35 @@ int run(int argc, const char* const* argv, int verbose) {
         groups[sys.group].systems.push_back(ns);
         if (verbose) printf("%s\nn_atom %i\n\n", sys.path.c_str(), sys.n_atom);
     }
+    // UPSIDE_B200_DEVICES=D: the systems of a group are dealt to D GPUs in contiguous blocks, one batched engine per device.
+    // All engines advance concurrently (every call below only enqueues on its engine's stream); a ladder over one
+    // Hamiltonian then exchanges on the devices over NCCL (csrc/ladder_nccl.cu), everything else goes through the host.
+    int n_device = 1;
+    if (const char* d = getenv("UPSIDE_B200_DEVICES")) {
+        int have = 0;
+        cudaGetDeviceCount(&have);
+        n_device = std::max(1, std::min(atoi(d), have));
+    }
+    for (size_t g = 0; g < groups.size(); ++g) groups[g].origin = (int)g;
+    if (n_device > 1) {
+        vector<Group> split;
+        for (auto& g : groups) {
+            const int n = (int)g.systems.size(), D = std::min(n_device, n);
+            for (int d = 0; d < D; ++d) {
+                const int lo = d * (n / D) + std::min(d, n % D), cnt = n / D + (d < n % D ? 1 : 0);
+                split.emplace_back();
+                Group& s = split.back();
+                s.potential = g.potential; s.n_atom = g.n_atom; s.device = d; s.origin = g.origin;
+                s.systems.assign(g.systems.begin() + lo, g.systems.begin() + lo + cnt);
+            }
+        }
+        groups = std::move(split);
+        for (size_t g = 0; g < groups.size(); ++g)
+            for (size_t r = 0; r < groups[g].systems.size(); ++r) { systems[groups[g].systems[r]].group = (int)g; systems[groups[g].systems[r]].slot = (int)r; }
+        if (verbose) printf("%i systems on %i devices\n", n_system, n_device);
+    }
     for (auto& g : groups) {
-        g.engine = ub::initialize_engine_from_hdf5(g.n_atom, *g.potential, (int)g.systems.size(), 0);
+        g.engine = ub::initialize_engine_from_hdf5(g.n_atom, *g.potential, (int)g.systems.size(), g.device);
         for (const auto& p : set_param_map) g.engine->get(p.first).set_param(p.second);
         if (log_level > 0)
             for (auto& n : g.engine->nodes) {
@@ -380,6 +410,43 @@ int run(int argc, const char* const* argv, int verbose) {
         for (auto& sys : systems)
             if (sys.n_atom != systems[0].n_atom) throw string("Replica exchange requires all systems have the same number of atoms");
     }
+    // A ladder whose rungs all share one Hamiltonian and sit in equal contiguous blocks, one per engine, exchanges on the
+    // devices: one evaluation per attempt instead of two per swap set, energies all-gathered and boundary coordinates sent
+    // over NCCL, no host synchronisation (csrc/ladder_nccl.cu).  Annealing changes the temperatures: host path.
+    vector<void*> ladder_comms;
+    struct CommGuard { vector<void*>& v; ~CommGuard() { for (void* c : v) ub::nccl_comm_destroy(c); } } comm_guard{ladder_comms};
+    vector<std::unique_ptr<ub::Ladder>> ladders;   // (destroyed before the communicators)
+    if (replex && !getenv("UPSIDE_B200_HOST_REPLEX") && anneal_factor == 1.) {
+        bool ok = true;
+        for (size_t g = 0; g < groups.size(); ++g) {
+            ok = ok && groups[g].origin == groups[0].origin && groups[g].systems.size() == groups[0].systems.size();
+            for (size_t r = 0; r < groups[g].systems.size() && ok; ++r) ok = groups[g].systems[r] == int(g * groups[0].systems.size() + r);
+        }
+        if (ok) {
+            vector<float> T(n_system);
+            for (int ns = 0; ns < n_system; ++ns) T[ns] = systems[ns].temperature;
+            if (groups.size() > 1) {
+                vector<int> devs;
+                for (auto& g : groups) devs.push_back(g.device);
+                ladder_comms = ub::nccl_comm_init_all(devs);
+            }
+            for (size_t g = 0; g < groups.size(); ++g)
+                ladders.emplace_back(new ub::Ladder(groups[g].engine.get(), ladder_comms.empty() ? nullptr : ladder_comms[g], (int)g,
+                                                    (int)groups.size(), n_system, args.swap_sets, base_random_seed, T.data()));
+            if (verbose) printf("replica exchange on the device%s\n", groups.size() > 1 ? "s, over NCCL" : "");
+        }
+    }
+    // host copy of the exchange bookkeeping (replica indices, attempt / success counters) for the frame logger
+    auto pull_ladder_state = [&]() {
+        if (ladders.empty()) return;
+        vector<int> ri;
+        vector<unsigned long long> cnt;
+        ladders[0]->download(&ri, nullptr, &cnt, nullptr);
+        replex->replica_indices = ri;
+        size_t k = 0;
+        for (auto& set : replex->swap_sets)
+            for (auto& sp : set) { sp.n_attempt = cnt[2 * k]; sp.n_success = cnt[2 * k + 1]; ++k; }
+    };
     if (verbose) {
         printf("\n");
         for (int ns = 0; ns < n_system; ++ns) printf("%i %.2f\n", ns, systems[ns].temperature);
@@ -414,6 +481,12 @@ int run(int argc, const char* const* argv, int verbose) {
         groups[b.group].engine->set_pos(pa.data(), b.slot, 1);
     };
     auto attempt_swaps = [&](uint32_t seed, uint64_t round) {   // main.cpp:227-275
+        if (!ladders.empty()) {
+            vector<ub::Ladder*> all;
+            for (auto& l : ladders) all.push_back(l.get());
+            ub::Ladder::attempt_all(all, round);
+            return;
+        }
         vector<float> beta(n_system), old_l(n_system), new_l(n_system);
         for (int i = 0; i < n_system; ++i) beta[i] = 1.f / systems[i].temperature;
         ub::HostRandomGenerator random(seed, ub::REPLICA_EXCHANGE_RANDOM_STREAM, 0u, round);
@@ -431,6 +504,7 @@ int run(int argc, const char* const* argv, int verbose) {
     };
 
     auto log_frame = [&](uint64_t nr) {
+        pull_ladder_state();
         for (auto& g : groups) {
             if (do_recenter) g.engine->recenter(xy_recenter_only);
             g.engine->compute(ub::PotentialAndDerivMode);
@@ -499,7 +573,10 @@ int run(int argc, const char* const* argv, int verbose) {
     uint64_t nr = 0, last_start = 0;
     // a failure inside the loop (pair-list capacity, CUDA error) must not lose the frames already sampled: they are
     // written before the error propagates (the reference's H5Logger flushes as it goes)
-    auto flush_all = [&]() { for (int ns = 0; ns < n_system; ++ns) write_output(systems[ns], invocation, bool(replex), replex.get(), ns); };
+    auto flush_all = [&]() {
+        try { pull_ladder_state(); } catch (...) {}
+        for (int ns = 0; ns < n_system; ++ns) write_output(systems[ns], invocation, bool(replex), replex.get(), ns);
+    };
     try {
     while (nr < n_round && !received_signal) {
         // no pivot at t=0, so that a partially strained system may relax first (main.cpp:628-631)

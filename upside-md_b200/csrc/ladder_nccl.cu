@@ -25,8 +25,7 @@
 #include <vector>
 
 #include "../../include/upside_b200.h"
-#include "engine.h"
-#include "replica_exchange.h"
+#include "ladder_nccl.h"
 #include "rng.cuh"
 
 namespace ub {
@@ -136,124 +135,153 @@ __global__ void k_ladder_apply(float* __restrict__ pos, int n_atom, int n_local_
     }
 }
 
-struct Ladder {
-    Engine* e;
-    ncclComm_t comm;
-    int rank, world, n_global, n_local, first;
-    uint32_t seed;
-    ReplicaExchangePlan plan;          // parsing + validation of the swap sets (main.cpp:130-191)
-    int n_set, n_pair_total;
-    std::vector<int> h_set_start;
-    DevBuf<int> set_start, pairs, accept, replica_index;
-    DevBuf<unsigned long long> counts;
-    DevBuf<float> beta, energy_all, energy_work, sendbuf, recvbuf;
-    struct SetPlan {
-        int n_local_pair = 0, local_offset = 0, n_cross = 0, cross_offset = 0;
-        std::vector<int> h_partner;   // partner rank of each boundary pair of this rank
-    };
-    std::vector<SetPlan> sets;
-    DevBuf<int> local_pairs, cross_slot, cross_k;   // all sets, concatenated
-
-    Ladder(Engine* e_, void* comm_, int rank_, int world_, int n_global_, const std::vector<std::string>& swap_sets, uint32_t seed_,
-           const float* temperature_all)
-        : e(e_), comm((ncclComm_t)comm_), rank(rank_), world(world_), n_global(n_global_), seed(seed_), plan(n_global_, swap_sets) {
-        if (world < 1 || rank < 0 || rank >= world) throw std::string("invalid rank / world size");
-        if (n_global % world) throw std::string("the ladder must divide evenly over the ranks (n_global % world != 0)");
-        if (world > 1 && !comm) throw std::string("a ladder sharded over several ranks needs an NCCL communicator");
-        n_local = n_global / world;
-        first = rank * n_local;
-        if (e->n_rep != n_local) throw "the engine holds " + std::to_string(e->n_rep) + " replicas but this rank owns " + std::to_string(n_local) + " rungs";
-        UB_CUDA(cudaSetDevice(e->device));
-        n_set = (int)plan.swap_sets.size();
-        std::vector<int> h_pairs, h_cross_slot, h_cross_k, lp;
-        h_set_start.push_back(0);
-        sets.resize(n_set);
-        for (int s = 0; s < n_set; ++s) {
-            sets[s].local_offset = (int)lp.size();
-            sets[s].cross_offset = (int)h_cross_slot.size();
-            for (auto& sp : plan.swap_sets[s]) {
-                const int k = (int)h_pairs.size() / 2;
-                h_pairs.push_back(sp.sys1);
-                h_pairs.push_back(sp.sys2);
-                const int r1 = sp.sys1 / n_local, r2 = sp.sys2 / n_local;
-                if (r1 == rank && r2 == rank) { lp.push_back(sp.sys1 - first); lp.push_back(sp.sys2 - first); lp.push_back(k); }
-                else if (r1 == rank || r2 == rank) {
-                    h_cross_slot.push_back((r1 == rank ? sp.sys1 : sp.sys2) - first);
-                    h_cross_k.push_back(k);
-                    sets[s].h_partner.push_back(r1 == rank ? r2 : r1);
-                }
+Ladder::Ladder(Engine* e_, void* comm_, int rank_, int world_, int n_global_, const std::vector<std::string>& swap_sets, uint32_t seed_,
+               const float* temperature_all)
+    : e(e_), comm(comm_), rank(rank_), world(world_), n_global(n_global_), seed(seed_), plan(n_global_, swap_sets) {
+    if (world < 1 || rank < 0 || rank >= world) throw std::string("invalid rank / world size");
+    if (n_global % world) throw std::string("the ladder must divide evenly over the ranks (n_global % world != 0)");
+    if (world > 1 && !comm) throw std::string("a ladder sharded over several ranks needs an NCCL communicator");
+    n_local = n_global / world;
+    first = rank * n_local;
+    if (e->n_rep != n_local) throw "the engine holds " + std::to_string(e->n_rep) + " replicas but this rank owns " + std::to_string(n_local) + " rungs";
+    UB_CUDA(cudaSetDevice(e->device));
+    n_set = (int)plan.swap_sets.size();
+    std::vector<int> h_pairs, h_cross_slot, h_cross_k, lp;
+    h_set_start.push_back(0);
+    sets.resize(n_set);
+    for (int s = 0; s < n_set; ++s) {
+        sets[s].local_offset = (int)lp.size();
+        sets[s].cross_offset = (int)h_cross_slot.size();
+        for (auto& sp : plan.swap_sets[s]) {
+            const int k = (int)h_pairs.size() / 2;
+            h_pairs.push_back(sp.sys1);
+            h_pairs.push_back(sp.sys2);
+            const int r1 = sp.sys1 / n_local, r2 = sp.sys2 / n_local;
+            if (r1 == rank && r2 == rank) { lp.push_back(sp.sys1 - first); lp.push_back(sp.sys2 - first); lp.push_back(k); }
+            else if (r1 == rank || r2 == rank) {
+                h_cross_slot.push_back((r1 == rank ? sp.sys1 : sp.sys2) - first);
+                h_cross_k.push_back(k);
+                sets[s].h_partner.push_back(r1 == rank ? r2 : r1);
             }
-            h_set_start.push_back((int)h_pairs.size() / 2);
-            sets[s].n_local_pair = ((int)lp.size() - sets[s].local_offset) / 3;
-            sets[s].n_cross = (int)sets[s].h_partner.size();
         }
-        if (lp.empty()) lp.push_back(0);
-        local_pairs.upload(lp);
-        n_pair_total = (int)h_pairs.size() / 2;
-        if (h_pairs.empty()) h_pairs.push_back(0);
-        set_start.upload(h_set_start);
-        pairs.upload(h_pairs);
-        accept.alloc(std::max(1, n_pair_total));
-        counts.alloc(std::max(1, 2 * n_pair_total));
-        std::vector<int> ri(n_global);
-        for (int i = 0; i < n_global; ++i) ri[i] = i;
-        replica_index.upload(ri);
-        std::vector<float> b(n_global);
-        for (int i = 0; i < n_global; ++i) b[i] = 1.f / temperature_all[i];
-        beta.upload(b);
-        energy_all.alloc(n_global);
-        energy_work.alloc(n_global);
-        const size_t n_cross_all = std::max<size_t>(1, h_cross_slot.size());
-        if (h_cross_slot.empty()) { h_cross_slot.push_back(0); h_cross_k.push_back(0); }
-        cross_slot.upload(h_cross_slot);
-        cross_k.upload(h_cross_k);
-        sendbuf.alloc(n_cross_all * e->n_atom * 4);
-        recvbuf.alloc(n_cross_all * e->n_atom * 4);
+        h_set_start.push_back((int)h_pairs.size() / 2);
+        sets[s].n_local_pair = ((int)lp.size() - sets[s].local_offset) / 3;
+        sets[s].n_cross = (int)sets[s].h_partner.size();
     }
+    if (lp.empty()) lp.push_back(0);
+    local_pairs.upload(lp);
+    n_pair_total = (int)h_pairs.size() / 2;
+    if (h_pairs.empty()) h_pairs.push_back(0);
+    set_start.upload(h_set_start);
+    pairs.upload(h_pairs);
+    accept.alloc(std::max(1, n_pair_total));
+    counts.alloc(std::max(1, 2 * n_pair_total));
+    std::vector<int> ri(n_global);
+    for (int i = 0; i < n_global; ++i) ri[i] = i;
+    replica_index.upload(ri);
+    std::vector<float> b(n_global);
+    for (int i = 0; i < n_global; ++i) b[i] = 1.f / temperature_all[i];
+    beta.upload(b);
+    energy_all.alloc(n_global);
+    energy_work.alloc(n_global);
+    const size_t n_cross_all = std::max<size_t>(1, h_cross_slot.size());
+    if (h_cross_slot.empty()) { h_cross_slot.push_back(0); h_cross_k.push_back(0); }
+    cross_slot.upload(h_cross_slot);
+    cross_k.upload(h_cross_k);
+    sendbuf.alloc(n_cross_all * e->n_atom * 4);
+    recvbuf.alloc(n_cross_all * e->n_atom * 4);
+}
 
-    void set_temperature(const float* temperature_all) {
-        std::vector<float> b(n_global);
-        for (int i = 0; i < n_global; ++i) b[i] = 1.f / temperature_all[i];
-        UB_CUDA(cudaMemcpyAsync(beta.p, b.data(), b.size() * sizeof(float), cudaMemcpyHostToDevice, e->stream));
-        UB_CUDA(cudaStreamSynchronize(e->stream));
+void Ladder::set_temperature(const float* temperature_all) {
+    UB_CUDA(cudaSetDevice(e->device));
+    std::vector<float> b(n_global);
+    for (int i = 0; i < n_global; ++i) b[i] = 1.f / temperature_all[i];
+    UB_CUDA(cudaMemcpyAsync(beta.p, b.data(), b.size() * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    UB_CUDA(cudaStreamSynchronize(e->stream));
+}
+
+void Ladder::comm_bytes(size_t* gather, size_t* coords) const {
+    *gather = world > 1 ? size_t(n_global - n_local) * sizeof(float) : 0;
+    size_t c = 0;
+    for (auto& s : sets) c += size_t(s.n_cross) * e->n_atom * 4 * sizeof(float);
+    *coords = c;
+}
+
+void Ladder::attempt_all(const std::vector<Ladder*>& ranks, unsigned long long round) {
+    if (ranks.empty()) return;
+    const bool many = ranks.size() > 1;   // one host thread drives several devices: NCCL calls go inside group brackets
+    const bool use_nccl = ranks[0]->world > 1;
+    for (Ladder* l : ranks) { UB_CUDA(cudaSetDevice(l->e->device)); l->e->compute(PotentialAndDerivMode); }
+    if (use_nccl) {
+        if (many) UB_NCCL(nccl().GroupStart());
+        for (Ladder* l : ranks)
+            UB_NCCL(nccl().AllGather(l->e->potential.p, l->energy_all.p, l->n_local, ncclFloat, (ncclComm_t)l->comm, l->e->stream));
+        if (many) UB_NCCL(nccl().GroupEnd());
+    } else {
+        Ladder* l = ranks[0];
+        UB_CUDA(cudaMemcpyAsync(l->energy_all.p, l->e->potential.p, l->n_local * sizeof(float), cudaMemcpyDeviceToDevice, l->e->stream));
     }
-
-    // bytes that cross GPUs per attempt on this rank: (all-gather receive, boundary coordinates sent)
-    void comm_bytes(size_t* gather, size_t* coords) const {
-        *gather = world > 1 ? size_t(n_global - n_local) * sizeof(float) : 0;
-        size_t c = 0;
-        for (auto& s : sets) c += size_t(s.n_cross) * e->n_atom * 4 * sizeof(float);
-        *coords = c;
+    for (Ladder* l : ranks) {
+        UB_CUDA(cudaSetDevice(l->e->device));
+        k_ladder_decide<<<1, 32, 0, l->e->stream>>>(l->n_global, l->n_set, l->set_start.p, l->pairs.p, l->beta.p, l->energy_all.p, l->seed, round,
+                                                    l->accept.p, l->counts.p, l->replica_index.p, l->energy_work.p);
     }
-
-    void attempt(unsigned long long round) {
-        UB_CUDA(cudaSetDevice(e->device));
-        cudaStream_t st = e->stream;
-        e->compute(PotentialAndDerivMode);
-        if (world > 1) UB_NCCL(nccl().AllGather(e->potential.p, energy_all.p, n_local, ncclFloat, comm, st));
-        else UB_CUDA(cudaMemcpyAsync(energy_all.p, e->potential.p, n_local * sizeof(float), cudaMemcpyDeviceToDevice, st));
-        k_ladder_decide<<<1, 32, 0, st>>>(n_global, n_set, set_start.p, pairs.p, beta.p, energy_all.p, seed, round, accept.p, counts.p,
-                                          replica_index.p, energy_work.p);
-        const size_t row = size_t(e->n_atom) * 4;
-        for (int s = 0; s < n_set; ++s) {
-            SetPlan& sp = sets[s];
-            if (sp.n_cross) {
-                k_ladder_pack<<<sp.n_cross, 128, 0, st>>>(e->pos->output, e->n_atom, cross_slot.p + sp.cross_offset, sendbuf.p + sp.cross_offset * row);
-                UB_NCCL(nccl().GroupStart());
+    const int n_set = ranks[0]->n_set;
+    for (int s = 0; s < n_set; ++s) {
+        bool any_cross = false;
+        for (Ladder* l : ranks) {
+            SetPlan& sp = l->sets[s];
+            if (!sp.n_cross) continue;
+            any_cross = true;
+            UB_CUDA(cudaSetDevice(l->e->device));
+            const size_t row = size_t(l->e->n_atom) * 4;
+            k_ladder_pack<<<sp.n_cross, 128, 0, l->e->stream>>>(l->e->pos->output, l->e->n_atom, l->cross_slot.p + sp.cross_offset,
+                                                                l->sendbuf.p + sp.cross_offset * row);
+        }
+        if (any_cross) {
+            UB_NCCL(nccl().GroupStart());
+            for (Ladder* l : ranks) {
+                SetPlan& sp = l->sets[s];
+                const size_t row = size_t(l->e->n_atom) * 4;
                 for (int c = 0; c < sp.n_cross; ++c) {
-                    UB_NCCL(nccl().Send(sendbuf.p + (sp.cross_offset + c) * row, row, ncclFloat, sp.h_partner[c], comm, st));
-                    UB_NCCL(nccl().Recv(recvbuf.p + (sp.cross_offset + c) * row, row, ncclFloat, sp.h_partner[c], comm, st));
+                    UB_NCCL(nccl().Send(l->sendbuf.p + (sp.cross_offset + c) * row, row, ncclFloat, sp.h_partner[c], (ncclComm_t)l->comm, l->e->stream));
+                    UB_NCCL(nccl().Recv(l->recvbuf.p + (sp.cross_offset + c) * row, row, ncclFloat, sp.h_partner[c], (ncclComm_t)l->comm, l->e->stream));
                 }
-                UB_NCCL(nccl().GroupEnd());
             }
-            if (sp.n_local_pair + sp.n_cross)
-                k_ladder_apply<<<sp.n_local_pair + sp.n_cross, 128, 0, st>>>(e->pos->output, e->n_atom, sp.n_local_pair, local_pairs.p + sp.local_offset,
-                                                                              cross_slot.p + sp.cross_offset, cross_k.p + sp.cross_offset,
-                                                                              recvbuf.p + sp.cross_offset * row, accept.p);
+            UB_NCCL(nccl().GroupEnd());
         }
-        UB_CUDA(cudaGetLastError());
+        for (Ladder* l : ranks) {
+            SetPlan& sp = l->sets[s];
+            if (!(sp.n_local_pair + sp.n_cross)) continue;
+            UB_CUDA(cudaSetDevice(l->e->device));
+            const size_t row = size_t(l->e->n_atom) * 4;
+            k_ladder_apply<<<sp.n_local_pair + sp.n_cross, 128, 0, l->e->stream>>>(l->e->pos->output, l->e->n_atom, sp.n_local_pair,
+                                                                                   l->local_pairs.p + sp.local_offset, l->cross_slot.p + sp.cross_offset,
+                                                                                   l->cross_k.p + sp.cross_offset, l->recvbuf.p + sp.cross_offset * row,
+                                                                                   l->accept.p);
+            UB_CUDA(cudaGetLastError());
+        }
     }
-};
+}
+
+void Ladder::download(std::vector<int>* replica_indices, std::vector<int>* accept_last, std::vector<unsigned long long>* counts_out,
+                      std::vector<float>* energies) {
+    UB_CUDA(cudaSetDevice(e->device));
+    e->sync_and_check();
+    if (replica_indices) *replica_indices = replica_index.download();
+    if (accept_last) { *accept_last = accept.download(); accept_last->resize(n_pair_total); }
+    if (counts_out) { *counts_out = counts.download(); counts_out->resize(2 * size_t(n_pair_total)); }
+    if (energies) *energies = energy_all.download();
+}
+
+std::vector<void*> nccl_comm_init_all(const std::vector<int>& devices) {
+    std::vector<ncclComm_t> c(devices.size());
+    UB_NCCL(nccl().CommInitAll(c.data(), (int)devices.size(), devices.data()));
+    return std::vector<void*>(c.begin(), c.end());
+}
+void nccl_comm_destroy(void* comm) {
+    try { if (comm) nccl().CommDestroy((ncclComm_t)comm); } catch (...) {}
+}
 
 }  // namespace ub
 
@@ -305,16 +333,13 @@ void* ub_nccl_comm_create(const char* unique_id, int world, int rank, int device
 /* one communicator per device of THIS process (ncclCommInitAll); comms[n_device] */
 int ub_nccl_comm_create_all(int n_device, const int* devices, void** comms) {
     LAD_TRY
-    std::vector<ncclComm_t> c(n_device);
-    UB_NCCL(ub::nccl().CommInitAll(c.data(), n_device, devices));
+    auto c = ub::nccl_comm_init_all(std::vector<int>(devices, devices + n_device));
     for (int i = 0; i < n_device; ++i) comms[i] = c[i];
     return 0;
     LAD_CATCH
 }
 
-void ub_nccl_comm_destroy(void* comm) {
-    try { if (comm) ub::nccl().CommDestroy((ncclComm_t)comm); } catch (...) {}
-}
+void ub_nccl_comm_destroy(void* comm) { ub::nccl_comm_destroy(comm); }
 
 UbLadder* ub_ladder_create(UbEngine* e, void* nccl_comm, int rank, int world, int n_global, int n_set, const char* const* swap_sets,
                            uint32_t seed, const float* temperature_all) {
@@ -349,17 +374,17 @@ int ub_ladder_n_pairs(const UbLadder* h) { return h->l->n_pair_total; }
 int ub_ladder_state(UbLadder* h, int* replica_indices, int* accept, uint64_t* n_attempt, uint64_t* n_success, float* energies) {
     LAD_TRY
     auto& l = *h->l;
-    l.e->sync_and_check();
-    if (replica_indices) { auto v = l.replica_index.download(); memcpy(replica_indices, v.data(), l.n_global * sizeof(int)); }
-    if (accept && l.n_pair_total) { auto v = l.accept.download(); memcpy(accept, v.data(), l.n_pair_total * sizeof(int)); }
-    if ((n_attempt || n_success) && l.n_pair_total) {
-        auto v = l.counts.download();
-        for (int k = 0; k < l.n_pair_total; ++k) {
-            if (n_attempt) n_attempt[k] = v[2 * k];
-            if (n_success) n_success[k] = v[2 * k + 1];
-        }
+    std::vector<int> ri, acc;
+    std::vector<unsigned long long> cnt;
+    std::vector<float> en;
+    l.download(replica_indices ? &ri : nullptr, accept ? &acc : nullptr, (n_attempt || n_success) ? &cnt : nullptr, energies ? &en : nullptr);
+    if (replica_indices) memcpy(replica_indices, ri.data(), l.n_global * sizeof(int));
+    if (accept && l.n_pair_total) memcpy(accept, acc.data(), l.n_pair_total * sizeof(int));
+    for (int k = 0; k < l.n_pair_total && (n_attempt || n_success); ++k) {
+        if (n_attempt) n_attempt[k] = cnt[2 * k];
+        if (n_success) n_success[k] = cnt[2 * k + 1];
     }
-    if (energies) { auto v = l.energy_all.download(); memcpy(energies, v.data(), l.n_global * sizeof(float)); }
+    if (energies) memcpy(energies, en.data(), l.n_global * sizeof(float));
     return 0;
     LAD_CATCH
 }
