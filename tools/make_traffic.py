@@ -19,8 +19,8 @@ GROUPS = {   # bench.py group name -> kernel-name substrings
     'hbond_coverage x2 (fwd + bwd)': ['k_hbond_coverage'],
     'environment_coverage (fwd + bwd)': ['k_env_coverage'],
     'protein_hbond (fwd + bwd)': ['k_protein_hbond'],
-    'pair lists (k_cache_check + k_pairlist + k_refine, all graphs)': ['k_refine', 'k_pairlist', 'k_cache_check'],
-    'rotamer prep (k_rot_prep)': ['k_rot_prep'],
+    'pair lists (k_cache_check + k_pairlist + k_refine, the four sparse graphs)': ['k_refine', 'k_pairlist', 'k_cache_check'],
+    'rotamer build (k_rot_build: residue spheres, bead masks, CSR rows)': ['k_rot_build'],
 }
 per = collections.defaultdict(lambda: collections.defaultdict(list))
 for r in rows[2:]:
@@ -32,17 +32,35 @@ for r in rows[2:]:
     per[short]['dram'].append(val(d, 'dram__bytes_read.sum') + val(d, 'dram__bytes_write.sum'))
     per[short]['issue'].append(val(d, 'smsp__issue_active.avg.pct_of_peak_sustained_active'))
     per[short]['fma'].append(val(d, 'sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active'))
+    # FP32 flops the kernel really executed (SURVEY.md section 8(d) names these counters as the roofline numerator)
+    fl = 0.0
+    for k, w in (('sm__sass_thread_inst_executed_op_fadd_pred_on.sum', 1), ('sm__sass_thread_inst_executed_op_fmul_pred_on.sum', 1),
+                 ('sm__sass_thread_inst_executed_op_ffma_pred_on.sum', 2)):
+        if k in d and d[k] not in ('', 'n/a'):
+            fl += w * float(d[k].replace(',', ''))
+    per[short]['flops'].append(fl)
+    if 'smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio' in d:
+        try: per[short]['barrier'].append(float(d['smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio']))
+        except ValueError: pass
 res = {'_source': 'ncu --set full --clock-control none, tools/profile_run.py 4096 (config 3), capture %s' % tag, '_kernels': {}}
 mean = lambda v: sum(v) / len(v)
 for k, m in per.items():
     res['_kernels'][k] = dict(launches=len(m['us']), us_per_launch=mean(m['us']), dram_bytes_per_launch=mean(m['dram']),
-                              issue_active_pct=mean(m['issue']), fma_pipe_active_pct=mean(m['fma']))
+                              issue_active_pct=mean(m['issue']), fma_pipe_active_pct=mean(m['fma']),
+                              fp32_flops_executed_per_launch=mean(m['flops']) if m['flops'] else None,
+                              barrier_stall_warps_per_issue=mean(m['barrier']) if m['barrier'] else None)
 for g, subs in GROUPS.items():
     ks = [res['_kernels'][s] for s in subs if s in res['_kernels']]
     if not ks: continue
     # the group figure is per LAUNCH of its dominant kernel (launch counts per evaluation differ between kernels)
     top = max(ks, key=lambda k: k['us_per_launch'])
     res[g] = dict(dram_bytes_per_launch=top['dram_bytes_per_launch'], issue_active_pct=top['issue_active_pct'],
-                  fma_pipe_active_pct=top['fma_pipe_active_pct'], us_per_launch_under_ncu=top['us_per_launch'])
+                  fma_pipe_active_pct=top['fma_pipe_active_pct'], us_per_launch_under_ncu=top['us_per_launch'],
+                  fp32_flops_executed_per_launch=top['fp32_flops_executed_per_launch'],
+                  barrier_stall_warps_per_issue=top['barrier_stall_warps_per_issue'])
+import os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench
+res['source_hash'] = bench.kernel_source_hash()     # bench.py quotes this file only for the build it was captured from
 json.dump(res, open(out, 'w'), indent=1)
 print(json.dumps({k: v for k, v in res.items() if not k.startswith('_')}, indent=1))
