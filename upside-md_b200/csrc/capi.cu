@@ -385,14 +385,14 @@ void free_deriv_engine(DerivEngine* engine) { delete engine; }
 
 int evaluate_energy(float* energy, DerivEngine* engine, const float* pos) {
     UB_TRY
-    engine->u.eng->set_pos(pos);
-    return ub_evaluate(&engine->u, energy, nullptr);
+    engine->u.eng->evaluate_host(pos, energy, nullptr);
+    return 0;
     UB_CATCH
 }
 int evaluate_deriv(float* deriv, DerivEngine* engine, const float* pos) {
     UB_TRY
-    engine->u.eng->set_pos(pos);
-    return ub_evaluate(&engine->u, nullptr, deriv);
+    engine->u.eng->evaluate_host(pos, nullptr, deriv);
+    return 0;
     UB_CATCH
 }
 int set_param(int n_param, const float* param, DerivEngine* engine, const char* node_name) {

@@ -148,6 +148,8 @@ Engine::~Engine() {
     if (mc) mc_destroy(mc);
     for (auto& g : graph_eval) if (g) cudaGraphExecDestroy(g);
     if (graph_round) cudaGraphExecDestroy(graph_round);
+    if (graph_host_eval) cudaGraphExecDestroy(graph_host_eval);
+    if (pinned_io) cudaFreeHost(pinned_io);
     nodes.clear();
     for (auto st : node_stream) cudaStreamDestroy(st);
     for (auto e : ev_fwd) cudaEventDestroy(e);
@@ -309,6 +311,38 @@ void Engine::compute(ComputeMode mode) {
     UB_CUDA(cudaGraphLaunch(graph_eval[mode], stream));
 }
 
+__global__ void k_pack3to4(float* __restrict__ dst, const float* __restrict__ src, long n);
+__global__ void k_unpack4to3(float* __restrict__ dst, const float* __restrict__ src, long n);
+void Engine::evaluate_host(const float* pos3, float* energy, float* deriv3) {
+    UB_CUDA(cudaSetDevice(device));
+    const size_t n3 = size_t(n_rep) * n_atom * 3;
+    const long cnt = long(n_rep) * n_atom;
+    if (!pinned_io) UB_CUDA(cudaMallocHost((void**)&pinned_io, sizeof(float) * (2 * n3 + n_rep + 1)));
+    float* h_in = pinned_io, *h_out = pinned_io + n3, *h_en = pinned_io + 2 * n3;
+    int* h_err = reinterpret_cast<int*>(pinned_io + 2 * n3 + n_rep);
+    if (!graph_host_eval) {
+        float* tmp = io_staging(2 * n3);
+        cudaGraph_t g;
+        UB_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+        UB_CUDA(cudaMemcpyAsync(tmp, h_in, n3 * sizeof(float), cudaMemcpyHostToDevice, stream));
+        k_pack3to4<<<(unsigned)((cnt + 255) / 256), 256, 0, stream>>>(pos->output, tmp, cnt);
+        enqueue_compute(stream, PotentialAndDerivMode);
+        k_unpack4to3<<<(unsigned)((cnt + 255) / 256), 256, 0, stream>>>(tmp + n3, pos->sens, cnt);
+        UB_CUDA(cudaMemcpyAsync(h_out, tmp + n3, n3 * sizeof(float), cudaMemcpyDeviceToHost, stream));
+        UB_CUDA(cudaMemcpyAsync(h_en, potential.p, n_rep * sizeof(float), cudaMemcpyDeviceToHost, stream));
+        UB_CUDA(cudaMemcpyAsync(h_err, error_flag.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        UB_CUDA(cudaStreamEndCapture(stream, &g));
+        UB_CUDA(cudaGraphInstantiate(&graph_host_eval, g, 0));
+        UB_CUDA(cudaGraphDestroy(g));
+    }
+    memcpy(h_in, pos3, n3 * sizeof(float));
+    UB_CUDA(cudaGraphLaunch(graph_host_eval, stream));
+    UB_CUDA(cudaStreamSynchronize(stream));
+    if (*h_err) sync_and_check();   // reports (and clears) the device-side failure
+    if (energy) memcpy(energy, h_en, n_rep * sizeof(float));
+    if (deriv3) memcpy(deriv3, h_out, n3 * sizeof(float));
+}
+
 std::vector<std::pair<std::string, float>> Engine::profile_eval(ComputeMode mode) {
     UB_CUDA(cudaSetDevice(device));
     UB_CUDA(cudaStreamSynchronize(stream));
@@ -340,6 +374,8 @@ void Engine::sync_and_check() {
         if (flag == 1)
             throw std::string("pair-list capacity exceeded on the device (raise UPSIDE_B200_NEIGHBOR_SCALE)");
         if (flag == 2) throw std::string("rotamer residue-pair capacity exceeded on the device");
+        if (flag == 3) throw std::string("rotamer bead-pair capacity exceeded on the device (raise UPSIDE_B200_NEIGHBOR_SCALE)");
+        if (flag == 4) throw std::string("rotamer build: candidate / active residue-pair capacity exceeded on the device (raise UPSIDE_B200_NEIGHBOR_SCALE)");
         throw std::string("device-side failure flag ") + std::to_string(flag);
     }
 }

@@ -256,6 +256,12 @@ struct Engine {
     void enqueue_compute_dag(cudaStream_t s, ComputeMode mode);
     void compute(ComputeMode mode);                 // one evaluation of all replicas (graph replay), asynchronous
     void sync_and_check();                          // cudaStreamSynchronize + device error flag -> throws
+    // One evaluation with HOST buffers in one CUDA graph: positions (n_rep,n_atom,3) from a pinned staging buffer, layout
+    // conversion, the evaluation, derivatives and energies back into pinned memory - one launch, one synchronisation (the
+    // reference ABI's evaluate_energy / evaluate_deriv pay for four synchronous copies otherwise).  energy / deriv may be NULL.
+    void evaluate_host(const float* pos3, float* energy, float* deriv3);
+    float* pinned_io = nullptr;                     // [n_rep*n_atom*3 (in) | n_rep*n_atom*3 (out) | n_rep (energy) | 1 (error flag)]
+    cudaGraphExec_t graph_host_eval = nullptr;
 
     // I/O in caller layout: pos/deriv/mom [B][n_atom][3]
     void set_pos(const float* p, int first_rep = 0, int n = -1);

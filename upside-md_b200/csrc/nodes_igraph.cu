@@ -69,6 +69,29 @@ void IGraphHost::allocate(Engine* e) {
         cnt2.alloc(size_t(e->n_rep) * n2);
     }
     if (const char* s = getenv("UPSIDE_B200_NO_VERLET_CACHE")) use_cache = atoi(s) == 0;
+    // SMALL BATCHES: asymmetric graphs build their exact rows in one launch from the positions (k_rows_direct) instead of the
+    // three launches of the cached path - with a few replicas per GPU an evaluation is a chain of launch latencies, and two of
+    // the sparse graphs sit on its critical path (76 residues x 1 replica: 214 -> 199 us per evaluation).  From a few
+    // hundred replicas on the cached path does less work per list (4096 x 100 residues: 461 us against 764 us for the four
+    // sparse graphs).  UPSIDE_B200_DIRECT_ROWS=0/1 overrides the batch-size rule.
+    bool want_direct = e->n_rep <= 64;
+    if (const char* dr = getenv("UPSIDE_B200_DIRECT_ROWS")) want_direct = atoi(dr) != 0;
+    if (!symmetric && use_cache && want_direct) {
+        h_cluster_start.assign(1, 0);   // clusters of group 2: runs of consecutive elements with one id, at most eight each
+        for (int j = 1; j <= n2; ++j)
+            if (j == n2 || id2[j] != id2[j - 1] || j - h_cluster_start.back() == 8) h_cluster_start.push_back(j);
+        const size_t n_cl = h_cluster_start.size() - 1, nW1 = (n1 + 31) / 32, nW2 = (n2 + 31) / 32;
+        smem_direct = sizeof(float4) * (size_t(n1) + n2 + n_cl) + 4 * (n_cl + 1) + 4 * ((need1 ? size_t(n1) * nW2 : 0) + (need2 ? size_t(n2) * nW1 : 0)) + 16;
+        int device_smem = 0;
+        UB_CUDA(cudaDeviceGetAttribute(&device_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, e->device));
+        // (beyond ~110 KB only one CTA fits an SM and the cached path is the better one)
+        if (smem_direct <= std::min<size_t>(device_smem, 110 * 1024)) {
+            direct = true;
+            use_cache = false;
+            d_cluster_start.upload(h_cluster_start);
+            UB_CUDA(cudaFuncSetAttribute(k_rows_direct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_direct, 48 * 1024)));
+        }
+    }
     if (use_cache) {
         // The skin only trades rebuild frequency against candidates per refine; the exact list does not depend on it.  The
         // reference uses 1 + 0.2*cutoff (cache_buffer, interaction_graph.h:395-396); here an all-pairs rebuild costs more
@@ -127,6 +150,13 @@ void IGraphHost::build(cudaStream_t s) {
     constexpr int RGL = 8;
     if (!n1 || !n2) return;
     const int B = engine->n_rep;
+    if (direct) {
+        const int which = (need1 ? 1 : 0) | (need2 ? 2 : 0);
+        ClusterDev C{d_cluster_start.p, (int)h_cluster_start.size() - 1};
+        k_rows_direct<<<B, ROWS_TPB, smem_direct, s>>>(d.s1, d.s2, C, which, d.nbr1, d.cnt1, d.K1, d.nbr2, d.cnt2, d.K2, d.cutoff, d.excl, d.error_flag);
+        engine->mark(s, "(pairlist)");
+        return;
+    }
     if (!use_cache) {
         if (need1)
             k_pairlist<TILE><<<dim3((n1 + TILE - 1) / TILE, B), TILE, 0, s>>>(d.s1, d.s2, d.nbr1, d.cnt1, d.K1, d.cutoff2, d.excl,
