@@ -1501,6 +1501,48 @@ __global__ void __launch_bounds__(BP2_TPB, BP2_OCC) k_rot_bp2(RotamerDev P, Bp2L
     const int n_multi = n_multi_s;
     const float damping = P.damping;
     const int dummy = (SP - 1) * MSG_STRIDE;   // row SP-1 holds ones: the neutral message
+    (void)dummy;
+#ifndef UB_BP2_NODE_THREAD
+    // node update: belief = prob * prod(incoming messages), max-normalised and damped (rotamer.cpp:488-499,258-273).  FOUR lanes
+    // per residue, each owning one or two states (lane s: states s and s+4): a lane multiplies its states' components of the
+    // incident messages - every factor scaled by 6, so that a uniform message is neutral and neither 40 factors overflow nor
+    // the product vanishes for every state at once (pure rescaling, as rotamer.cpp:492-493) - and the four lanes agree on the
+    // maximum by two shuffles.  Against one thread per residue (three busy warps with 24 dependent loads per step) this
+    // spreads the phase over ten warps and cuts its serial chain to one load and one multiply per incident pair.
+    auto nodes = [&]() -> float {
+        float dev = 0.f;
+        const int sub = tid & 3;
+        for (int i0 = (tid & ~31) >> 2; i0 < n_multi; i0 += BP2_TPB >> 2) {   // i0: first residue of this warp's eight
+            const int i = i0 + ((tid & 31) >> 2);
+            const bool act = i < n_multi;
+            const int A = act ? nlist[i] : 0;
+            const int nA = act ? nrot[A] : 0;
+            const bool has0 = sub < nA, has1 = sub + 4 < nA;
+            float b0 = has0 ? prob[A * NODE_STRIDE + sub] : 0.f, b1 = has1 ? prob[A * NODE_STRIDE + sub + 4] : 0.f;
+            const int t1 = act ? istart[A + 1] : 0;
+            for (int t = act ? istart[A] : 0; t < t1; ++t) {
+                const int off = inc2[t];
+                if (has0) b0 *= 6.f * msg[off + sub];
+                if (has1) b1 *= 6.f * msg[off + sub + 4];
+            }
+            float mx = fmaxf(b0, b1);
+            mx = fmaxf(mx, __shfl_xor_sync(UB_FULL_MASK, mx, 1));
+            mx = fmaxf(mx, __shfl_xor_sync(UB_FULL_MASK, mx, 2));
+            const float sc = (damping != 0.f ? 1.f - damping : 1.f) * __fdividef(1.f, mx);
+            if (has0) {
+                const float o = bel[A * NODE_STRIDE + sub], n = fmaf(sc, b0, damping * o);
+                dev = fmaxf(dev, n - o);
+                bel[A * NODE_STRIDE + sub] = n;
+            }
+            if (has1) {
+                const float o = bel[A * NODE_STRIDE + sub + 4], n = fmaf(sc, b1, damping * o);
+                dev = fmaxf(dev, n - o);
+                bel[A * NODE_STRIDE + sub + 4] = n;
+            }
+        }
+        return dev;
+    };
+#else
     auto nodes = [&]() -> float {
         float dev = 0.f;
         for (int i = tid; i < n_multi; i += BP2_TPB) {
@@ -1510,6 +1552,7 @@ __global__ void __launch_bounds__(BP2_TPB, BP2_OCC) k_rot_bp2(RotamerDev P, Bp2L
         }
         return dev;
     };
+#endif
     // initial sweep: first messages from (prob, unit messages); node beliefs restart from prob/max (rotamer.cpp:1034)
     messages();
     __syncthreads();
