@@ -834,13 +834,24 @@ __global__ void __launch_bounds__(EDGE_MAXT, EDGE_OCC) k_rot_energy(RotamerDev P
             const int base = rowstart[i], c = rowstart[i + 1] - base;
             const int lo = lower[i];   // first entry to evaluate: folding partners below the bead, then the partners above
             float fold = 0.f;
+            // software pipeline: the partner / code loads of the NEXT four entries are in flight while these four are evaluated
+            // (the kernel sat on the long scoreboard: 6 stalled warps per issue, 38 % issue-slot utilisation)
+            int js_n[PF], cds_n[PF];
+#pragma unroll
+            for (int u = 0; u < PF; ++u) {
+                const int k = lo + u;
+                js_n[u] = k < c ? (int)dj[base + k] : -1;
+                cds_n[u] = k < c ? code[base + k] : CODE_SS;
+            }
             for (int k0 = lo; k0 < c; k0 += PF) {
                 int js[PF], cds[PF];
 #pragma unroll
+                for (int u = 0; u < PF; ++u) { js[u] = js_n[u]; cds[u] = cds_n[u]; }
+#pragma unroll
                 for (int u = 0; u < PF; ++u) {
-                    const int k = k0 + u;
-                    js[u] = k < c ? (int)dj[base + k] : -1;
-                    cds[u] = k < c ? code[base + k] : CODE_SS;
+                    const int k = k0 + PF + u;
+                    js_n[u] = k < c ? (int)dj[base + k] : -1;
+                    cds_n[u] = k < c ? code[base + k] : CODE_SS;
                 }
 #pragma unroll
                 for (int u = 0; u < PF; ++u) {
@@ -947,9 +958,16 @@ __device__ __forceinline__ void emit_entry_weights(const RotamerDev& P, int r, i
     const int n_ent = P.rowstart[size_t(r) * (P.n_bead + 1) + P.n_bead];
     const int* code = P.code + size_t(r) * P.cap_e;
     float* ss = P.ss + size_t(r) * P.cap_e;
-    for (int e = threadIdx.x; e < n_ent; e += n_thread) {
-        const int cd = code[e];
-        ss[e] = cd >= 0 ? pair_marg(cd) : (cd == CODE_SS ? 1.f : node_marg((-2 - cd) >> 1));
+    // four entries per step: the code loads of a step are independent, so their global-memory latency overlaps (one load per
+    // step left this loop waiting on the long scoreboard for 10 % of the BP kernel's time)
+    for (int e0 = threadIdx.x; e0 < n_ent; e0 += 4 * n_thread) {
+        int cd[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) cd[u] = e0 + u * n_thread < n_ent ? code[e0 + u * n_thread] : CODE_SS;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (e0 + u * n_thread < n_ent)
+                ss[e0 + u * n_thread] = cd[u] >= 0 ? pair_marg(cd[u]) : (cd[u] == CODE_SS ? 1.f : node_marg((-2 - cd[u]) >> 1));
     }
 }
 
