@@ -20,6 +20,7 @@ CONFIGS = {
     4: os.path.join(ROOT, 'configs', 'config4_150res.up'),
     5: os.path.join(ROOT, 'configs', 'config5_300res.up'),
     6: os.path.join(ROOT, 'configs', 'config6_restraints_20res.up'),
+    9: os.path.join(ROOT, 'configs', 'config9_coupling_20res.up'),     # config 1 + uniform_transform / linear_coupling nodes
     8: os.path.join(ROOT, 'configs', 'config8_radial_20res.up'),       # config 1 + radial / hbond_sc_radial pair nodes
     7: os.path.join(ROOT, 'configs', 'config7_concat_20res.up'),       # config 1 + slice/constant/concat -> tether springs   # config 1 + restraint / plumbing nodes (tools/make_restraint_config.py)
 }

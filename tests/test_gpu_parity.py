@@ -47,7 +47,7 @@ def _check_report(rep):
 
 
 @pytest.mark.skipif(not ref_engine.available('pinned'), reason='oracle/_ref not shipped')
-@pytest.mark.parametrize('cid,n_rep', [(1, 4), (2, 2), (3, 3), (4, 2), (5, 2), (6, 3), (8, 3)])
+@pytest.mark.parametrize('cid,n_rep', [(1, 4), (2, 2), (3, 3), (4, 2), (5, 2), (6, 3), (8, 3), (9, 3)])
 def test_every_node_matches_oracle(cid, n_rep):
     cfg = parity.CONFIGS[cid]
     pos = parity.test_positions(cfg, n_rep + 1)[1:]     # relaxed structures (see DESIGN.md on /input/pos itself)

@@ -84,6 +84,19 @@ def main():
     w.save(path)
     print(path, os.path.getsize(path))
 
+    # config 9: uniform_transform and both linear_coupling nodes (src/environment.cpp:158-321) on top of config 1
+    w = config.ConfigWriter.from_file(os.path.join(ROOT, 'configs', 'config1_20res.up'))
+    r = np.random.default_rng(9)
+    types = np.array([names.index(x) for x in w.fasta], dtype='i')
+    w.write_linear_coupling('environment_coverage', r.uniform(-0.3, 0.3, 20), types)
+    w.write_linear_coupling('environment_coverage', r.uniform(-0.3, 0.3, 20), types, inactivation='placement_fixed_point_vector_only_CB',
+                            inactivation_dim=3)
+    w.write_uniform_transform('environment_coverage', r.uniform(-1., 1., 12), -0.5, 1.5)
+    w.write_linear_coupling('uniform_transform', r.uniform(-0.5, 0.5, 20), types, suffix='_transformed')
+    path = os.path.join(ROOT, 'configs', 'config9_coupling_20res.up')
+    w.save(path)
+    print(path, os.path.getsize(path))
+
 
 if __name__ == '__main__':
     main()

@@ -575,6 +575,21 @@ class ConfigWriter:
         self.arr(g, 'id2', np.arange(self.n_res, dtype='i'))
         self.arr(g, 'interaction_param', np.asarray(interaction_param, dtype='f4'))
 
+    def write_uniform_transform(self, argument, bspline_coeff, spline_offset, spline_inv_dx, suffix=''):
+        """uniform_transform (src/environment.cpp:158-233): one clamped cubic B-spline applied to every element of a width-1 node"""
+        g = self.group('uniform_transform' + suffix, [argument])
+        d = self.arr(g, 'bspline_coeff', np.asarray(bspline_coeff, dtype='f4'))
+        d.attrs['spline_offset'], d.attrs['spline_inv_dx'] = float(spline_offset), float(spline_inv_dx)
+
+    def write_linear_coupling(self, argument, couplings, coupling_types, inactivation=None, inactivation_dim=0, suffix=''):
+        """linear_coupling_uniform / linear_coupling_with_inactivation (src/environment.cpp:235-321)"""
+        name = ('linear_coupling_with_inactivation' if inactivation else 'linear_coupling_uniform') + suffix
+        g = self.group(name, [argument] + ([inactivation] if inactivation else []))
+        self.arr(g, 'couplings', np.asarray(couplings, dtype='f4'))
+        self.arr(g, 'coupling_types', np.asarray(coupling_types, dtype='i4'))
+        if inactivation:
+            g.attrs['inactivation_dim'] = int(inactivation_dim)
+
     def write_jump_moves(self, atom_ranges, sigma_trans, sigma_rot):
         """/input/jump_moves as JumpSampler reads it (src/monte_carlo_sampler.cpp:174-201): rigid translations (sigma_trans,
         Angstrom) and rotations about the centre of mass (sigma_rot, radians) of the atom ranges [first, next_first)"""

@@ -1053,6 +1053,151 @@ struct NonlinearCoupling : PotentialNode {
 };
 RegisterNodeType<NonlinearCoupling, 1> nonlinear_coupling_node("nonlinear_coupling");
 
+// ---------------------------------------------------------------------------------------------- UniformTransform
+// reference environment.cpp:158-233: output = clamped cubic B-spline of a width-1 coordinate, one spline for all
+// elements; the backward pass recomputes the slope instead of storing a Jacobian
+__device__ __forceinline__ void clamped_scalar_spline(const float* __restrict__ c, int n_coeff, float x, float& v, float& d) {
+    if (x <= 1.f) { v = (1.f / 6.f) * c[0] + (2.f / 3.f) * c[1] + (1.f / 6.f) * c[2]; d = 0.f; }
+    else if (x >= (float)(n_coeff - 2)) { v = (1.f / 6.f) * c[n_coeff - 3] + (2.f / 3.f) * c[n_coeff - 2] + (1.f / 6.f) * c[n_coeff - 1]; d = 0.f; }
+    else { const int b = (int)x; deboor_core(c[b - 1], c[b], c[b + 1], c[b + 2], x - b, v, d); }
+}
+__global__ void k_uniform_transform(const float* __restrict__ in, float* __restrict__ out, const float* __restrict__ coeff, int n, int n_coeff,
+                                    float offset, float inv_dx) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+    if (i >= n) return;
+    float v, d;
+    clamped_scalar_spline(coeff, n_coeff, (in[size_t(r) * n + i] - offset) * inv_dx, v, d);
+    out[size_t(r) * n + i] = v;
+}
+__global__ void k_uniform_transform_deriv(const float* __restrict__ in, float* __restrict__ in_sens, const float* __restrict__ sens,
+                                          const float* __restrict__ coeff, int n, int n_coeff, float offset, float inv_dx) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+    if (i >= n) return;
+    float v, d;
+    clamped_scalar_spline(coeff, n_coeff, (in[size_t(r) * n + i] - offset) * inv_dx, v, d);
+    atomicAdd(&in_sens[size_t(r) * n + i], d * inv_dx * sens[size_t(r) * n + i]);   // other consumers of the input add here too
+}
+struct UniformTransform : CoordNode {
+    CoordNode& input;
+    int n_coeff;
+    float offset, inv_dx;
+    std::vector<float> h_coeff;
+    DevBuf<float> coeff;
+    UniformTransform(Engine&, const h5l::Node& g, CoordNode& in) : CoordNode(in.n_elem, 1), input(in) {
+        check_elem_width(input, 1);
+        n_coeff = (int)h5_dims(g, "bspline_coeff", 1)[0];
+        offset = h5_attr<float>(g, "bspline_coeff", "spline_offset");
+        inv_dx = h5_attr<float>(g, "bspline_coeff", "spline_inv_dx");
+        h_coeff = h5_read<float>(g, "bspline_coeff");
+        if (n_coeff < 4) throw std::string("too small of size for spline");
+        coeff.upload(h_coeff);
+    }
+    void compute_value(cudaStream_t s, ComputeMode) override {
+        if (!n_elem) return;
+        k_uniform_transform<<<grid_for(n_elem, engine->n_rep), TPB, 0, s>>>(input.output, output, coeff.p, n_elem, n_coeff, offset, inv_dx);
+    }
+    void propagate_deriv(cudaStream_t s) override {
+        if (!n_elem) return;
+        k_uniform_transform_deriv<<<grid_for(n_elem, engine->n_rep), TPB, 0, s>>>(input.output, input.sens, sens, coeff.p, n_elem, n_coeff, offset, inv_dx);
+    }
+    std::vector<float> get_param() const override {   // (offset, inv_dx, coefficients): environment.cpp:198-204
+        std::vector<float> p{offset, inv_dx};
+        p.insert(p.end(), h_coeff.begin(), h_coeff.end());
+        return p;
+    }
+    void set_param(const std::vector<float>& p) override {   // environment.cpp:222-232
+        if (p.size() < size_t(2 + 4)) throw std::string("too small of size for spline");
+        offset = p[0]; inv_dx = p[1];
+        h_coeff.assign(p.begin() + 2, p.end());
+        n_coeff = (int)h_coeff.size();
+        coeff.upload(h_coeff);
+    }
+};
+RegisterNodeType<UniformTransform, 1> uniform_transform_node("uniform_transform");
+
+// ---------------------------------------------------------------------------------------------- LinearCoupling
+// reference environment.cpp:235-321: E = sum_i c[type_i] * x_i * (1 - inact_i)^2, with the optional inactivation read
+// from component `inactivation_dim` of a second node; logger: c * x per element (:270-278)
+__global__ void k_linear_coupling(const float* __restrict__ in, float* __restrict__ in_sens, const float* __restrict__ inact,
+                                  float* __restrict__ inact_sens, int inact_wp, int inact_dim, const float* __restrict__ couplings,
+                                  const int* __restrict__ types, int n, float* __restrict__ pot, int want_pot) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+    float e = 0.f;
+    if (i < n) {
+        const float c = couplings[types[i]], val = in[size_t(r) * n + i];
+        float act = 1.f;
+        if (inact) { const float u = 1.f - inact[(size_t(r) * n + i) * inact_wp + inact_dim]; act = u * u; }
+        e = c * val * act;
+        atomicAdd(&in_sens[size_t(r) * n + i], c * act);
+        if (inact) atomicAdd(&inact_sens[(size_t(r) * n + i) * inact_wp + inact_dim], -c * val);   // sic: the reference's derivative (:293)
+    }
+    if (want_pot) accumulate_potential(e, pot);
+}
+struct LinearCoupling : PotentialNode {
+    CoordNode& input;
+    CoordNode* inactivation;
+    int inactivation_dim = 0;
+    std::vector<float> h_couplings;
+    std::vector<int> h_types;
+    DevBuf<float> couplings;
+    DevBuf<int> types;
+    LinearCoupling(Engine& e, const h5l::Node& g, CoordNode& in) : LinearCoupling(e, g, in, nullptr) {}
+    LinearCoupling(Engine& e, const h5l::Node& g, CoordNode& in, CoordNode& inact) : LinearCoupling(e, g, in, &inact) {}
+    LinearCoupling(Engine&, const h5l::Node& g, CoordNode& in, CoordNode* inact) : input(in), inactivation(inact) {
+        check_elem_width(input, 1);
+        if (inactivation) {
+            inactivation_dim = h5_attr<int>(g, ".", "inactivation_dim");
+            if (input.n_elem != inactivation->n_elem) throw std::string("Inactivation size must match input size");
+            check_elem_width_lower_bound(*inactivation, inactivation_dim + 1);
+        }
+        h_couplings = h5_read<float>(g, "couplings");
+        h5_check_size(g, "coupling_types", {(uint64_t)input.n_elem});
+        h_types = h5_read<int>(g, "coupling_types");
+        for (int v : h_types) if (v < 0 || v >= (int)h_couplings.size()) throw std::string("invalid coupling type");
+        couplings.upload(h_couplings);
+        types.upload(h_types);
+    }
+    void compute_value(cudaStream_t s, ComputeMode mode) override {
+        if (!input.n_elem) return;
+        k_linear_coupling<<<grid_for(input.n_elem, engine->n_rep), TPB, 0, s>>>(
+            input.output, input.sens, inactivation ? inactivation->output : nullptr, inactivation ? inactivation->sens : nullptr,
+            inactivation ? inactivation->wp : 1, inactivation_dim, couplings.p, types.p, input.n_elem, potential, mode == PotentialAndDerivMode);
+    }
+    std::vector<float> get_param() const override { return h_couplings; }
+    void set_param(const std::vector<float>& p) override {
+        if (p.size() != h_couplings.size()) throw std::string("attempting to change size of couplings vector on set_param");
+        h_couplings = p;
+        couplings.upload(h_couplings);
+    }
+    std::vector<float> get_param_deriv(int replica) override {   // environment.cpp:305-314 (PARAM_DERIV build)
+        if (replica >= engine->n_rep) throw std::string("replica out of range");
+        engine->sync_and_check();
+        std::vector<float> d(h_couplings.size(), 0.f);
+        const int r0 = replica < 0 ? 0 : replica, r1 = replica < 0 ? engine->n_rep : replica + 1;
+        for (int r = r0; r < r1; ++r) {
+            auto x = input.host_rows(input.output, r);
+            std::vector<float> u;
+            if (inactivation) u = inactivation->host_rows(inactivation->output, r);
+            for (int ne = 0; ne < input.n_elem; ++ne) {
+                const float act = inactivation ? 1.f - u[size_t(ne) * inactivation->wp + inactivation_dim] : 1.f;
+                d[h_types[ne]] += x[size_t(ne) * input.wp] * act;
+            }
+        }
+        return d;
+    }
+    void add_loggers(int level, std::vector<NodeLogger>& out) override {
+        if (level < 1) return;
+        out.push_back({inactivation ? "linear_coupling_with_inactivation" : "linear_coupling_uniform", {(uint64_t)input.n_elem}, false, [this](int r) {
+            auto x = input.host_rows(input.output, r);
+            std::vector<float> v(input.n_elem);
+            for (int ne = 0; ne < input.n_elem; ++ne) v[ne] = h_couplings[h_types[ne]] * x[size_t(ne) * input.wp];
+            return v;
+        }});
+    }
+};
+RegisterNodeType<LinearCoupling, 1> linear_coupling_node1("linear_coupling_uniform");
+RegisterNodeType<LinearCoupling, 2> linear_coupling_node2("linear_coupling_with_inactivation");
+
 // ---------------------------------------------------------------------------------------------- HBondEnergy
 // reference hbond.cpp:417-456: E = E_hb * sum_sites hb, sens(6) += E_hb
 __global__ void k_hbond_energy(const float* __restrict__ hb, float* __restrict__ hb_sens, float* __restrict__ pot,
