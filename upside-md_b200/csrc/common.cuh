@@ -41,6 +41,15 @@ __device__ __forceinline__ void atomic_add3v(float* p16, f3 a) {
     atomicAdd(reinterpret_cast<float4*>(p16), make_float4(a.x, a.y, a.z, 0.f));
 }
 
+// One-instruction reciprocal (MUFU.RCP).  `__fdividef(x, y)` and `1.f / y` guard against denormal denominators with a compare and
+// two predicated multiplies per call (five instructions); where the denominator is known to be a normal number - 1e-10 plus a
+// probability, a sum of L1-normalised messages, a maximum of beliefs - the guarded and the plain form return the same bits.
+__device__ __forceinline__ float rcp_fast(float y) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(y));
+    return r;
+}
+
 // quaternion (a,b,c,d) -> row-major rotation matrix; reference affine.h:99-108
 __device__ __forceinline__ void quat_to_rot(float* U, const float* q) {
     float a = q[0], b = q[1], c = q[2], d = q[3];

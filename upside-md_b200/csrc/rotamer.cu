@@ -1259,9 +1259,9 @@ __device__ __forceinline__ void bp2_pair(const float* __restrict__ bel, int nRp,
                                          const float* __restrict__ Pq) {
     float v1[NA], v2[NB], m1[NA], m2[NB];
 #pragma unroll
-    for (int a = 0; a < NA; ++a) { v1[a] = __fdividef(bel[(F) * NODE_STRIDE + a], 1e-10f + msg_p[a]); m1[a] = 0.f; }
+    for (int a = 0; a < NA; ++a) { v1[a] = bel[(F) * NODE_STRIDE + a] * rcp_fast(1e-10f + msg_p[a]); m1[a] = 0.f; }
 #pragma unroll
-    for (int b = 0; b < NB; ++b) { v2[b] = __fdividef(bel[(S) * NODE_STRIDE + b], 1e-10f + msg_p[6 + b]); m2[b] = 0.f; }
+    for (int b = 0; b < NB; ++b) { v2[b] = bel[(S) * NODE_STRIDE + b] * rcp_fast(1e-10f + msg_p[6 + b]); m2[b] = 0.f; }
 #pragma unroll
     for (int a = 0; a < NA; ++a)
 #pragma unroll
@@ -1275,7 +1275,7 @@ __device__ __forceinline__ void bp2_pair(const float* __restrict__ bel, int nRp,
     for (int a = 0; a < NA; ++a) s1 += m1[a];
 #pragma unroll
     for (int b = 0; b < NB; ++b) s2 += m2[b];
-    float i1 = __fdividef(1.f, s1), i2 = __fdividef(1.f, s2);
+    float i1 = rcp_fast(s1), i2 = rcp_fast(s2);
 #pragma unroll
     for (int a = 0; a < NA; ++a) msg_p[a] = m1[a] * i1;
 #pragma unroll
@@ -1546,7 +1546,7 @@ __global__ void __launch_bounds__(BP2_TPB, BP2_OCC) k_rot_bp2(RotamerDev P, Bp2L
             float mx = fmaxf(b0, b1);
             mx = fmaxf(mx, __shfl_xor_sync(UB_FULL_MASK, mx, 1));
             mx = fmaxf(mx, __shfl_xor_sync(UB_FULL_MASK, mx, 2));
-            const float sc = (damping != 0.f ? 1.f - damping : 1.f) * __fdividef(1.f, mx);
+            const float sc = (damping != 0.f ? 1.f - damping : 1.f) * rcp_fast(mx);
             if (has0) {
                 const float o = bel[A * NODE_STRIDE + sub], n = fmaf(sc, b0, damping * o);
                 dev = fmaxf(dev, n - o);
