@@ -788,7 +788,7 @@ __device__ __forceinline__ float pair_term(const RotamerDev& P, const PairTab& T
         f3 deriv_dir = inv_dist * (rXX - dot(u, rXX) * u);
         f3 dd = radial_deriv * u + deriv_dir;
         d1[0] = -dd.x; d1[1] = -dd.y; d1[2] = -dd.z; d1[3] = ang_d1 * u.x; d1[4] = ang_d1 * u.y; d1[5] = ang_d1 * u.z;
-        d2[0] = dd.x; d2[1] = dd.y; d2[2] = dd.z; d2[3] = -ang_d2 * u.x; d2[4] = -ang_d2 * u.y; d2[5] = -ang_d2 * u.z;
+        if (d2) { d2[0] = dd.x; d2[1] = dd.y; d2[2] = dd.z; d2[3] = -ang_d2 * u.x; d2[4] = -ang_d2 * u.y; d2[5] = -ang_d2 * u.z; }
     }
     return wv + angular_weight * nv;
 }
@@ -932,14 +932,14 @@ __global__ void __launch_bounds__(EDGE_MAXT, EDGE_OCC) k_rot_deriv(RotamerDev P,
 #pragma unroll
                 for (int u = 0; u < PF; ++u) {
                     if (js[u] < 0) continue;
-                    // one evaluation with the operands in (lower index, higher index) order, as the reference's i1<i2
-                    // edge; selecting operands and results instead of branching keeps the warp converged
-                    float d1[6], d2[6];
-                    const bool first = i < js[u];
-                    const BeadRec bj = beads[js[u]];
-                    pair_term<true, NKA, NK>(P, T, first ? bi : bj, first ? bj : bi, d1, d2);
+                    // The pair term is symmetric under exchange of its operands down to the last bit - the displacement and
+                    // every quantity odd in it change sign exactly, the angular tables trade places through the row-offset
+                    // table - so the row's bead always goes first and only ITS derivative is formed (no operand ordering by
+                    // index, no selects, no partner half: -30 instructions per entry)
+                    float d1[6];
+                    pair_term<true, NKA, NK>(P, T, bi, beads[js[u]], d1, nullptr);
 #pragma unroll
-                    for (int q = 0; q < 6; ++q) acc[q] += ss[u] * (first ? d1[q] : d2[q]);
+                    for (int q = 0; q < 6; ++q) acc[q] += ss[u] * d1[q];
                 }
             }
             old_a.x += acc[0]; old_a.y += acc[1]; old_a.z += acc[2]; old_a.w += acc[3]; old_b.x += acc[4]; old_b.y += acc[5];
