@@ -60,6 +60,7 @@ struct RotamerDev {
     QuadSplineShape q;
     int n_bead, n_res, n_words, n_type;
     const int *bead_res, *bead_rot, *res_nrot;
+    int loc_identity;       // bead b is element b of the position and probability nodes (ff_1): no index indirection
     const int* res_first;   // first bead of a residue (fast build: the beads of a residue are contiguous, one per state)
     const float* table;   // symmetric-compressed B-spline table: rows (t1<=t2), n_param floats each
     int n_prob;
@@ -362,7 +363,7 @@ constexpr int BUILD_MAX_RES = 2047, BUILD_MAX_SLOT = 65535;
 
 __host__ __device__ inline size_t build_spill_words(const BuildLay& L) {   // 64-bit words of global scratch per replica
     const size_t n_row_g = 2 * size_t(L.capa_tot - L.capa), n_c_g = size_t(L.capc_tot - L.capc);
-    return n_row_g + n_c_g + (n_c_g + 1) / 2 + (6 * n_row_g + 3) / 4;
+    return n_row_g + n_c_g + (n_c_g + 1) / 2 + (6 * n_row_g + 3) / 4 + (n_row_g + 3) / 4;
 }
 
 // returns false (uniformly, nothing written) if SPILL is off and the shared-memory capacities do not hold this replica
@@ -393,6 +394,7 @@ __device__ __forceinline__ bool rot_build_body(const RotamerDev& P, const BuildL
     unsigned short* awpre = wpre + nR * nW;                                 // [nR][nW] the same for `adj`
     unsigned short* lo_s = awpre + nR * nW;                                 // [nb]
     unsigned short* ce_s = lo_s + nb;                                       // [nb]
+    unsigned short* rowner_s = ce_s + nb;                                   // [2*capa] residue that owns neighbour-row entry t
 
     // spill areas of this replica: [2*(capa_tot-capa)] rows | [capc_tot-capc] masks | [capc_tot-capc] candidates | offsets
     const size_t n_row_g = 2 * size_t(L.capa_tot - L.capa), n_c_g = size_t(L.capc_tot - L.capc);
@@ -401,6 +403,7 @@ __device__ __forceinline__ bool rot_build_body(const RotamerDev& P, const BuildL
     const SpillArr<unsigned long long, SPILL> cmask{cmask_s, sp + n_row_g, L.capc};
     const SpillArr<unsigned, SPILL> cand{cand_s, reinterpret_cast<unsigned*>(sp + n_row_g + n_c_g), L.capc};
     const SpillArr<unsigned short, SPILL> off{off_s, reinterpret_cast<unsigned short*>(sp + n_row_g + n_c_g + (n_c_g + 1) / 2), 12 * L.capa};
+    const SpillArr<unsigned short, SPILL> rowner{rowner_s, reinterpret_cast<unsigned short*>(sp + n_row_g + n_c_g + (n_c_g + 1) / 2 + (6 * n_row_g + 3) / 4), 2 * L.capa};
     const int capc_use = SPILL ? L.capc_tot : L.capc, capa_use = SPILL ? L.capa_tot : L.capa;
 
     for (int i = tid; i < nR * nW; i += BUILD_TPB) { bitmap[i] = 0u; adj[i] = 0u; }
@@ -408,9 +411,9 @@ __device__ __forceinline__ bool rot_build_body(const RotamerDev& P, const BuildL
     for (int A = tid; A < nR; A += BUILD_TPB) { nrot[A] = P.res_nrot[A]; rfirst[A] = P.res_first[A]; }
     __syncthreads();
     for (int i = tid; i < nb; i += BUILD_TPB) {
-        bpos[i] = *reinterpret_cast<const float4*>(elem_ptr(P.g.s1, r, i));
+        const int loc = P.loc_identity ? i : P.g.s1.loc[i];   // (an index load in front of every gather is a second trip to memory)
+        bpos[i] = *reinterpret_cast<const float4*>(P.g.s1.out + (size_t(r) * P.g.s1.n_node + loc) * P.g.s1.wp);
         float e = 0.f;
-        const int loc = P.g.s1.loc[i];
         for (int p = 0; p < P.n_prob; ++p) e += P.prob_out[p][(size_t(r) * P.prob_n[p] + loc) * P.prob_wp[p]];
         en[P.bead_res[i] * MAXR + P.bead_rot[i]] = e;   // one bead per state
     }
@@ -598,6 +601,8 @@ __device__ __forceinline__ bool rot_build_body(const RotamerDev& P, const BuildL
         }
         rown[astart[A] + pa] = nbr_pack(m, true, B, slot);
         rown[astart[B] + pb] = nbr_pack(mt, false, A, slot);
+        rowner[astart[A] + pa] = (unsigned short)A;
+        rowner[astart[B] + pb] = (unsigned short)B;
     }
     for (int A = tid; A <= nR; A += BUILD_TPB) P.istart[size_t(r) * (nR + 1) + A] = istart[A];
     for (int i = tid; i < nR * MAXR; i += BUILD_TPB) P.enode[size_t(r) * nR * MAXR + i] = en[i];
@@ -644,44 +649,67 @@ __device__ __forceinline__ bool rot_build_body(const RotamerDev& P, const BuildL
     for (int i = tid; i <= nb; i += BUILD_TPB) rowstart[i] = rs[i];
     unsigned short* dj = P.dj + size_t(r) * P.cap_e;
     int* code = P.code + size_t(r) * P.cap_e;
-    // pass 2, one thread per (residue, neighbour): the entries of all the residue's beads against that neighbour.  What a
-    // pair decides - who folds, which matrix, where the neighbour's beads start - is worked out once, not once per bead.
+    // pass 2, one thread per (neighbour-row entry, own state): the up to six entries of one bead against one neighbouring
+    // residue, at positions known in advance (offset recorded by pass 1 + rank of the partner state among the set bits), so
+    // the stores are predicated, not branched over, and the lanes of a warp stay together.
     // Order inside a row as k_rot_prep: partners below that do not fold, those that fold, partners above ascending.
-    for (int t = tid; t < n_act2; t += BUILD_TPB) {
+    for (int id = tid; id < 6 * n_act2; id += BUILD_TPB) {
+        const int t = id / 6, a = id - 6 * t;
         const unsigned long long nr = rown[t];
-        const int C = (int)(nr >> 37) & 0x7ff, slot36 = 36 * (int)(nr >> 48);
+        const unsigned pb = (unsigned)(nr >> (6 * a)) & 63u;
+        if (!pb) continue;   // (also: states the owner does not have)
+        const int A = rowner[t], C = (int)(nr >> 37) & 0x7ff, slot36 = 36 * (int)(nr >> 48);
         const bool up = (nr >> 36) & 1ull;
-        int A;   // owner of entry t: the residue whose neighbour row contains it
-        {
-            int lo_r = 0, hi_r = nR - 1;
-            while (lo_r < hi_r) { const int mid = (lo_r + hi_r + 1) >> 1; if (astart[mid] <= t) lo_r = mid; else hi_r = mid - 1; }
-            A = lo_r;
-        }
-        const int nA = nrot[A], fA = rfirst[A], fC = rfirst[C];
-        const bool mA = nA > 1, mB = nrot[C] > 1, fold = mA && !mB;
-        for (int a = 0; a < nA; ++a) {
-            const unsigned pb = (unsigned)(nr >> (6 * a)) & 63u;
-            if (!pb) continue;
-            const int i = fA + a;
-            int at = rs[i] + (int)off[6 * t + a] + ((!up && fold) ? (int)lo_s[i] : 0);
-            // code of partner state b = cbase + b * cstep (matrix element / node whose marginal weights the entry)
-            int cbase, cstep;
-            if (mA && mB) { cbase = slot36 + (up ? a * 6 : a); cstep = up ? 1 : 6; }
-            else if (mA) { cbase = code_node(A * MAXR + a, true); cstep = 0; }
-            else if (mB) { cbase = code_node(C * MAXR, false); cstep = -2; }
-            else { cbase = CODE_SS; cstep = 0; }
+        const int fC = rfirst[C], i = rfirst[A] + a;
+        const bool mA = nrot[A] > 1, mB = nrot[C] > 1, fold = mA && !mB;
+        const int at = rs[i] + (int)off[6 * t + a] + ((!up && fold) ? (int)lo_s[i] : 0);
+        // code of partner state b = cbase + b * cstep (matrix element / node whose marginal weights the entry)
+        int cbase, cstep;
+        if (mA && mB) { cbase = slot36 + (up ? a * 6 : a); cstep = up ? 1 : 6; }
+        else if (mA) { cbase = code_node(A * MAXR + a, true); cstep = 0; }
+        else if (mB) { cbase = code_node(C * MAXR, false); cstep = -2; }
+        else { cbase = CODE_SS; cstep = 0; }
 #pragma unroll
-            for (int b = 0; b < MAXR; ++b)
-                if (pb & (1u << b)) {
-                    dj[at] = (unsigned short)(fC + b);
-                    code[at] = cbase + b * cstep;
-                    ++at;
-                }
+        for (int b = 0; b < MAXR; ++b) {
+            const int where = at + __popc(pb & ((1u << b) - 1u));
+            if (pb & (1u << b)) {
+                dj[where] = (unsigned short)(fC + b);
+                code[where] = cbase + b * cstep;
+            }
         }
     }
     for (int i = tid; i < nb; i += BUILD_TPB) P.lower[size_t(r) * nb + i] = lo_s[i];
-    sort_rows_desc_u16(nb, [&](int i) { return (int)ce_s[i]; }, P.order_e + size_t(r) * nb, hist);
-    sort_rows_desc_u16(nb, [&](int i) { return rs[i + 1] - rs[i]; }, P.order_d + size_t(r) * nb, hist);
+    // both row orders in one pass: two histograms side by side (keys clipped to 127), one set of barriers
+    {
+        int* hist_e = hist;          // [128]
+        int* hist_d = hist + 128;    // [128]
+        auto key_e = [&](int i) { return min((int)ce_s[i], 127); };
+        auto key_d = [&](int i) { return min(rs[i + 1] - rs[i], 127); };
+        for (int b = tid; b < 256; b += BUILD_TPB) hist[b] = 0;
+        __syncthreads();
+        for (int i = tid; i < nb; i += BUILD_TPB) { atomicAdd(&hist_e[key_e(i)], 1); atomicAdd(&hist_d[key_d(i)], 1); }
+        __syncthreads();
+        if (tid < 64) {   // warp 0: order_e, warp 1: order_d; offsets for falling keys (bin b starts after all larger bins)
+            int* h = tid < 32 ? hist_e : hist_d;
+            const int lane = tid & 31;
+            int sum = 0, v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { v[u] = h[127 - (lane * 4 + u)]; sum += v[u]; }
+            int incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(UB_FULL_MASK, incl, o); if (lane >= o) incl += t; }
+            int run = incl - sum;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { h[127 - (lane * 4 + u)] = run; run += v[u]; }
+        }
+        __syncthreads();
+        unsigned short* oe = P.order_e + size_t(r) * nb;
+        unsigned short* od = P.order_d + size_t(r) * nb;
+        for (int i = tid; i < nb; i += BUILD_TPB) {
+            oe[atomicAdd(&hist_e[key_e(i)], 1)] = (unsigned short)i;
+            od[atomicAdd(&hist_d[key_d(i)], 1)] = (unsigned short)i;
+        }
+    }
     return true;
 }
 
@@ -1906,7 +1934,7 @@ struct RotamerSidechain : PotentialNode {
     size_t build_bytes() const {
         const size_t nR = n_res, nW = n_words, nb = ig.n1;
         return 16 * size_t(blay.capa) + 8 * size_t(blay.capc) + 16 * (nb + nR) + 4 * (2 * nR * nW + blay.capc) + 4 * (6 * nR + 3) +
-               4 * nR * MAXR + 4 * (nb + 1 + 33 + 256) + 2 * (2 * nR * nW + 2 * nb) + 16;
+               4 * nR * MAXR + 4 * (nb + 1 + 33 + 256) + 2 * (2 * nR * nW + 2 * nb + 2 * size_t(blay.capa)) + 16;
     }
     RotamerDev dev() {
         RotamerDev P;
@@ -1914,6 +1942,8 @@ struct RotamerSidechain : PotentialNode {
         P.q.nka = nka; P.q.nk = nk; P.q.inv_dx = 1.f / knot_spacing; P.q.inv_dtheta = (nka - 3) / 2.f;
         P.n_bead = ig.n1; P.n_res = n_res; P.n_words = n_words; P.n_type = ig.n_type1;
         P.bead_res = d_bead_res.p; P.bead_rot = d_bead_rot.p; P.res_nrot = d_res_nrot.p; P.res_first = d_res_first.p;
+        P.loc_identity = 1;
+        for (int b = 0; b < ig.n1; ++b) if (ig.loc1[b] != b) P.loc_identity = 0;
         P.table = table.p;
         P.n_prob = (int)prob_nodes.size();
         for (int i = 0; i < P.n_prob; ++i) {
