@@ -334,3 +334,37 @@ def test_param_deriv_matches_oracle(cid):
     assert np.abs(be.get_param_deriv('rotamer', 0)).max() > 0
     be.close()
     ref.close()
+
+
+@pytest.mark.parametrize('env,cids', [({'UPSIDE_B200_NO_FAST_BUILD': '1'}, (1, 3, 5)),        # Verlet cache + k_refine + k_rot_prep
+                                      ({'UPSIDE_B200_BUILD_CAPS': '1.5,0.5'}, (1, 3)),          # k_rot_build with its arrays spilling to global memory
+                                      ({'UPSIDE_B200_DIRECT_ROWS': '1'}, (2, 3)),               # one-launch exact rows (the small-batch path) at any batch size
+                                      ({'UPSIDE_B200_DIRECT_ROWS': '0'}, (2,))])                # ... and the cached path at a small batch
+def test_alternative_list_paths_give_identical_lists(env, cids, monkeypatch):
+    """every way the engine can build its pair structures - the fast rotamer build, its global-memory spill twin, the general
+    Verlet / refine / prep path, the one-launch direct rows of the sparse graphs - must produce the same pair lists bit for
+    bit (they apply the same predicate to the same node outputs) and energies / forces equal to summation-order rounding"""
+    for cid in cids:
+        cfg = parity.CONFIGS[cid]
+        g = np.load(os.path.join(GOLD, 'config%d.npz' % cid)) if cid != 4 else None
+        pos = g['pos']
+        base = ue.BatchEngine(cfg, len(pos))
+        e0, d0 = base.evaluate(pos)
+        lists0 = {n: [base.pairlist(n, r) for r in range(len(pos))] for n in parity.PAIRLIST_NODES if n != 'backbone_pairs'}
+        m0 = [base.get_value_by_name('rotamer', 'bead_marginal', r) for r in range(len(pos))]
+        base.close()
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        alt = ue.BatchEngine(cfg, len(pos))
+        e1, d1 = alt.evaluate(pos)
+        for n, ls in lists0.items():
+            for r, l0 in enumerate(ls):
+                l1 = alt.pairlist(n, r)
+                assert l1.shape == l0.shape and (l1 == l0).all(), (env, cid, n, r)
+        for r in range(len(pos)):
+            assert np.abs(alt.get_value_by_name('rotamer', 'bead_marginal', r) - m0[r]).max() <= 1e-5
+        np.testing.assert_allclose(e1, e0, rtol=2e-6, atol=1e-4)
+        assert np.abs(d1 - d0).max() <= 2e-3
+        alt.close()
+        for k in env:
+            monkeypatch.delenv(k)
