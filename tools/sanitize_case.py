@@ -15,3 +15,20 @@ be.md_init(0.8, seed=1)
 be.md_run(4)
 print('finite', bool(np.isfinite(be.get_pos()).all()))
 be.close()
+# round 2: the spill twin of k_rot_build (tiny shared-memory capacities), the device ladder, host-buffer evaluation, checkpoint
+os.environ['UPSIDE_B200_BUILD_CAPS'] = '1.5,0.5'
+be = ue.BatchEngine(CONFIGS[1], 4)
+del os.environ['UPSIDE_B200_BUILD_CAPS']
+en2, _ = be.evaluate(np.repeat(pos[:1], 4, 0))
+print('spill-path energies', en2)
+T = np.array([0.7, 0.8, 0.9, 1.0], dtype='f4')
+be.md_init(T, seed=3)
+lad = ue.Ladder(be, ['0-1,2-3', '1-2'], T, seed=3)
+for k in range(3):
+    be.md_run(2, sync=False)
+    lad.attempt(2 * (k + 1))
+print('ladder', lad.state()[0])
+blob = be.checkpoint(); be.restore(blob); be.md_run(1)
+lad.close(); be.close()
+u = ue.Upside(CONFIGS[1])
+print('host-buffer evaluation', u.energy(pos[0]), float(np.abs(u.deriv(pos[0])).max()))
