@@ -338,11 +338,12 @@ def test_param_deriv_matches_oracle(cid):
 
 @pytest.mark.parametrize('env,cids', [({'UPSIDE_B200_NO_FAST_BUILD': '1'}, (1, 3, 5)),        # Verlet cache + k_refine + k_rot_prep
                                       ({'UPSIDE_B200_BUILD_CAPS': '1.5,0.5'}, (1, 3)),          # k_rot_build with its arrays spilling to global memory
-                                      ({'UPSIDE_B200_DIRECT_ROWS': '1'}, (2, 3)),               # one-launch exact rows (the small-batch path) at any batch size
-                                      ({'UPSIDE_B200_DIRECT_ROWS': '0'}, (2,))])                # ... and the cached path at a small batch
+                                      ({'UPSIDE_B200_FUSED_REBUILD': '0'}, (2, 3)),             # cache check / tiled rebuild / refine as three launches
+                                      ({'UPSIDE_B200_FUSED_REBUILD': '1'}, (5,)),               # in-CTA rebuild on a graph above its size threshold
+                                      ({'UPSIDE_B200_NO_VERLET_CACHE': '1'}, (1, 3))])          # all-pairs exact rows every evaluation
 def test_alternative_list_paths_give_identical_lists(env, cids, monkeypatch):
     """every way the engine can build its pair structures - the fast rotamer build, its global-memory spill twin, the general
-    Verlet / refine / prep path, the one-launch direct rows of the sparse graphs - must produce the same pair lists bit for
+    Verlet / refine / prep path, the fused and the three-launch Verlet cache of the sparse graphs, uncached all-pairs rows - must produce the same pair lists bit for
     bit (they apply the same predicate to the same node outputs) and energies / forces equal to summation-order rounding"""
     for cid in cids:
         cfg = parity.CONFIGS[cid]

@@ -220,12 +220,46 @@ __device__ __forceinline__ void refine_rows(int r, const RefineRole& R, float cu
     }
 }
 
+// Verlet cache handled INSIDE the refine kernel (round 2; k_cache_check and the rebuild launch of k_pairlist are gone from
+// the cached path): the CTA has the positions of both groups staged anyway, so it compares them with the positions at build
+// time itself; if an element has moved more than skin/2 (or nothing was built yet) it refreshes the cached positions and
+// rebuilds ITS replica's candidate rows on the spot - one thread per row against the staged partner positions (a broadcast
+// per partner) - before refining.  About one replica in fifteen rebuilds per evaluation; those CTAs run ~3x longer.
+struct VerletCache {
+    float* cposA; float* cposB;   // positions at build time, [B][n][4]
+    int* flag;                    // [B] 2 = never built
+    float max_move2, cand_cutoff2;
+    int excl, same_group;
+};
+// candidate rows of the elements of X against Y (cutoff + skin), column-major slices of eight as k_pairlist(colmajor) writes them
+__device__ __forceinline__ void rebuild_candidates(int r, const IGraphSide& X, const IGraphSide& Y, const float4* posX, const float4* posY,
+                                                   const RefineTable& T, const VerletCache& V, int* error_flag) {
+    unsigned short* base = const_cast<unsigned short*>(T.cand) + size_t(r) * T.Kc * X.n;
+    for (int i = threadIdx.x; i < X.n; i += blockDim.x) {
+        const float4 pi = posX[i];
+        const int idi = X.id[i];
+        int n = 0;
+        for (int j = 0; j < Y.n; ++j) {
+            const float4 pj = posY[j];
+            const float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
+            const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+            if (d2 < V.cand_cutoff2 && acceptable_id_pair(V.excl, idi, Y.id[j]) && !(V.same_group && j == i)) {
+                if (n < T.Kc) base[(size_t(n >> 3) * X.n + i) * 8 + (n & 7)] = (unsigned short)j;
+                ++n;
+            }
+        }
+        if (n > T.Kc) { atomicExch(error_flag, 1); n = T.Kc; }
+        const_cast<int*>(T.ccnt)[size_t(r) * X.n + i] = n;
+        for (int k = n; k & 7; ++k) base[(size_t(k >> 3) * X.n + i) * 8 + (k & 7)] = (unsigned short)Y.n;   // sentinel: the far-away position
+    }
+}
+
 // `which`: bit 0 = refine table 1, bit 1 = refine the transposed table (two groups only)
 #ifndef UB_REFINE_OCC
 #define UB_REFINE_OCC 3
 #endif
 template <int G>
-__global__ void __launch_bounds__(256, UB_REFINE_OCC) k_refine(IGraphSide A, IGraphSide Bs, int two_groups, int which, RefineTable T1, RefineTable T2, float cutoff2, int* error_flag) {
+__global__ void __launch_bounds__(256, UB_REFINE_OCC) k_refine(IGraphSide A, IGraphSide Bs, int two_groups, int which, RefineTable T1, RefineTable T2, float cutoff2, int* error_flag, VerletCache V) {
     extern __shared__ float4 sm_pos[];
     const int r = blockIdx.x;
     float4* posA = sm_pos;                                  // [A.n + 1], last = sentinel
@@ -244,19 +278,42 @@ __global__ void __launch_bounds__(256, UB_REFINE_OCC) k_refine(IGraphSide A, IGr
     RefinePrefetch F;
     refine_prefetch(r, R1, R1.t0, F);
     const float4 far = make_float4(1e18f, 1e18f, 1e18f, 0.f);
+    // stage the positions and, on the way, compare them with the positions the candidate rows were built from
+    int moved = V.flag ? V.flag[r] == 2 : 0;
     for (int i = threadIdx.x; i < A.n; i += blockDim.x) {
         const float* p = A.out + (size_t(r) * A.n_node + A.loc[i]) * A.wp;
-        posA[i] = make_float4(p[0], p[1], p[2], 0.f);
+        const float4 v = make_float4(p[0], p[1], p[2], 0.f);
+        posA[i] = v;
+        if (V.flag) {
+            const float4 q = reinterpret_cast<const float4*>(V.cposA)[size_t(r) * A.n + i];
+            const float dx = v.x - q.x, dy = v.y - q.y, dz = v.z - q.z;
+            moved |= V.max_move2 < dx * dx + dy * dy + dz * dz;
+        }
     }
     if (threadIdx.x == 0) posA[A.n] = far;
     if (two_groups) {
         for (int i = threadIdx.x; i < Bs.n; i += blockDim.x) {
             const float* p = Bs.out + (size_t(r) * Bs.n_node + Bs.loc[i]) * Bs.wp;
-            posB[i] = make_float4(p[0], p[1], p[2], 0.f);
+            const float4 v = make_float4(p[0], p[1], p[2], 0.f);
+            posB[i] = v;
+            if (V.flag) {
+                const float4 q = reinterpret_cast<const float4*>(V.cposB)[size_t(r) * Bs.n + i];
+                const float dx = v.x - q.x, dy = v.y - q.y, dz = v.z - q.z;
+                moved |= V.max_move2 < dx * dx + dy * dy + dz * dz;
+            }
         }
         if (threadIdx.x == 0) posB[Bs.n] = far;
     }
-    __syncthreads();
+    moved = __syncthreads_or(moved);   // (also: the staged positions are complete)
+    if (moved) {   // uniform: refresh the cache of this replica, then rebuild its candidate rows
+        for (int i = threadIdx.x; i < A.n; i += blockDim.x) reinterpret_cast<float4*>(V.cposA)[size_t(r) * A.n + i] = posA[i];
+        if (two_groups) for (int i = threadIdx.x; i < Bs.n; i += blockDim.x) reinterpret_cast<float4*>(V.cposB)[size_t(r) * Bs.n + i] = posB[i];
+        if (!two_groups || (which & 1)) rebuild_candidates(r, A, two_groups ? Bs : A, posA, posB, T1, V, error_flag);
+        if (two_groups && (which & 2)) rebuild_candidates(r, Bs, A, posB, posA, T2, V, error_flag);
+        if (threadIdx.x == 0) V.flag[r] = 0;
+        __syncthreads();   // this CTA's candidate rows are visible to all its threads
+        refine_prefetch(r, R1, R1.t0, F);
+    }
     refine_rows(r, R1, cutoff2, error_flag, F);
     if (both) {
         refine_prefetch(r, R2, R2.t0, F);
@@ -268,117 +325,6 @@ __global__ void __launch_bounds__(256, UB_REFINE_OCC) k_refine(IGraphSide A, IGr
 // was measured for the sparse asymmetric tables and lost: 803 us against 730 us per evaluation for all pair lists.  A
 // candidate costs five global loads there (index, two element rows behind their `loc` indirection) against one shared-memory
 // gather here, and candidates outnumber elements ten to one.)
-
-// k_rows_direct: exact ELL rows of an asymmetric graph straight from the positions - ONE launch per evaluation, no Verlet
-// cache (no k_cache_check, no candidate rebuild, no k_refine, no candidate tables).  The elements of group 2 come in
-// CLUSTERS: runs of consecutive elements with the same id, i.e. the side-chain beads of one residue (its rotamer states, a
-// few Angstrom apart), at most eight to a cluster.  One CTA per replica:
-//   1. both groups staged in shared memory (x, y, z, id); one bounding sphere per cluster;
-//   2. a warp takes an element of group 1, its lanes take the clusters: sphere test (the element is a broadcast, the spheres
-//      consecutive 16-byte words: conflict-free), the id exclusion applied once per cluster; the clusters that pass are then
-//      taken four at a time by the four 8-lane quarters of the warp, one lane per member, with the reference's exact
-//      predicate (interaction_graph.h:223-244); a hit sets a bit in the shared-memory bitmap of every wanted table (table 1:
-//      rows of group 1; table 2: rows of group 2) - integer atomics, order-independent;
-//   3. one thread per row reads its bitmap row back in ascending order into the ELL table.
-// Deterministic and exact; the random 16-byte shared-memory gathers over cached candidate indices that bound k_refine are
-// gone (the members of a cluster are consecutive words).
-struct ClusterDev { const int* start; int n_cl; };   // cluster c = elements [start[c], start[c+1]) of group 2
-constexpr int ROWS_TPB = 512;
-static __global__ void __launch_bounds__(ROWS_TPB) k_rows_direct(IGraphSide A, IGraphSide Bs, ClusterDev C, int which, unsigned short* __restrict__ nbr1,
-                                                          int* __restrict__ cnt1, int K1, unsigned short* __restrict__ nbr2, int* __restrict__ cnt2,
-                                                          int K2, float cutoff, int excl, int* error_flag) {
-    extern __shared__ float4 sm_pos[];
-    const int r = blockIdx.x, n1 = A.n, n2 = Bs.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int nW2 = (n2 + 31) >> 5, nW1 = (n1 + 31) >> 5;
-    float4* posA = sm_pos;                    // [n1] x,y,z,id
-    float4* posB = posA + n1;                 // [n2]
-    float4* sph = posB + n2;                  // [n_cl] centre, radius
-    int* cstart = reinterpret_cast<int*>(sph + C.n_cl);                     // [n_cl+1]
-    unsigned* bm1 = reinterpret_cast<unsigned*>(cstart + C.n_cl + 1);       // [n1][nW2]  (which & 1)
-    unsigned* bm2 = bm1 + ((which & 1) ? size_t(n1) * nW2 : 0);             // [n2][nW1]  (which & 2)
-    for (int i = tid; i < n1; i += ROWS_TPB) {
-        const float* p = A.out + (size_t(r) * A.n_node + A.loc[i]) * A.wp;
-        posA[i] = make_float4(p[0], p[1], p[2], __int_as_float(A.id[i]));
-    }
-    for (int j = tid; j < n2; j += ROWS_TPB) {
-        const float* p = Bs.out + (size_t(r) * Bs.n_node + Bs.loc[j]) * Bs.wp;
-        posB[j] = make_float4(p[0], p[1], p[2], __int_as_float(Bs.id[j]));
-    }
-    for (int c = tid; c <= C.n_cl; c += ROWS_TPB) cstart[c] = C.start[c];
-    const int n_bm = ((which & 1) ? n1 * nW2 : 0) + ((which & 2) ? n2 * nW1 : 0);
-    for (int k = tid; k < n_bm; k += ROWS_TPB) bm1[k] = 0u;
-    __syncthreads();
-    for (int c = tid; c < C.n_cl; c += ROWS_TPB) {
-        const int j0 = cstart[c], j1 = cstart[c + 1];
-        float cx = 0.f, cy = 0.f, cz = 0.f;
-        for (int j = j0; j < j1; ++j) { const float4 p = posB[j]; cx += p.x; cy += p.y; cz += p.z; }
-        const float inv = 1.f / float(j1 - j0);
-        cx *= inv; cy *= inv; cz *= inv;
-        float r2 = 0.f;
-        for (int j = j0; j < j1; ++j) { const float4 p = posB[j]; const float dx = p.x - cx, dy = p.y - cy, dz = p.z - cz; r2 = fmaxf(r2, dx * dx + dy * dy + dz * dz); }
-        sph[c] = make_float4(cx, cy, cz, sqrtf(r2) + cutoff + 1e-3f);   // reach of the cluster: slack >> rounding
-    }
-    __syncthreads();
-    const float cutoff2 = cutoff * cutoff;
-    const int quarter = lane >> 3, member = lane & 7;
-    for (int i = warp; i < n1; i += ROWS_TPB / 32) {
-        const float4 a = posA[i];
-        const int ida = __float_as_int(a.w);
-        for (int c0 = 0; c0 < C.n_cl; c0 += 32) {
-            const int c = c0 + lane;
-            bool pass = false;
-            if (c < C.n_cl) {
-                const float4 s = sph[c];
-                const float dx = a.x - s.x, dy = a.y - s.y, dz = a.z - s.z;
-                // all members of a cluster share the id: the exclusion is decided once per cluster
-                pass = dx * dx + dy * dy + dz * dz < s.w * s.w && acceptable_id_pair(excl, ida, __float_as_int(posB[cstart[c]].w));
-            }
-            unsigned hits = __ballot_sync(UB_FULL_MASK, pass);
-            while (hits) {   // four passing clusters per step, one per 8-lane quarter, one lane per member
-                unsigned h = hits;
-                int mine = -1;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    if (h) { const int l = __ffs(h) - 1; h &= h - 1; if (q == quarter) mine = c0 + l; }
-                }
-                hits = h;
-                if (mine >= 0) {
-                    const int j = cstart[mine] + member;
-                    if (j < cstart[mine + 1]) {
-                        const float4 b = posB[j];
-                        const float dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z;   // group 1 minus group 2 (interaction_graph.h:230-232)
-                        const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-                        if (d2 < cutoff2) {
-                            if (which & 1) atomicOr(&bm1[i * nW2 + (j >> 5)], 1u << (j & 31));
-                            if (which & 2) atomicOr(&bm2[j * nW1 + (i >> 5)], 1u << (i & 31));
-                        }
-                    }
-                }
-            }
-        }
-    }
-    __syncthreads();
-    const int rows1 = (which & 1) ? n1 : 0, rows2 = (which & 2) ? n2 : 0;
-    for (int t = tid; t < rows1 + rows2; t += ROWS_TPB) {
-        const bool second = t >= rows1;
-        const int row = second ? t - rows1 : t;
-        const unsigned* bits = second ? bm2 + size_t(row) * nW1 : bm1 + size_t(row) * nW2;
-        const int nW = second ? nW1 : nW2, K = second ? K2 : K1;
-        unsigned short* out = second ? nbr2 + (size_t(r) * n2 + row) * K2 : nbr1 + (size_t(r) * n1 + row) * K1;
-        int n = 0;
-        for (int w = 0; w < nW; ++w) {
-            unsigned m = bits[w];
-            while (m) {
-                const int k = (w << 5) + __ffs(m) - 1;
-                m &= m - 1;
-                if (n < K) out[n] = (unsigned short)k;
-                ++n;
-            }
-        }
-        if (n > K) { atomicExch(error_flag, 1); n = K; }
-        (second ? cnt2 + size_t(r) * n2 : cnt1 + size_t(r) * n1)[row] = n;
-    }
-}
 
 // ---- row scheduling ---------------------------------------------------------------------------------------
 // Counting sort of n rows by descending key (row length, clipped to 255) into order[0..n).  Lane groups that take
@@ -617,11 +563,7 @@ struct IGraphHost {
     // which exact tables the owning node's kernels read (asymmetric graphs; set before allocate()): a table nobody gathers
     // from is neither rebuilt nor refined
     bool need1 = true, need2 = true;
-    // direct rows (k_rows_direct): asymmetric graphs whose shared-memory plan fits; clusters of group 2
-    bool direct = false;
-    size_t smem_direct = 0;
-    std::vector<int> h_cluster_start;
-    DevBuf<int> d_cluster_start;
+    bool fused_rebuild = true;   // cache check + rebuild inside k_refine (graphs of up to 250 k element pairs)
     bool lists = true;   // false: the owning node builds its own pair structure (rotamer fast build); no tables are allocated
     Engine* engine = nullptr;
 

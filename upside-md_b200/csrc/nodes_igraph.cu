@@ -69,29 +69,6 @@ void IGraphHost::allocate(Engine* e) {
         cnt2.alloc(size_t(e->n_rep) * n2);
     }
     if (const char* s = getenv("UPSIDE_B200_NO_VERLET_CACHE")) use_cache = atoi(s) == 0;
-    // SMALL BATCHES: asymmetric graphs build their exact rows in one launch from the positions (k_rows_direct) instead of the
-    // three launches of the cached path - with a few replicas per GPU an evaluation is a chain of launch latencies, and two of
-    // the sparse graphs sit on its critical path (76 residues x 1 replica: 214 -> 199 us per evaluation).  From a few
-    // hundred replicas on the cached path does less work per list (4096 x 100 residues: 461 us against 764 us for the four
-    // sparse graphs).  UPSIDE_B200_DIRECT_ROWS=0/1 overrides the batch-size rule.
-    bool want_direct = e->n_rep <= 64;
-    if (const char* dr = getenv("UPSIDE_B200_DIRECT_ROWS")) want_direct = atoi(dr) != 0;
-    if (!symmetric && use_cache && want_direct) {
-        h_cluster_start.assign(1, 0);   // clusters of group 2: runs of consecutive elements with one id, at most eight each
-        for (int j = 1; j <= n2; ++j)
-            if (j == n2 || id2[j] != id2[j - 1] || j - h_cluster_start.back() == 8) h_cluster_start.push_back(j);
-        const size_t n_cl = h_cluster_start.size() - 1, nW1 = (n1 + 31) / 32, nW2 = (n2 + 31) / 32;
-        smem_direct = sizeof(float4) * (size_t(n1) + n2 + n_cl) + 4 * (n_cl + 1) + 4 * ((need1 ? size_t(n1) * nW2 : 0) + (need2 ? size_t(n2) * nW1 : 0)) + 16;
-        int device_smem = 0;
-        UB_CUDA(cudaDeviceGetAttribute(&device_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, e->device));
-        // (beyond ~110 KB only one CTA fits an SM and the cached path is the better one)
-        if (smem_direct <= std::min<size_t>(device_smem, 110 * 1024)) {
-            direct = true;
-            use_cache = false;
-            d_cluster_start.upload(h_cluster_start);
-            UB_CUDA(cudaFuncSetAttribute(k_rows_direct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_direct, 48 * 1024)));
-        }
-    }
     if (use_cache) {
         // The skin only trades rebuild frequency against candidates per refine; the exact list does not depend on it.  The
         // reference uses 1 + 0.2*cutoff (cache_buffer, interaction_graph.h:395-396); here an all-pairs rebuild costs more
@@ -125,6 +102,8 @@ void IGraphHost::allocate(Engine* e) {
             UB_CUDA(cudaFuncSetAttribute(k_refine<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
         }
         flag.upload(std::vector<int>(e->n_rep, 2));   // 2 = never built
+        fused_rebuild = double(n1) * n2 <= 2.5e5;
+        if (const char* fr = getenv("UPSIDE_B200_FUSED_REBUILD")) fused_rebuild = atoi(fr) != 0;
         rep_list.alloc(e->n_rep);
         n_list.alloc(1);
     }
@@ -150,13 +129,6 @@ void IGraphHost::build(cudaStream_t s) {
     constexpr int RGL = 8;
     if (!n1 || !n2) return;
     const int B = engine->n_rep;
-    if (direct) {
-        const int which = (need1 ? 1 : 0) | (need2 ? 2 : 0);
-        ClusterDev C{d_cluster_start.p, (int)h_cluster_start.size() - 1};
-        k_rows_direct<<<B, ROWS_TPB, smem_direct, s>>>(d.s1, d.s2, C, which, d.nbr1, d.cnt1, d.K1, d.nbr2, d.cnt2, d.K2, d.cutoff, d.excl, d.error_flag);
-        engine->mark(s, "(pairlist)");
-        return;
-    }
     if (!use_cache) {
         if (need1)
             k_pairlist<TILE><<<dim3((n1 + TILE - 1) / TILE, B), TILE, 0, s>>>(d.s1, d.s2, d.nbr1, d.cnt1, d.K1, d.cutoff2, d.excl,
@@ -167,24 +139,33 @@ void IGraphHost::build(cudaStream_t s) {
         return;
     }
     const float cc = cutoff + skin;
-    const float max_move2 = (0.5f * skin) * (0.5f * skin);
-    UB_CUDA(cudaMemsetAsync(n_list.p, 0, sizeof(int), s));
-    k_cache_check<<<B, 128, 0, s>>>(d.s1, d.s2, symmetric ? 0 : 1, cpos1.p, cpos2.p, max_move2, flag.p, rep_list.p, n_list.p);
-    // rebuilds touch only the flagged replicas: a modest grid strides over the compacted list
-    const int gy = std::min(B, 592);
-    if (need1)
-        k_pairlist<TILE><<<dim3((n1 + TILE - 1) / TILE, gy), TILE, 0, s>>>(d.s1, d.s2, cand1.p, ccnt1.p, Kc1, cc * cc, d.excl, symmetric,
-                                                                           1, d.error_flag, rep_list.p, n_list.p, 1);
-    if (!symmetric && need2)
-        k_pairlist<TILE><<<dim3((n2 + TILE - 1) / TILE, gy), TILE, 0, s>>>(d.s2, d.s1, cand2.p, ccnt2.p, Kc2, cc * cc, d.excl, 0, 0,
-                                                                           d.error_flag, rep_list.p, n_list.p, 1);
     RefineTable T1{cand1.p, ccnt1.p, Kc1, d.nbr1, d.cnt1, d.K1};
     RefineTable T2{cand2.p, ccnt2.p, Kc2, symmetric ? nullptr : d.nbr2, symmetric ? nullptr : d.cnt2, d.K2};
     size_t smem = sizeof(float4) * size_t(symmetric ? n1 + 1 : n1 + n2 + 2);
     const int which = symmetric ? 1 : (need1 ? 1 : 0) | (need2 ? 2 : 0);
     const int rows = which == 3 ? ((n1 + 31) & ~31) + n2 : (which == 2 ? n2 : n1);
     const int tpb = std::min(256, std::max(64, (rows + 31) & ~31));   // smaller blocks keep more of them resident
-    k_refine<RGL><<<B, tpb, smem, s>>>(d.s1, d.s2, symmetric ? 0 : 1, which, T1, T2, d.cutoff2, d.error_flag);
+    if (fused_rebuild) {
+        // cache check, rebuild of the replicas that need it and refine in ONE launch (see VerletCache)
+        VerletCache V{cpos1.p, cpos2.p, flag.p, (0.5f * skin) * (0.5f * skin), cc * cc, d.excl, symmetric ? 1 : 0};
+        k_refine<RGL><<<B, tpb, smem, s>>>(d.s1, d.s2, symmetric ? 0 : 1, which, T1, T2, d.cutoff2, d.error_flag, V);
+    } else {
+        // large graphs: an all-pairs rebuild inside one CTA would hold up its whole launch (300 residues: 1.2 M pair tests per
+        // replica); the flagged replicas are rebuilt by a tiled kernel over many CTAs instead
+        const float max_move2 = (0.5f * skin) * (0.5f * skin);
+        constexpr int TILE = 128;
+        UB_CUDA(cudaMemsetAsync(n_list.p, 0, sizeof(int), s));
+        k_cache_check<<<B, 128, 0, s>>>(d.s1, d.s2, symmetric ? 0 : 1, cpos1.p, cpos2.p, max_move2, flag.p, rep_list.p, n_list.p);
+        const int gy = std::min(B, 592);
+        if (need1)
+            k_pairlist<TILE><<<dim3((n1 + TILE - 1) / TILE, gy), TILE, 0, s>>>(d.s1, d.s2, cand1.p, ccnt1.p, Kc1, cc * cc, d.excl, symmetric,
+                                                                               1, d.error_flag, rep_list.p, n_list.p, 1);
+        if (!symmetric && need2)
+            k_pairlist<TILE><<<dim3((n2 + TILE - 1) / TILE, gy), TILE, 0, s>>>(d.s2, d.s1, cand2.p, ccnt2.p, Kc2, cc * cc, d.excl, 0, 0,
+                                                                               d.error_flag, rep_list.p, n_list.p, 1);
+        VerletCache V{nullptr, nullptr, nullptr, 0.f, 0.f, 0, 0};
+        k_refine<RGL><<<B, tpb, smem, s>>>(d.s1, d.s2, symmetric ? 0 : 1, which, T1, T2, d.cutoff2, d.error_flag, V);
+    }
     engine->mark(s, "(pairlist)");
 }
 
