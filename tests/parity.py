@@ -22,6 +22,7 @@ CONFIGS = {
     6: os.path.join(ROOT, 'configs', 'config6_restraints_20res.up'),
     9: os.path.join(ROOT, 'configs', 'config9_coupling_20res.up'),     # config 1 + uniform_transform / linear_coupling nodes
     8: os.path.join(ROOT, 'configs', 'config8_radial_20res.up'),       # config 1 + radial / hbond_sc_radial pair nodes
+    10: os.path.join(ROOT, 'configs', 'config10_two_chains_40res.up'),  # two chains: chain_break group, bonded terms split, a jump move per chain
     7: os.path.join(ROOT, 'configs', 'config7_concat_20res.up'),       # config 1 + slice/constant/concat -> tether springs   # config 1 + restraint / plumbing nodes (tools/make_restraint_config.py)
 }
 PAIRLIST_NODES = ['rotamer', 'hbond_coverage', 'hbond_coverage_hydrophobe', 'environment_coverage', 'protein_hbond',

@@ -108,6 +108,45 @@ def test_cli_detailed_loggers_match_reference_binary(tmp_path):
         assert np.isfinite(np.array(oa['rotamer_free_energy'].data)).all()
 
 
+def test_cli_extensive_loggers_match_reference_binary(tmp_path):
+    """--log-level extensive adds `virtual` (hbond.cpp:48-56), `environment_coverage` (environment.cpp:77-82) and
+    `placement_pos` (placement.cpp:254-261).  Every placement node asks for the same dataset name, so the reference cannot
+    run a full ff_1 configuration at this level (its second H5Dcreate fails) - and neither does the CLI here; a backbone-only
+    configuration runs on both and the logged H / O site positions agree."""
+    import subprocess
+    g = np.load(os.path.join(GOLD, 'config1.npz'))
+    full = _write_inputs(tmp_path, g['start'][:1] if 'start' in g.files else g['pos'][:1])[0]
+    args = ['--duration', '0.2', '--frame-interval', '0.054', '--temperature', '0.8', '--seed', '7', '--log-level', 'extensive']
+    exe = os.path.join(parity.ROOT, 'oracle', '_ref', 'upside_ref')
+    env = dict(os.environ, OMP_NUM_THREADS='1')
+    ref_copy = str(tmp_path / 'full_ref.up')
+    shutil.copy(full, ref_copy)
+    assert subprocess.run([exe] + args + [ref_copy], capture_output=True, text=True, env=env).returncode != 0
+    with pytest.raises(RuntimeError):      # "while adding '...', logger placement_pos exists already", return code 2
+        ue.in_process_upside(args + [full], verbose=False)
+    # backbone only: springs, Rama map, backbone pairs, H-bond inference and energy - no placement node
+    t = h5lite.load(full)
+    pot = t['input/potential']
+    keep = {'dist_spring', 'angle_spring', 'dihedral_spring', 'rama_coord', 'rama_map_pot', 'rama_map_pot_ref', 'affine_alignment',
+            'backbone_pairs', 'infer_H_O', 'protein_hbond', 'hbond_energy'}
+    for name in list(pot.children):
+        if name not in keep:
+            del pot.children[name]
+    if 'output' in t.children:
+        del t.children['output']
+    mine, theirs = str(tmp_path / 'bb.up'), str(tmp_path / 'bb_ref.up')
+    h5lite.save(t, mine)
+    shutil.copy(mine, theirs)
+    r = subprocess.run([exe] + args + [theirs], capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stderr
+    ue.in_process_upside(args + [mine], verbose=False)
+    oa, ob = h5lite.load(mine)['output'], h5lite.load(theirs)['output']
+    assert sorted(oa.children) == sorted(ob.children) and 'virtual' in oa.children
+    da, db = np.array(oa['virtual'].data), np.array(ob['virtual'].data)
+    assert da.shape == db.shape and da.dtype == db.dtype
+    assert np.abs(da[:2] - db[:2]).max() <= 2e-3
+
+
 def test_cli_errors_and_flags(tmp_path):
     g = np.load(os.path.join(GOLD, 'cli_replex.npz'))
     paths = _write_inputs(tmp_path, g['start'][:2])

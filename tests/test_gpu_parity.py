@@ -47,7 +47,7 @@ def _check_report(rep):
 
 
 @pytest.mark.skipif(not ref_engine.available('pinned'), reason='oracle/_ref not shipped')
-@pytest.mark.parametrize('cid,n_rep', [(1, 4), (2, 2), (3, 3), (4, 2), (5, 2), (6, 3), (8, 3), (9, 3)])
+@pytest.mark.parametrize('cid,n_rep', [(1, 4), (2, 2), (3, 3), (4, 2), (5, 2), (6, 3), (8, 3), (9, 3), (10, 3)])
 def test_every_node_matches_oracle(cid, n_rep):
     cfg = parity.CONFIGS[cid]
     pos = parity.test_positions(cfg, n_rep + 1)[1:]     # relaxed structures (see DESIGN.md on /input/pos itself)
@@ -173,17 +173,22 @@ def test_monte_carlo_pivot_moves_match_reference(cid):
 
 
 @pytest.mark.skipif(not ref_engine.available('pinned'), reason='oracle/_ref not shipped')
-def test_monte_carlo_jump_moves_match_reference(tmp_path):
+@pytest.mark.parametrize('cid', [5, 10])
+def test_monte_carlo_jump_moves_match_reference(tmp_path, cid):
     """rigid-body jump moves (JumpSampler, src/monte_carlo_sampler.cpp:203-251) next to the pivot moves: config 5 (the membrane
     potential makes the energy depend on where the molecule sits, so the Metropolis test of a jump is not vacuous) with a
-    /input/jump_moves group over the whole chain; same seeds and rounds on both engines => the same proposals (translation
+    /input/jump_moves group over the whole chain, and the two-chain config 10 with its own move per chain (the chains see
+    each other through the pair potentials); same seeds and rounds on both engines => the same proposals (translation
     or rotation from the reference's random stream), the same decisions, the same coordinates"""
     from upside_md_b200 import config
-    cfg = str(tmp_path / 'config5_jump.up')
-    w = config.ConfigWriter.from_file(parity.CONFIGS[5])
-    w.write_jump_moves([[0, w.n_atom]], 1.5, 0.4)
-    w.save(cfg)
-    pos = parity.test_positions(parity.CONFIGS[5], 7, relax_rounds=20)[1:]
+    if cid == 5:
+        cfg = str(tmp_path / 'config5_jump.up')
+        w = config.ConfigWriter.from_file(parity.CONFIGS[5])
+        w.write_jump_moves([[0, w.n_atom]], 1.5, 0.4)
+        w.save(cfg)
+    else:
+        cfg = parity.CONFIGS[cid]
+    pos = parity.test_positions(parity.CONFIGS[cid], 7, relax_rounds=20)[1:]
     rounds = list(range(5, 15))
     ref_pos, ref_stats = ref_engine.mc_steps(cfg, pos, 0.8, 42, rounds[0], len(rounds))
     be = ue.BatchEngine(cfg, len(pos))

@@ -53,6 +53,27 @@ def test_config_files_have_reference_schema():
         assert ((ids & 15) < ((ids >> 4) & 15)).all()
 
 
+def test_chain_break_writer():
+    """two-chain configuration (config 10): the chain_break group of upside_config.py:1440-1441, no donor / acceptor on the
+    residues next to the break (:1445-1449), bonded terms and Rama coordinates confined to one chain, one jump move per chain"""
+    t = h5lite.load(parity.CONFIGS[10])
+    cfr = t['input/chain_break/chain_first_residue'].data
+    assert cfr.tolist() == [20]
+    pot = t['input/potential']
+    for site in ('donors', 'acceptors'):
+        assert not set(pot['infer_H_O/%s/residue' % site].data.tolist()) & {19, 20}
+    for node in ('dist_spring', 'angle_spring', 'dihedral_spring'):
+        ids = pot[node + '/id'].data
+        assert ((ids // 3 >= 20) == (ids[:, :1] // 3 >= 20)).all(), node
+    assert len(pot['dist_spring/id'].data) == 3 * 40 - 2
+    rc = pot['rama_coord/id'].data
+    assert rc[19, 4] == -1 and rc[20, 0] == -1 and (rc[19, :4] >= 0).all() and (rc[20, 1:] >= 0).all()
+    assert t['input/jump_moves/atom_range'].data.tolist() == [[0, 60], [60, 120]]
+    w = config.ConfigWriter(['ALA'] * 6, np.zeros((18, 3)))
+    with pytest.raises(ValueError):
+        w.write_chain_break([4, 2])
+
+
 def test_random_initial_config_geometry():
     pos = config.random_initial_config(30, np.random.default_rng(1))
     d = np.linalg.norm(pos[1:] - pos[:-1], axis=1)

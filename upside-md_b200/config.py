@@ -264,31 +264,46 @@ class ConfigWriter:
         self.arr(g, 'bonded_atoms', np.concatenate((old['bonded_atoms'], np.zeros(len(pairs), dtype='int')), axis=0))
 
     # -- bonded (upside_config.py:480-525) -------------------------------------------------------
+    def _within_chain(self, atom_ids):
+        """rows of an atom-index table that stay inside one chain (all rows unless write_chain_break was asked to split the
+        bonded terms)"""
+        ids = np.asarray(atom_ids)
+        if not getattr(self, 'split_bonded', False):
+            return np.ones(len(ids), dtype=bool)
+        chain = np.searchsorted(self.chain_first_residue, ids // 3, side='right')
+        return (chain == chain[:, :1]).all(axis=1)
+
     def write_dist_spring(self, bond_stiffness=48.):
         g = self.group('dist_spring', ['pos'])
         i = np.arange(self.n_atom - 1)
         eq = np.zeros(len(i))
         eq[0::3], eq[1::3], eq[2::3] = 1.453, 1.526, 1.300
-        self.arr(g, 'id', np.column_stack((i, i + 1)))
-        self.arr(g, 'equil_dist', eq)
-        self.arr(g, 'spring_const', bond_stiffness * np.ones(len(i)))
-        self.arr(g, 'bonded_atoms', np.ones(len(i), dtype='int'))
+        ids = np.column_stack((i, i + 1))
+        keep = self._within_chain(ids)
+        self.arr(g, 'id', ids[keep])
+        self.arr(g, 'equil_dist', eq[keep])
+        self.arr(g, 'spring_const', bond_stiffness * np.ones(keep.sum()))
+        self.arr(g, 'bonded_atoms', np.ones(keep.sum(), dtype='int'))
 
     def write_angle_spring(self, angle_stiffness=175.):
         g = self.group('angle_spring', ['pos'])
         i = np.arange(self.n_atom - 2)
         eq = np.zeros(len(i))
         eq[0::3], eq[1::3], eq[2::3] = np.cos(109.5 * deg), np.cos(120.0 * deg), np.cos(120.0 * deg)
-        self.arr(g, 'id', np.column_stack((i, i + 2, i + 1)))
-        self.arr(g, 'equil_dist', eq)
-        self.arr(g, 'spring_const', angle_stiffness * np.ones(len(i)))
+        ids = np.column_stack((i, i + 2, i + 1))
+        keep = self._within_chain(ids)
+        self.arr(g, 'id', ids[keep])
+        self.arr(g, 'equil_dist', eq[keep])
+        self.arr(g, 'spring_const', angle_stiffness * np.ones(keep.sum()))
 
     def write_dihedral_spring(self):
         g = self.group('dihedral_spring', ['pos'])
         i = np.arange(1, self.n_atom - 3, 3)
-        self.arr(g, 'id', np.column_stack((i, i + 1, i + 2, i + 3)))
-        self.arr(g, 'equil_dist', np.where(self.fasta[1:] == 'CPR', 0. * deg, 180. * deg))
-        self.arr(g, 'spring_const', 30.0 * np.ones(len(i)))
+        ids = np.column_stack((i, i + 1, i + 2, i + 3))
+        keep = self._within_chain(ids)
+        self.arr(g, 'id', ids[keep])
+        self.arr(g, 'equil_dist', np.where(self.fasta[1:] == 'CPR', 0. * deg, 180. * deg)[keep])
+        self.arr(g, 'spring_const', 30.0 * np.ones(keep.sum()))
 
     # -- coordinate nodes -------------------------------------------------------------------------
     def write_rama_coord(self):
@@ -297,6 +312,10 @@ class ConfigWriter:
         n = 3 * np.arange(self.n_res)
         idx = np.column_stack((n - 1, n, n + 1, n + 2, n + 3))
         idx[idx >= self.n_atom] = -1
+        if getattr(self, 'split_bonded', False):   # phi / psi of a chain end have no partner atom, as at the termini
+            res = np.arange(self.n_res)[:, None]
+            chain = np.searchsorted(self.chain_first_residue, np.where(idx >= 0, idx // 3, res), side='right')
+            idx[chain != np.searchsorted(self.chain_first_residue, res, side='right')] = -1
         self.arr(g, 'id', idx)
 
     def write_affine_alignment(self):
@@ -599,6 +618,35 @@ class ConfigWriter:
         self.arr(g, 'sigma_trans', np.broadcast_to(np.asarray(sigma_trans, dtype='f4'), (len(atom_ranges),)).copy())
         self.arr(g, 'sigma_rot', np.broadcast_to(np.asarray(sigma_rot, dtype='f4'), (len(atom_ranges),)).copy())
 
+    def write_chain_break(self, chain_first_residue, rl_chains=None, split_bonded=False):
+        """/input/chain_break as upside_config.py:1413-1449 writes it for --chain-break-from-file: the first residue of every
+        chain after the first (what extract_vtf.py / mdtraj_upside.py read back).  Returns the residues next to the breaks,
+        which that script adds to --hbond-exclude-residues (no donor / acceptor is inferred across a break).  Like the
+        reference generator this leaves the bonded terms alone unless ``split_bonded`` is set: then the bond / angle / dihedral
+        springs and the Rama coordinates written AFTER this call skip the atoms of another chain.  Call it first."""
+        cfr = np.asarray(chain_first_residue, dtype='i4').reshape(-1)
+        if cfr.size and (np.any(np.diff(cfr) <= 0) or cfr[0] <= 0 or cfr[-1] >= self.n_res):
+            raise ValueError('chain_first_residue must be ascending and inside (0, n_res)')
+        self.chain_first_residue = cfr
+        self.split_bonded = bool(split_bonded) and cfr.size > 0
+        if cfr.size:
+            g = self.root['input'].create_group('chain_break')
+            self.arr(g, 'chain_first_residue', cfr)
+            if rl_chains is not None:
+                self.arr(g, 'rl_chains', np.asarray(rl_chains, dtype='i4'))
+        return sorted({int(i) + j for i in cfr for j in (-1, 0)})
+
+    def chain_endpts(self, i):
+        """[first residue, first residue of the next chain) of chain i (upside_config.py:1184-1196)"""
+        cfr = getattr(self, 'chain_first_residue', np.zeros(0, dtype='i4'))
+        bounds = [0] + [int(x) for x in cfr] + [self.n_res]
+        return bounds[i], bounds[i + 1]
+
+    def write_jump_moves_per_chain(self, sigma_trans, sigma_rot):
+        """one rigid-body jump move per chain of a multi-chain configuration"""
+        n_chain = len(getattr(self, 'chain_first_residue', ())) + 1
+        self.write_jump_moves([[3 * a, 3 * b] for a, b in (self.chain_endpts(i) for i in range(n_chain))], sigma_trans, sigma_rot)
+
     def save(self, path):
         h5lite.save(self.root, path)
 
@@ -622,14 +670,19 @@ def load_rama_reference(path):
 
 
 def write_ff1_config(path, fasta, pos, sidechain_lib, environment_lib, hbond_energy, rama_reference,
-                     rama_pot=None, membrane=None, membrane_thickness=30., compress=True):
-    """Order of calls follows ``main()`` of upside_config.py:1371-1671 for the README invocation."""
+                     rama_pot=None, membrane=None, membrane_thickness=30., compress=True, chain_first_residue=None,
+                     hbond_exclude_residues=(), split_bonded=False):
+    """Order of calls follows ``main()`` of upside_config.py:1371-1671 for the README invocation; ``chain_first_residue`` is
+    the content of its --chain-break-from-file."""
     w = ConfigWriter(fasta, pos, compress=compress)
+    excluded = set(int(x) for x in hbond_exclude_residues)
+    if chain_first_residue is not None:
+        excluded |= set(w.write_chain_break(chain_first_residue, split_bonded=split_bonded))
     w.write_dist_spring()
     w.write_angle_spring()
     w.write_dihedral_spring()
     w.write_rotamer_placement(sidechain_lib)
-    w.write_infer_H_O()
+    w.write_infer_H_O(excluded=excluded)
     w.write_count_hbond(hbond_energy, sidechain_lib)
     w.write_environment(environment_lib)
     w.write_rama_map_pot(synthetic_rama_pot(w.fasta) if rama_pot is None else rama_pot)

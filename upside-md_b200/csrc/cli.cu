@@ -248,8 +248,8 @@ int run(int argc, const char* const* argv, int verbose) {
     const int mc_interval = args.mc_interval > 0. ? std::max(1, int(args.mc_interval / (3 * dt))) : 0;   // main.cpp:409-411
     if (!args.log_level.empty() && args.log_level != "basic" && args.log_level != "detailed" && args.log_level != "extensive")
         throw string("Illegal value for --log-level");
-    // main.cpp:474-479.  The extensive-only loggers (placement_pos, virtual, environment_coverage) are not offered: with
-    // several placement nodes the reference itself cannot create them (duplicate dataset name).
+    // main.cpp:474-479.  extensive adds placement_pos, virtual and environment_coverage; with several placement nodes the
+    // reference cannot create its second placement_pos dataset, and the duplicate check below stops the run the same way.
     // an empty --log-level means detailed, as in the reference (main.cpp:475)
     const int log_level = args.log_level == "basic" ? 0 : (args.log_level == "extensive" ? 2 : 1);
 

@@ -658,6 +658,15 @@ struct InferHO : CoordNode {
         if (!n_elem) return;
         k_infer_ho_deriv<<<grid_for(n_elem, engine->n_rep), TPB, 0, s>>>(pos.output, pos.sens, sens, prm.p, n_elem, pos.n_elem);
     }
+    void add_loggers(int level, std::vector<NodeLogger>& out) override {   // hbond.cpp:48-56 (extensive only): site positions
+        if (level < 2) return;
+        out.push_back({"virtual", {(uint64_t)n_elem, 3}, false, [this](int r) {
+            auto o = host_rows(output, r);
+            std::vector<float> v(size_t(n_elem) * 3);
+            for (int i = 0; i < n_elem; ++i) for (int d = 0; d < 3; ++d) v[size_t(i) * 3 + d] = o[size_t(i) * wp + d];
+            return v;
+        }});
+    }
 };
 RegisterNodeType<InferHO, 1> infer_node("infer_H_O");
 
@@ -849,6 +858,17 @@ template <bool RAMA> struct PlacementNode : CoordNode {
             alignment.output, alignment.sens, RAMA ? rama->output : nullptr, RAMA ? rama->sens : nullptr, output, sens,
             rama_deriv.p, nullptr, affine_residue.p, rama_residue.p, layer.p, sig, n_elem, wp, alignment.n_elem,
             RAMA ? rama->n_elem : 0, nx, ny);
+    }
+    // placement.cpp:254-261 (extensive only).  The reference names the dataset "placement_pos" for every placement node, so a
+    // configuration with several of them fails there when the second dataset is created; the CLI reports the same clash.
+    void add_loggers(int level, std::vector<NodeLogger>& out) override {
+        if (level < 2) return;
+        out.push_back({"placement_pos", {(uint64_t)n_elem, (uint64_t)sig.n_dim}, false, [this](int r) {
+            auto o = host_rows(output, r);
+            std::vector<float> v(size_t(n_elem) * sig.n_dim);
+            for (int i = 0; i < n_elem; ++i) for (int d = 0; d < sig.n_dim; ++d) v[size_t(i) * sig.n_dim + d] = o[size_t(i) * wp + d];
+            return v;
+        }});
     }
     std::vector<float> get_param() const override { return h_data; }
     // placement.cpp:138-161: sensitivity of every element rotated back into the reference frame, summed per layer

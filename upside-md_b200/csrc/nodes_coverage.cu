@@ -228,6 +228,15 @@ struct EnvironmentCoverage : CoordNode {
     bool get_pairlist(int replica, std::vector<int>& i1, std::vector<int>& i2) override { return ig.pairlist(replica, i1, i2); }
     std::vector<float> get_param() const override { return ig.h_param; }
     void set_param(const std::vector<float>& p) override { ig.set_param(p); }   // a cutoff change needs a new engine
+    void add_loggers(int level, std::vector<NodeLogger>& out) override {   // environment.cpp:77-82 (extensive only)
+        if (level < 2) return;
+        out.push_back({"environment_coverage", {(uint64_t)n_elem}, false, [this](int r) {
+            auto o = host_rows(output, r);
+            std::vector<float> v(n_elem);
+            for (int i = 0; i < n_elem; ++i) v[i] = o[size_t(i) * wp];
+            return v;
+        }});
+    }
     // the reference leaves this derivative unimplemented and returns zeros (environment.cpp:62-65)
     std::vector<float> get_param_deriv(int) override { return std::vector<float>(ig.h_param.size(), 0.f); }
 };
