@@ -155,6 +155,8 @@ Engine::~Engine() {
     for (auto e : ev_fwd) cudaEventDestroy(e);
     for (auto e : ev_bwd) cudaEventDestroy(e);
     if (ev_start) cudaEventDestroy(ev_start);
+    if (ev_zeroed) cudaEventDestroy(ev_zeroed);
+    if (zero_stream) cudaStreamDestroy(zero_stream);
     if (stream) cudaStreamDestroy(stream);
 }
 
@@ -227,15 +229,15 @@ void Engine::enqueue_compute(cudaStream_t s, ComputeMode mode) {
     // The reference zeroes each CoordNode's sens right after its forward pass and lets PotentialNodes add into
     // their parents' sens during compute_value (deriv_engine.cpp:143-151).  Zeroing everything first and running
     // forward in construction (topological) order, then backward in reverse order, is equivalent.
-    UB_CUDA(cudaMemsetAsync(sens_arena.p, 0, sens_arena.n * sizeof(float), s));
-    // every mode: nodes that report their potential in DerivMode too (tension, AFM) add into a zeroed slot, so the slot holds
-    // the last evaluation's value as in the reference, not a running sum
-    UB_CUDA(cudaMemsetAsync(pot_arena.p, 0, pot_arena.n * sizeof(float), s));
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     UB_CUDA(cudaStreamIsCapturing(s, &cap));
     if (use_dag && cap == cudaStreamCaptureStatusActive) {
-        enqueue_compute_dag(s, mode);
+        enqueue_compute_dag(s, mode);   // (zeroes the arenas on a branch of its own)
     } else {
+        UB_CUDA(cudaMemsetAsync(sens_arena.p, 0, sens_arena.n * sizeof(float), s));
+        // every mode: nodes that report their potential in DerivMode too (tension, AFM) add into a zeroed slot, so the slot
+        // holds the last evaluation's value as in the reference, not a running sum
+        UB_CUDA(cudaMemsetAsync(pot_arena.p, 0, pot_arena.n * sizeof(float), s));
         for (auto& n : nodes) { n.computation->compute_value(s, mode); mark(s, n.name + ":fwd"); }
         for (size_t i = nodes.size(); i-- > 0;)
             if (!nodes[i].computation->potential_term) { nodes[i].computation->propagate_deriv(s); mark(s, nodes[i].name + ":bwd"); }
@@ -263,8 +265,17 @@ void Engine::enqueue_compute_dag(cudaStream_t s, ComputeMode mode) {
             UB_CUDA(cudaEventCreateWithFlags(&ev_bwd[i], cudaEventDisableTiming));
         }
         if (!ev_start) UB_CUDA(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
+        if (!ev_zeroed) UB_CUDA(cudaEventCreateWithFlags(&ev_zeroed, cudaEventDisableTiming));
+        if (!zero_stream) UB_CUDA(cudaStreamCreateWithFlags(&zero_stream, cudaStreamNonBlocking));
     }
-    UB_CUDA(cudaEventRecord(ev_start, s));   // after the memsets
+    UB_CUDA(cudaEventRecord(ev_start, s));
+    // The sens and potential arenas (56 KB per replica in ff_1) are zeroed on a branch of their own: only the kernels that ADD
+    // into them wait for it - the forward pass of a PotentialNode and every backward pass - so the forward kernels of the
+    // coordinate nodes start at once instead of behind a 230 MB memset (B = 4096).
+    UB_CUDA(cudaStreamWaitEvent(zero_stream, ev_start, 0));
+    UB_CUDA(cudaMemsetAsync(sens_arena.p, 0, sens_arena.n * sizeof(float), zero_stream));
+    UB_CUDA(cudaMemsetAsync(pot_arena.p, 0, pot_arena.n * sizeof(float), zero_stream));
+    UB_CUDA(cudaEventRecord(ev_zeroed, zero_stream));
     std::vector<cudaEvent_t> last_writer(N, nullptr);   // last kernel set that added into sens of node i
     std::vector<cudaEvent_t> last_event(N, nullptr);    // last thing recorded on node i's stream (for the final join)
     for (size_t i = 0; i < N; ++i) {
@@ -273,6 +284,7 @@ void Engine::enqueue_compute_dag(cudaStream_t s, ComputeMode mode) {
         UB_CUDA(cudaStreamWaitEvent(st, ev_start, 0));
         for (size_t p : nd.parents) if (p) UB_CUDA(cudaStreamWaitEvent(st, ev_fwd[p], 0));
         const bool pot = nd.computation->potential_term;
+        if (pot) UB_CUDA(cudaStreamWaitEvent(st, ev_zeroed, 0));
         if (pot) for (size_t p : nd.parents) if (last_writer[p]) UB_CUDA(cudaStreamWaitEvent(st, last_writer[p], 0));
         nd.computation->compute_value(st, mode);
         UB_CUDA(cudaEventRecord(ev_fwd[i], st));
@@ -283,6 +295,7 @@ void Engine::enqueue_compute_dag(cudaStream_t s, ComputeMode mode) {
         auto& nd = nodes[i];
         if (nd.computation->potential_term) continue;
         cudaStream_t st = node_stream[i];
+        UB_CUDA(cudaStreamWaitEvent(st, ev_zeroed, 0));
         for (size_t c : nd.children) UB_CUDA(cudaStreamWaitEvent(st, nodes[c].computation->potential_term ? ev_fwd[c] : ev_bwd[c], 0));
         for (size_t p : nd.parents) if (last_writer[p]) UB_CUDA(cudaStreamWaitEvent(st, last_writer[p], 0));
         nd.computation->propagate_deriv(st);
@@ -291,6 +304,7 @@ void Engine::enqueue_compute_dag(cudaStream_t s, ComputeMode mode) {
         for (size_t p : nd.parents) last_writer[p] = ev_bwd[i];
     }
     for (size_t i = 0; i < N; ++i) UB_CUDA(cudaStreamWaitEvent(s, last_event[i], 0));
+    UB_CUDA(cudaStreamWaitEvent(s, ev_zeroed, 0));
 }
 
 void Engine::compute(ComputeMode mode) {

@@ -226,7 +226,8 @@ struct Engine {
     bool use_dag = true;
     std::vector<cudaStream_t> node_stream;
     std::vector<cudaEvent_t> ev_fwd, ev_bwd;
-    cudaEvent_t ev_start = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_zeroed = nullptr;
+    cudaStream_t zero_stream = nullptr;   // branch of the evaluation graph that zeroes the sens / potential arenas
 
     // Live timing of one evaluation kernel group by kernel group (CUDA events on the engine's stream, linear order, no graph):
     // while `profiling` is set, mark(s, label) records an event; the engine marks every node's forward / backward, nodes
