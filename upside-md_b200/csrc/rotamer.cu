@@ -1380,7 +1380,11 @@ __device__ __forceinline__ float bp2_node(int A, const float* __restrict__ prob,
     return dev;
 }
 
-__global__ void __launch_bounds__(BP2_TPB, BP2_OCC) k_rot_bp2(RotamerDev P, Bp2Lay L, int want_pot) {
+// TPB / OCC: 384 threads x 3 CTAs per SM where the pair capacity of a replica fits a third of the shared memory (100 residues);
+// larger systems get 512 x 2 or 1024 x 1, so that a CTA that has the SM to itself still fills it with warps
+template <int TPB, int OCC>
+__global__ void __launch_bounds__(TPB, OCC) k_rot_bp2(RotamerDev P, Bp2Lay L, int want_pot) {
+    constexpr int BP2_TPB = TPB;   // (shadows the default block size)
     extern __shared__ float smem[];
     const int r = blockIdx.x, tid = threadIdx.x;
     const int nR = P.n_res, nRp = L.nRp, SP = L.SP;
@@ -1711,6 +1715,7 @@ struct RotamerSidechain : PotentialNode {
     float damping, tol;
     int max_iter, chunk;
     size_t smem_prep = 0, smem_edge = 0, smem_bp = 0, smem_bp2 = 0, smem_build = 0;
+    int bp2_occ = BP2_OCC;   // CTAs per SM the fast BP kernel was planned for (picks its block size)
     bool fast_build = false;   // k_rot_build instead of Verlet cache + k_refine + k_rot_prep
     BuildLay blay{0, 0, 0, 0, nullptr, nullptr};
     DevBuf<unsigned long long> build_spill;
@@ -1926,7 +1931,11 @@ struct RotamerSidechain : PotentialNode {
             L.Pcap = 27 * L.SP;
             lay2 = L;
             smem_bp2 = bp2_bytes(n_res, L);
-            UB_CUDA(cudaFuncSetAttribute(k_rot_bp2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bp2));
+            bp2_occ = occ;
+            if (const char* e = getenv("UPSIDE_B200_BP2_SMALL_BLOCKS")) if (atoi(e)) bp2_occ = BP2_OCC;   // 384 threads whatever the occupancy
+            if (bp2_occ >= BP2_OCC) UB_CUDA(cudaFuncSetAttribute(k_rot_bp2<BP2_TPB, BP2_OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bp2));
+            else if (bp2_occ == 2) UB_CUDA(cudaFuncSetAttribute(k_rot_bp2<512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bp2));
+            else UB_CUDA(cudaFuncSetAttribute(k_rot_bp2<1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bp2));
             fast_bp = true;
             return;
         }
@@ -1981,7 +1990,9 @@ struct RotamerSidechain : PotentialNode {
         else k_rot_energy<0, 0><<<dim3(edge_split, persist), edge_tpb * edge_G, smem_edge, s>>>(P, want, engine->n_rep, edge_tpb);
         engine->mark(s, "rotamer/energy");
         if (fast_bp) {
-            k_rot_bp2<<<engine->n_rep, BP2_TPB, smem_bp2, s>>>(P, lay2, want);
+            if (bp2_occ >= BP2_OCC) k_rot_bp2<BP2_TPB, BP2_OCC><<<engine->n_rep, BP2_TPB, smem_bp2, s>>>(P, lay2, want);
+            else if (bp2_occ == 2) k_rot_bp2<512, 2><<<engine->n_rep, 512, smem_bp2, s>>>(P, lay2, want);
+            else k_rot_bp2<1024, 1><<<engine->n_rep, 1024, smem_bp2, s>>>(P, lay2, want);
             k_rot_bp<<<std::min(engine->n_rep, 148), BP_TPB, smem_bp, s>>>(P, want, 1);   // replicas the fast path declined
         } else {
             k_rot_bp<<<engine->n_rep, BP_TPB, smem_bp, s>>>(P, want, 0);
