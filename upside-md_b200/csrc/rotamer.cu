@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(PREP_TPB) k_rot_prep(RotamerDev P) {
 //      thread per bead walks its residue's adjacency row and reads its partners off the masks: the CSR rows, codes, pair
 //      slots and incidence lists come out exactly as k_rot_prep writes them, so the consumers are unchanged.
 // Nothing is read from or written to global memory between the bead positions and the CSR rows.
-constexpr int BUILD_TPB = 256;
+constexpr int BUILD_TPB_SMALL = 256, BUILD_TPB_LARGE = 1024;
 // capacities of the shared-memory arrays (sphere-test survivors, active residue pairs); what does not fit spills to a
 // per-replica global scratch area (clashing start structures have several times the pairs of a relaxed chain) up to
 // capc_tot / capa_tot, beyond which the error flag is raised
@@ -367,7 +367,7 @@ __host__ __device__ inline size_t build_spill_words(const BuildLay& L) {   // 64
 }
 
 // returns false (uniformly, nothing written) if SPILL is off and the shared-memory capacities do not hold this replica
-template <bool SPILL>
+template <bool SPILL, int BUILD_TPB>
 __device__ __forceinline__ bool rot_build_body(const RotamerDev& P, const BuildLay& L, unsigned long long* smem_ull) {
     const int r = blockIdx.x, tid = threadIdx.x;
     const int nR = P.n_res, nW = P.n_words, nb = P.n_bead;
@@ -715,11 +715,15 @@ __device__ __forceinline__ bool rot_build_body(const RotamerDev& P, const BuildL
 
 // the shared-memory-only body first; a replica that overflows its capacities (clashing start structures) is redone by the
 // body whose arrays continue in global memory
-__global__ void __launch_bounds__(BUILD_TPB, 4) k_rot_build(RotamerDev P, BuildLay L) {
+// BUILD_TPB x OCC: 256 threads and four CTAs per SM for the shared-memory plan of ~100 residues; a large system, whose plan
+// leaves room for one or two CTAs per SM, gets 1024 threads so that its 45 k sphere tests and 10 k entries do not queue
+// behind eight warps
+template <int BUILD_TPB, int OCC>
+__global__ void __launch_bounds__(BUILD_TPB, OCC) k_rot_build(RotamerDev P, BuildLay L) {
     extern __shared__ unsigned long long smem_ull[];
-    if (rot_build_body<false>(P, L, smem_ull)) return;
+    if (rot_build_body<false, BUILD_TPB>(P, L, smem_ull)) return;
     __syncthreads();
-    rot_build_body<true>(P, L, smem_ull);
+    rot_build_body<true, BUILD_TPB>(P, L, smem_ull);
 }
 
 // ================================================================================================ edge kernels
@@ -1717,6 +1721,7 @@ struct RotamerSidechain : PotentialNode {
     size_t smem_prep = 0, smem_edge = 0, smem_bp = 0, smem_bp2 = 0, smem_build = 0;
     int bp2_occ = BP2_OCC;   // CTAs per SM the fast BP kernel was planned for (picks its block size)
     bool fast_build = false;   // k_rot_build instead of Verlet cache + k_refine + k_rot_prep
+    bool build_large = false;  // ... with 1024-thread CTAs (large systems)
     BuildLay blay{0, 0, 0, 0, nullptr, nullptr};
     DevBuf<unsigned long long> build_spill;
     DevBuf<int> build_stats;
@@ -1871,7 +1876,10 @@ struct RotamerSidechain : PotentialNode {
         if (smem_prep > (size_t)device_smem || smem_edge > (size_t)device_smem || fixed_bp > (size_t)device_smem)
             throw std::string("rotamer node: system too large for the shared-memory kernels");
         UB_CUDA(cudaFuncSetAttribute(k_rot_prep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_prep));
-        if (fast_build) UB_CUDA(cudaFuncSetAttribute(k_rot_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_build));
+        // block size of the build kernel: many warps per CTA once fewer than three CTAs fit an SM
+        build_large = fast_build && smem_build * 3 > (size_t)device_smem && !getenv("UPSIDE_B200_BUILD_SMALL_BLOCKS");
+        if (fast_build && build_large) UB_CUDA(cudaFuncSetAttribute(k_rot_build<BUILD_TPB_LARGE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_build));
+        else if (fast_build) UB_CUDA(cudaFuncSetAttribute(k_rot_build<BUILD_TPB_SMALL, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_build));
         UB_CUDA(cudaFuncSetAttribute(k_rot_energy<15, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_edge));
         UB_CUDA(cudaFuncSetAttribute(k_rot_deriv<15, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_edge));
         UB_CUDA(cudaFuncSetAttribute(k_rot_energy<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_edge));
@@ -1977,7 +1985,8 @@ struct RotamerSidechain : PotentialNode {
         // edge kernels: persistent CTAs (as many as stay resident) striding over the replicas, edge_G replicas at a time
         int persist = std::min((engine->n_rep + edge_G - 1) / edge_G, 148 * EDGE_OCC);
         if (fast_build) {
-            k_rot_build<<<engine->n_rep, BUILD_TPB, smem_build, s>>>(P, blay);
+            if (build_large) k_rot_build<BUILD_TPB_LARGE, 1><<<engine->n_rep, BUILD_TPB_LARGE, smem_build, s>>>(P, blay);
+            else k_rot_build<BUILD_TPB_SMALL, 4><<<engine->n_rep, BUILD_TPB_SMALL, smem_build, s>>>(P, blay);
             engine->mark(s, "rotamer/build");
         } else {
             ig.build(s);
