@@ -58,3 +58,15 @@ def test_bench_cli_surface():
     assert r.returncode == 0
     for flag in ('--gpus', '--steps', '--warmup', '--impl'):
         assert flag in r.stdout + r.stderr      # (bench.py keeps stdout for its one JSON line)
+
+
+def test_replica_sharding_covers_every_replica_once():
+    """config 3 is 4096 replicas IN TOTAL: rank r of N gets a contiguous block, blocks tile the range"""
+    sys.path.insert(0, parity.ROOT)
+    import bench
+    for total, world in ((4096, 1), (4096, 2), (4096, 8), (256, 8), (48, 8), (10, 4)):
+        seen = []
+        for rank in range(world):
+            first, n = bench._shard(total, world, rank)
+            seen.extend(range(first, first + n))
+        assert seen == list(range(total)), (total, world)
