@@ -77,3 +77,35 @@ def test_population_pass_fraction(cid):
     assert sweeps_equal >= 0.90 * len(pos) and sweeps_within_chunk >= 0.98 * len(pos), (sweeps_equal, sweeps_within_chunk)
     # about one bead pair in 1e5 lies within rounding of the cutoff: ~1 % of replicas at 100 residues, ~5 % at 300 (12 k pairs each)
     assert flips <= 0.10 * len(pos), flips
+
+
+@pytest.mark.skipif(not ref_engine.available('pinned'), reason='oracle/_ref not shipped')
+def test_outliers_of_the_bench_batch_match_the_reference():
+    """The bench batch itself (4096 random coils of config 3, 300 rounds): a dozen of its replicas sit in trapped, clashing
+    states with stretched bonds and energies of 10^3-10^4 (median ~10^2).  Those are where a rare-event defect of a kernel
+    would hide, so the ten highest-energy replicas go through the reference engine on the same coordinates: total energy,
+    every node potential and the forces must agree there as they do on relaxed structures."""
+    import bench
+    B = 4096
+    be = ue.BatchEngine(bench.CONFIG, B)
+    n_res = be.n_atom // 3
+    be.set_pos(bench.workload_positions(B, 0, n_res))
+    be.md_init_seeds(np.full(B, bench.TEMPERATURE, dtype='f4'), bench.SEED + np.arange(B), dt=bench.DT)
+    be.md_run(300)
+    en, dv = be.evaluate(want_deriv=True)
+    pos = be.get_pos()
+    assert np.isfinite(en).all() and np.isfinite(dv).all()
+    worst = np.argsort(en)[::-1][:10]
+    node_pot = {name: be.node_potential(name) for name, is_pot in be.node_names() if is_pot}
+    ref = ref_engine.RefEngine(bench.CONFIG, be.n_atom)
+    for w in worst:
+        e_ref = ref.energy(pos[w])
+        d_ref = ref.deriv(pos[w])
+        assert abs(en[w] - e_ref) <= E_RTOL * max(1.0, abs(e_ref)), (int(w), float(en[w]), e_ref)
+        assert np.abs(dv[w] - d_ref).max() <= F_RTOL * max(1.0, np.abs(d_ref).max()), (int(w), float(np.abs(dv[w] - d_ref).max()))
+        for name, v in node_pot.items():
+            r = ref.node_potential(name)
+            assert abs(v[w] - r) <= 5e-3 + E_RTOL * abs(r), (int(w), name, float(v[w]), r)
+    assert en[worst[0]] > 10 * np.median(en)          # the sample does contain outliers
+    ref.close()
+    be.close()
